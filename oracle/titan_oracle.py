@@ -517,12 +517,12 @@ def uniroot(f, lower, upper, tol=1e-15, maxiter=1000):
     raises when the end points are NA or do not bracket (the reference's tryCatch then keeps the
     previous iterate, R/paramEstimation.R:134-139)."""
     big = float(np.finfo(np.float64).max)
-    fl, fu = f(lower), f(upper)
+    fl, fu = float(f(lower)), float(f(upper))
     if math.isnan(fl) or math.isnan(fu):
         raise RootError("f.lower/f.upper is NA")
     fl = max(min(fl, big), -big)
     fu = max(min(fu, big), -big)
-    sgn = lambda v: (v > 0) - (v < 0)
+    sgn = lambda v: int(v > 0) - int(v < 0)
     if not (sgn(fl) * sgn(fu) <= 0):
         raise RootError("f() values at end points not of opposite sign")
 

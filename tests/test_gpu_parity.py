@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): Viterbi paths bit-exact; per-chromosome log-likelihood
+within 1e-9 relative; posteriors and converged EM parameters within 1e-6.  The asserts below are
+tighter than required wherever the implementation allows.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import titancna_b200 as T
+from oracle import titan_oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9      # north_star: per-chromosome log-likelihood, relative
+POST_ATOL = 1e-6    # north_star: posteriors / parameters, absolute
+
+
+def _fixture(golden, col=2):
+    g = {k[2:]: golden[k] for k in golden if k.startswith("g_")}
+    muR, muC = O.clonal_two_component_mixture(g["rt"], float(g["rn"][0]), golden["cp_n"][col], golden["cp_s"][:, col],
+                                              g["ct"], golden["cp_phi"][col])
+    py = O.compute_py_c(golden["data_ref"], golden["data_tumDepth"], golden["data_logR"], muR, muC,
+                        golden["cp_var"][:, col])
+    lp = np.log(np.outer(golden["cp_piG"][:, col], golden["cp_piZ"][:, col]).reshape(-1, order="F"))
+    return g, py, lp
+
+
+def test_library_loaded_and_device_present():
+    assert T.device_count() >= 1
+    assert b"sm_100a" in T.lib().titan_version()
+
+
+def test_legacy_fwd_back_reproduces_reference_fixture(golden):
+    """.Call-compatible entry on data/EMresults.rda: stored rhoG/rhoZ are the known answer."""
+    g, py, lp = _fixture(golden)
+    txn = float(golden["cp_txnExpLen"][0])
+    zst = float(golden["cp_txnZstrength"][0]) * txn
+    out = T.fwd_back_clonalCN(lp, py, g["ct"], g["ZS"], 2, golden["data_posn"].astype(float), zst, txn, 0)
+    r = np.exp(out["rho"]).reshape((12, 2, -1), order="F")
+    assert np.abs(r.sum(1) - golden["cp_rhoG"]).max() < 1e-9
+    assert np.abs(r.sum(0) - golden["cp_rhoZ"]).max() < 1e-9
+    ref_ll = float(golden["ref_loglik"][0])
+    assert abs(out["loglik"] - ref_ll) <= 1e-11 * abs(ref_ll)
+    # production transition settings on the same data, against the reference's own C
+    out2 = T.fwd_back_clonalCN(lp, py, g["ct"], g["ZS"], 2, golden["data_posn"].astype(float), 1e15, 1e15, 0)
+    ref_ll2 = float(golden["ref_loglik_1e15"][0])
+    assert abs(out2["loglik"] - ref_ll2) <= 1e-11 * abs(ref_ll2)
+
+
+def test_legacy_viterbi_bit_exact_on_fixture(golden):
+    g, py, lp = _fixture(golden)
+    txn = float(golden["cp_txnExpLen"][0])
+    zst = float(golden["cp_txnZstrength"][0]) * txn
+    posn = golden["data_posn"].astype(float)
+    path = T.viterbi_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, zst, txn, 0)
+    assert np.array_equal(path, golden["ref_path"].astype(np.int32))
+    path2 = T.viterbi_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, 1e15, 1e15, 0)
+    assert np.array_equal(path2, golden["ref_path_1e15"].astype(np.int32))
+
+
+def _oracle_estep(data, p, n, s, phi, var, piG, piZ, txn, zfac):
+    g = p["genotypeParams"]
+    Z = len(s)
+    muR, muC = O.clonal_two_component_mixture(g["rt"], g["rn"], n, s, g["ct"], phi)
+    py = O.compute_py_c(data["ref"], data["tumDepth"], data["logR"], muR, muC, var)
+    chrsI = O.chromosome_slices(data["chr"])
+    es = O.e_step(data, chrsI, py, piG, piZ, g["ZS"], g["ct"], Z, txn, zfac, engine="port", threads=8)
+    es["stats"] = O.sufficient_statistics(data["ref"], data["tumDepth"], data["logR"], es["rho"])
+    es["py"], es["chrsI"] = py, chrsI
+    return es
+
+
+CASES = [
+    # N, Z, maxCN, n_chr, txnExpLen, txnZstrength, chunk_len, warm
+    (6000, 3, 8, 3, 1e15, 1.0, 512, 160),      # production transition settings, K=75
+    (6000, 3, 8, 3, 1e15, 1.0, 0, 1),          # plain sequential recursion
+    (5000, 1, 8, 2, 1e15, 5e5, 256, 64),       # vignette zStrength: 1-rhoZ == 0 exactly at short range
+    (4000, 5, 8, 2, 1e9, 1e9, 300, 100),       # K=125, man-page settings
+    (3000, 2, 5, 4, 1e5, 1.0, 128, 32),        # short txnExpLen: non-sticky transitions
+    (3000, 4, 3, 1, 1e15, 1.0, 64, 16),        # smallest genotype table (U=6)
+]
+
+
+@pytest.mark.parametrize("N,Z,maxCN,n_chr,txn,zfac,chunk,warm", CASES)
+def test_fused_estep_matches_oracle(N, Z, maxCN, n_chr, txn, zfac, chunk, warm):
+    data, truth = synth.make_data(N, Z=Z, maxCN=maxCN, n_chr=n_chr, seed=11 + Z, mean_seg=300)
+    p = T.loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    n, phi, s = 0.35, 2.1, np.array(synth.S_TRUE[:Z]) * 0.9 + 0.02
+    var = g["var_0"] * np.linspace(0.5, 1.5, g["var_0"].size)
+    es = _oracle_estep(data, p, n, s, phi, var, g["piG_0"], sP["piZ_0"], txn, zfac)
+    sol = T.Solver(data, g, Z, txn, zfac)
+    sol.configure(chunk, warm, 1e-10)
+    out = sol.estep(n, s, phi, var, g["piG_0"], sP["piZ_0"], g, posteriors=True)
+    tm = sol.timing()
+    sol.close()
+    assert np.allclose(out["loglik_chr"], es["loglik_chr"], rtol=LL_RTOL, atol=0)
+    assert np.abs(out["loglik_chr"] - es["loglik_chr"]).max() <= 1e-11 * np.abs(es["loglik_chr"]).max()
+    assert np.abs(out["rhoG"] - es["rhoG"]).max() < 1e-9 and np.abs(out["rhoG"] - es["rhoG"]).max() < POST_ATOL
+    assert np.abs(out["rhoZ"] - es["rhoZ"]).max() < 1e-9
+    chr0 = np.array([ix[0] for ix in es["chrsI"]])
+    assert np.abs(out["rhoG0"] - es["rhoG"][:, chr0]).max() < 1e-9
+    assert np.abs(out["rhoZ0"] - es["rhoZ"][:, chr0]).max() < 1e-9
+    for k in "abcdeg":
+        ref = es["stats"][k]
+        assert np.abs(out["stats"][k] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), k
+    assert tm["n_chunks"] >= n_chr
+
+
+@pytest.mark.parametrize("N,Z,maxCN,n_chr,txn,zfac", [
+    (6000, 3, 8, 3, 1e15, 1.0), (5000, 1, 8, 2, 1e15, 5e5), (4000, 5, 8, 2, 1e9, 1e9), (3000, 2, 5, 4, 1e5, 1.0),
+    (2000, 8, 4, 2, 1e15, 1.0)])
+def test_fused_viterbi_bit_exact(N, Z, maxCN, n_chr, txn, zfac):
+    """Systematic near-ties included: with hetBaselineSkew = 0 the diploid-HET states of different
+    clusters have identical emissions."""
+    data, truth = synth.make_data(N, Z=Z, maxCN=maxCN, n_chr=n_chr, seed=5 + Z, mean_seg=250)
+    for skew in (None, 0.0):
+        p = T.loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z, hetBaselineSkew=skew)
+        g, sP = p["genotypeParams"], p["cellPrevParams"]
+        n, phi = 0.3, 2.0
+        s = np.array((synth.S_TRUE + (0.9, 0.93, 0.96))[:Z]) * 0.95 + 0.01
+        muR, muC = O.clonal_two_component_mixture(g["rt"], g["rn"], n, s, g["ct"], phi)
+        py = O.compute_py_c(data["ref"], data["tumDepth"], data["logR"], muR, muC, g["var_0"])
+        lp = np.vectorize(math.log)(np.outer(g["piG_0"], sP["piZ_0"]).reshape(-1, order="F"))
+        want = np.empty(N, dtype=np.int32)
+        for idx in O.chromosome_slices(data["chr"]):
+            want[idx] = O.viterbi(lp, py[:, idx], g["ZS"], Z, data["posn"][idx], zfac * txn, txn, engine="port")
+        sol = T.Solver(data, g, Z, txn, zfac)
+        got = sol.viterbi(n, s, phi, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+        sol.close()
+        assert np.array_equal(got, want), f"first mismatch at {np.flatnonzero(got != want)[:5]}"
+
+
+def test_em_matches_oracle_on_reference_fixture_data(golden):
+    """Full runEMclonalCN + viterbiClonalCN on the chr2 fixture with the man-page settings
+    (man/TitanCNA-package.Rd:48-76): converged parameters within 1e-6, same iteration count,
+    identical Viterbi calls."""
+    data = {"chr": golden["data_chr"], "posn": golden["data_posn"].astype(float), "ref": golden["data_ref"].astype(float),
+            "tumDepth": golden["data_tumDepth"].astype(float), "logR": golden["data_logR"]}
+    kw = dict(txnExpLen=1e9, txnZstrength=1e9, maxiter=3, maxiterUpdate=500)
+    po = O.load_default_parameters(5, 2, skew=0.1)
+    po["genotypeParams"]["alphaKHyper"][:] = 500
+    po["ploidyParams"]["phi_0"] = 1.5
+    want = O.run_em_clonal_cn(data, po, engine="port", **kw)
+    pg = T.loadDefaultParameters(copyNumber=5, numberClonalClusters=2, skew=0.1)
+    pg["genotypeParams"]["alphaKHyper"][:] = 500
+    pg["ploidyParams"]["phi_0"] = 1.5
+    got = T.runEMclonalCN(data, pg, verbose=False, **kw)
+    assert got["n"].shape == want["n"].shape
+    assert list(got["cd_sweeps"][1:]) == want["cd_sweeps"]
+    for k in ("n", "phi", "s", "var", "piG", "piZ", "muR", "muC"):
+        assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < POST_ATOL, k
+    assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=LL_RTOL, atol=0)
+    assert np.abs(got["rhoG"] - want["rhoG"]).max() < POST_ATOL
+    assert np.abs(got["rhoZ"] - want["rhoZ"]).max() < POST_ATOL
+    wp = O.viterbi_clonal_cn(data, want, engine="port")
+    gp = T.viterbiClonalCN(data, got)
+    assert np.array_equal(gp, wp)
+
+
+def test_em_production_settings_synthetic():
+    """scripts/R_scripts/titanCNA.R:243-256 settings on a sub-sampled synthetic genome."""
+    N, Z = 12000, 2
+    data, truth = synth.make_data(N, Z=Z, maxCN=8, n_chr=4, seed=99, mean_seg=400)
+    kw = dict(txnExpLen=1e15, txnZstrength=1.0, maxiter=4, maxiterUpdate=1500)
+
+    def params(mod):
+        p = mod(8, Z, data=data)
+        p["genotypeParams"]["alphaKHyper"][:] = 10000
+        p["genotypeParams"]["betaKHyper"][:] = 25
+        p["ploidyParams"]["phi_0"] = 2.0
+        p["normalParams"]["n_0"] = 0.5
+        return p
+
+    want = O.run_em_clonal_cn(data, params(O.load_default_parameters), engine="port", threads=8, **kw)
+    got = T.runEMclonalCN(data, params(T.loadDefaultParameters), verbose=False, **kw)
+    assert got["n"].shape == want["n"].shape
+    for k in ("n", "phi", "s", "var"):
+        assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < POST_ATOL, k
+    assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=LL_RTOL, atol=0)
+    assert np.array_equal(T.viterbiClonalCN(data, got), O.viterbi_clonal_cn(data, want, engine="port", threads=8))
+
+
+def test_chunked_scan_equals_sequential_recursion_at_scale():
+    """Size-independent property at a size the O(N K^2) oracle cannot reach: the chunk-parallel scan
+    and the plain sequential recursion are the same function."""
+    N, Z = 400000, 3
+    data, truth = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=20261020)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=Z)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    sol = T.Solver(data, g, Z, 1e15, 1.0)
+    args = (0.5, sP["s_0"], 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    sol.configure(0, 1, 1e-10)
+    seq = sol.estep(*args, posteriors=True)
+    sol.configure(512, 160, 1e-10)
+    par = sol.estep(*args, posteriors=True)
+    tm = sol.timing()
+    sol.close()
+    assert tm["n_chunks"] > 23 and tm["last_fwd_rounds"] >= 2
+    assert np.allclose(par["loglik_chr"], seq["loglik_chr"], rtol=1e-12, atol=0)
+    assert np.abs(par["rhoG"] - seq["rhoG"]).max() < 1e-8
+    assert np.abs(par["rhoZ"] - seq["rhoZ"]).max() < 1e-8
+    for k in "abcdeg":
+        assert np.allclose(par["stats"][k], seq["stats"][k], rtol=1e-9, atol=1e-7), k
+    # posterior marginals are distributions; the e statistic counts every SNP once
+    assert np.abs(par["rhoG"].sum(0) - 1).max() < 1e-12
+    assert np.abs(par["rhoZ"].sum(0) - 1).max() < 1e-12
+    assert abs(par["stats"]["e"].sum() - N) < 1e-6
+    assert abs(par["stats"]["a"].sum() - data["ref"].sum()) < 1e-6 * data["ref"].sum()
+
+
+def test_edge_cases_and_errors():
+    # chromosomes of length 1 and 2 next to a normal one
+    data, _ = synth.make_data(600, Z=2, maxCN=5, n_chr=3, seed=3, mean_seg=100)
+    keep = np.r_[0:1, np.flatnonzero(data["chr"] == 2)[:2], np.flatnonzero(data["chr"] == 3)]
+    data = {k: v[keep] for k, v in data.items()}
+    p = T.loadDefaultParameters(copyNumber=5, numberClonalClusters=2)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    es = _oracle_estep(data, p, 0.4, sP["s_0"], 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], 1e15, 1.0)
+    sol = T.Solver(data, g, 2, 1e15, 1.0)
+    sol.configure(50, 10, 1e-10)
+    out = sol.estep(0.4, sP["s_0"], 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], g, posteriors=True)
+    path = sol.viterbi(0.4, sP["s_0"], 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    sol.close()
+    assert np.allclose(out["loglik_chr"], es["loglik_chr"], rtol=LL_RTOL, atol=0)
+    assert np.abs(out["rhoG"] - es["rhoG"]).max() < 1e-9
+    lp = np.vectorize(math.log)(np.outer(g["piG_0"], sP["piZ_0"]).reshape(-1, order="F"))
+    want = np.concatenate([O.viterbi(lp, es["py"][:, ix], g["ZS"], 2, data["posn"][ix], 1e15, 1e15) for ix in es["chrsI"]])
+    assert np.array_equal(path, want)
+    # error behaviour mirrors the reference's error() text / refuses what it does not cover
+    with pytest.raises(T.TitanError, match="obslik must be"):
+        T.fwd_back_clonalCN(np.zeros(4), np.zeros((3, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15)
+    with pytest.raises(T.TitanError, match="useOutlier"):
+        T.fwd_back_clonalCN(np.zeros(5), np.zeros((5, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15, 1)
+    with pytest.raises(T.TitanError, match="positive"):
+        T.Solver(data, g, 2, 0.0, 1.0)

@@ -1,0 +1,136 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import titancna_b200 as T
+from titancna_b200 import _lib, build as B
+from oracle import titan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    B.build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "titancna_b200.h")).read()
+    declared = set(re.findall(r"\b(titan_[a-z_A-Z0-9]+)\s*\(", hdr))
+    declared -= {"titan_solver"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_compute_fails_loudly_without_a_device():
+    if T.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(T.TitanError) as ei:
+        T.fwd_back_clonalCN(np.zeros(4), np.zeros((4, 3)), np.zeros(2), np.array([0.0, -1.0]), 2, np.arange(3.0), 1e15, 1e15)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+    p = T.loadDefaultParameters(5, 2)
+    data = {"chr": np.ones(4), "posn": np.arange(4.0), "ref": np.full(4, 9.0), "tumDepth": np.full(4, 12.0), "logR": np.zeros(4)}
+    with pytest.raises(T.TitanError):
+        T.runEMclonalCN(data, p, verbose=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "titancna_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".c", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "titan_port" not in src and "libtitanref" not in src, f
+
+
+@pytest.mark.parametrize("cn", [3, 4, 5, 6, 7, 8])
+def test_load_default_parameters_matches_oracle_restatement(cn):
+    rng = np.random.default_rng(cn)
+    data = {"ref": rng.integers(10, 40, 200).astype(float), "tumDepth": np.full(200, 45.0), "logR": rng.normal(0, 0.2, 200)}
+    for kw in (dict(), dict(skew=0.1), dict(hetBaselineSkew=0.0), dict(data=data)):
+        a = T.loadDefaultParameters(copyNumber=cn, numberClonalClusters=3, **kw)
+        b = O.load_default_parameters(cn, 3, **kw)
+        for grp in a:
+            for k, v in a[grp].items():
+                if isinstance(v, np.ndarray):
+                    assert np.array_equal(v, b[grp][k]), (grp, k)
+                elif isinstance(v, float):
+                    assert v == pytest.approx(b[grp][k], rel=1e-15), (grp, k)
+    assert {6: 16, 3: 6, 4: 9, 5: 12, 7: 20, 8: 25}[cn] == a["genotypeParams"]["rt"].size
+
+
+def test_load_default_parameters_errors():
+    with pytest.raises(ValueError, match="Fewer than 3 or more than 8"):
+        T.loadDefaultParameters(copyNumber=9)
+    with pytest.raises(ValueError, match="alleleEmissionModel"):
+        T.loadDefaultParameters(alleleEmissionModel="poisson")
+
+
+def test_chromosome_offsets():
+    assert T.chromosome_offsets(np.array([1, 1, 2, 2, 2, 5])).tolist() == [0, 2, 5, 6]
+    assert T.chromosome_offsets(np.array(["1", "1", "X"])).tolist() == [0, 2, 3]
+    with pytest.raises(ValueError):
+        T.chromosome_offsets(np.array([1, 2, 1]))
+
+
+def test_run_em_argument_checks_mirror_reference():
+    p = T.loadDefaultParameters(5, 2)
+    data = {"chr": np.ones(4), "posn": np.arange(4.0), "ref": np.full(4, 9.0), "tumDepth": np.full(4, 12.0)}
+    bad = dict(p)
+    del bad["normalParams"]
+    with pytest.raises(ValueError, match="params must include genotypeParams"):
+        T.runEMclonalCN(data, bad)
+    with pytest.raises(T.TitanError, match="useOutlierState"):
+        T.runEMclonalCN(data, p, useOutlierState=True)
+
+
+def test_host_mstep_matches_oracle(golden):
+    """titan_mstep is host code (O(U*Z) scalars, the reference runs it in R): compare the C++
+    coordinate descent with the oracle's restatement on statistics from an oracle E-step."""
+    data = {"chr": golden["data_chr"], "posn": golden["data_posn"].astype(float), "ref": golden["data_ref"].astype(float),
+            "tumDepth": golden["data_tumDepth"].astype(float), "logR": golden["data_logR"]}
+    po = O.load_default_parameters(5, 2, skew=0.1)
+    g, nP, sP, pP = po["genotypeParams"], po["normalParams"], po["cellPrevParams"], po["ploidyParams"]
+    U, Z = 12, 2
+    rng = np.random.default_rng(1)
+    rho = rng.dirichlet(np.full(24, 0.05), size=3000).T.reshape((U, Z, 3000), order="F")
+    sub = {k: v[:3000] for k, v in data.items()}
+    es = {"rho": rho, "rhoG": rho.sum(1), "rhoZ": rho.sum(0)}
+    want = O.m_step(sub, es, 0.5, sP["s_0"], 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], np.array([0]), po, maxiterUpdate=1500)
+    st = np.concatenate([want["stats"][k].reshape(-1, order="F") for k in "abcdeg"])
+    keep = []
+    from titancna_b200.hmm import _hyper
+    h = _hyper(T.loadDefaultParameters(5, 2, skew=0.1), keep)
+    out_s, out_var, out_piG, out_piZ = np.zeros(Z), np.zeros(U), np.zeros(U), np.zeros(Z)
+    n, phi, prior = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    sweeps = ctypes.c_int()
+    P = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(_lib.c_double_p)
+    rG0 = np.ascontiguousarray(es["rhoG"][:, 0])
+    rZ0 = np.ascontiguousarray(es["rhoZ"][:, 0])
+    s0, v0, pg, pz = (np.ascontiguousarray(a, dtype=np.float64) for a in (sP["s_0"], g["var_0"], g["piG_0"], sP["piZ_0"]))
+    rc = T.lib().titan_mstep(ctypes.byref(h), U, Z, 1, 1500, 1, 1, 1, P(st), P(rG0), P(rZ0), 0.5, P(s0), P(v0), 2.0, P(pg),
+                             P(pz), ctypes.byref(n), P(out_s), P(out_var), ctypes.byref(phi), P(out_piG), P(out_piZ),
+                             ctypes.byref(sweeps), ctypes.byref(prior))
+    assert rc == 0, T.lib().titan_last_error()
+    assert sweeps.value == want["sweeps"] == 10
+    assert abs(n.value - want["n"]) < 1e-12 and abs(phi.value - want["phi"]) < 1e-12
+    assert np.abs(out_s - want["s"]).max() < 1e-12 and np.abs(out_var - want["var"]).max() < 1e-14
+    assert np.abs(out_piG - want["piG"]).max() < 1e-15 and np.abs(out_piZ - want["piZ"]).max() < 1e-15
+    pr = O.prior_probs(want["n"], want["s"], want["phi"], want["var"], want["piG"], want["piZ"], g, nP, sP, pP)
+    assert abs(prior.value - pr["prior"]) < 1e-9 * abs(pr["prior"])
+
+
+def test_position_overlap_host_entry():
+    posn = np.array([5.0, 50.0, 500.0])
+    out = np.zeros(3)
+    P = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    st, sp = np.array([1.0, 40.0]), np.array([10.0, 60.0])
+    assert T.lib().titan_get_position_overlap(P(posn), 3, P(st), P(sp), 2, P(out)) == 0
+    assert out.tolist() == [1.0, 2.0, 0.0]

@@ -1,0 +1,12 @@
+"""titancna_b200 -- B200-native (sm_100a) implementation of TitanCNA's E-step hot path.
+
+Host-side mirror of the reference's R API for the path (same function names):
+    loadDefaultParameters, setupClonalParameters, runEMclonalCN, viterbiClonalCN
+over the C ABI in include/titancna_b200.h (titancna_b200/csrc/libtitancna_b200.so).
+"""
+from .params import loadDefaultParameters, setupClonalParameters, estimateDirichletParamsMap  # noqa: F401
+from .hmm import (Solver, runEMclonalCN, viterbiClonalCN, fwd_back_clonalCN, viterbi_clonalCN,  # noqa: F401
+                  chromosome_offsets)
+from ._lib import TitanError, device_count, lib, LIB_PATH  # noqa: F401
+
+__version__ = "0.1.0"

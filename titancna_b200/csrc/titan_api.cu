@@ -1,0 +1,907 @@
+// titan_api.cu -- C ABI (include/titancna_b200.h) and host orchestration of the sm_100a kernels.
+//
+// There is deliberately no CPU implementation of the hot path in this file: every compute entry
+// fails with TITAN_ERR_NO_DEVICE when no CUDA device is usable.
+#include "../../include/titancna_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "titan_host.hpp"
+#include "titan_kernels.cuh"
+
+using namespace titan;
+namespace th = titan_host;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+struct CudaFail {
+  int code;
+};
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      int code_ = (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? TITAN_ERR_NO_DEVICE \
+                                                                                 : TITAN_ERR_CUDA;  \
+      fail(code_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);      \
+      throw CudaFail{code_};                                                                        \
+    }                                                                                               \
+  } while (0)
+
+extern "C" const char *titan_last_error(void) { return g_err.c_str(); }
+extern "C" const char *titan_version(void) { return "titancna_b200 0.1 (sm_100a)"; }
+
+extern "C" int titan_device_count(int *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (count) *count = 0;
+    return fail(TITAN_ERR_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(e));
+  }
+  if (count) *count = n;
+  return n > 0 ? TITAN_OK : fail(TITAN_ERR_NO_DEVICE, "no CUDA device present (this library has no CPU fallback)");
+}
+
+extern "C" int titan_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  return TITAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solver
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+template <class T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CK(cudaMallocHost(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~PinBuf() { release(); }
+};
+
+static const int kMaxZ = 8;
+static const int kRoundSlots = 4096;
+
+struct titan_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t N = 0;
+  int nChr = 0, U = 0, Z = 0, K = 0, h = 0;
+  bool legacy_py = false;          // emissions come from a materialised py matrix
+  std::vector<int64_t> chr_start;
+  std::vector<unsigned char> het;
+  std::vector<double> rhoG_h, rhoZ_h;   // host-exact transition terms between t-1 and t
+
+  // configuration
+  int chunk_len = 512, warm = 160, max_rounds = 64;
+  double rtol = 1e-10, atol = 1e-290;
+
+  // device data
+  DevBuf<SnpRec> snp;
+  DevBuf<TxnRec> txn;
+  DevBuf<double> py;               // legacy mode only
+  DevBuf<Chunk> chunks;
+  std::vector<Chunk> chunks_h;
+  int nChunks = 0, maxChunksPerChr = 1;
+  DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
+  DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
+  DevBuf<double> model;            // packed ModelConsts arrays
+  DevBuf<unsigned char> het_d;
+  PinBuf<double> model_h, out_h;
+  PinBuf<unsigned int> rerun_h;
+  int nSlices = 1, slice = 64;
+
+  // Viterbi (lazy)
+  DevBuf<int> chr_start32, txn_id, path;
+  DevBuf<double> ltab;
+  DevBuf<unsigned char> psi;
+  bool vit_ready = false;
+
+  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  titan_timing tm{};
+
+  ~titan_solver() {
+    for (auto &e : ev)
+      if (e) cudaEventDestroy(e);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+static void build_chunks(titan_solver *s) {
+  s->chunks_h.clear();
+  s->maxChunksPerChr = 1;
+  for (int c = 0; c < s->nChr; ++c) {
+    int cs = (int)s->chr_start[c], ce = (int)s->chr_start[c + 1];
+    if (ce <= cs) continue;
+    int T = ce - cs;
+    int L = s->chunk_len > 0 ? s->chunk_len : T;
+    int n = (T + L - 1) / L;
+    // even split so that no chunk is a short straggler
+    int base = T / n, extra = T % n, t = cs;
+    for (int i = 0; i < n; ++i) {
+      int len = base + (i < extra ? 1 : 0);
+      Chunk ch{t, t + len, cs, ce, c, 0};
+      s->chunks_h.push_back(ch);
+      t += len;
+    }
+    s->maxChunksPerChr = std::max(s->maxChunksPerChr, n);
+  }
+  s->nChunks = (int)s->chunks_h.size();
+  s->chunks.alloc(s->nChunks);
+  CK(cudaMemcpy(s->chunks.p, s->chunks_h.data(), sizeof(Chunk) * s->nChunks, cudaMemcpyHostToDevice));
+  const size_t K = s->K, nc = s->nChunks;
+  s->startf.alloc(nc * K);
+  s->startb.alloc(nc * K);
+  s->endf.alloc(2 * nc * K);
+  s->endb.alloc(2 * nc * K);
+  s->chunk_ll.alloc(nc);
+  s->part.alloc(nc * 6 * K);
+  s->slice = 64;
+  s->nSlices = (s->nChunks + s->slice - 1) / s->slice;
+  s->tmp.alloc((size_t)s->nSlices * 6 * K);
+  s->tm.n_chunks = s->nChunks;
+}
+
+struct SolverInit {
+  int64_t N;
+  int nChr;
+  const int64_t *chr_start;
+  const double *posn, *ref, *depth, *logR, *py;
+  double txnExpLen, zStrength;
+  int U, Z;
+  const double *ZS;
+  int nZS;
+};
+
+static int solver_create_impl(const SolverInit &in, titan_solver **out) {
+  if (!out) return fail(TITAN_ERR_ARG, "titan_solver_create: out is NULL");
+  *out = nullptr;
+  if (in.N <= 0 || in.nChr <= 0 || !in.chr_start || !in.posn)
+    return fail(TITAN_ERR_ARG, "titan_solver_create: empty data (N=%lld, nChr=%d)", (long long)in.N, in.nChr);
+  if (in.N > 2000000000LL) return fail(TITAN_ERR_UNSUPPORTED, "N=%lld exceeds the 32-bit SNP index range", (long long)in.N);
+  if (in.Z < 1 || in.Z > kMaxZ)
+    return fail(TITAN_ERR_UNSUPPORTED, "numClusters=%d outside the supported range 1..%d", in.Z, kMaxZ);
+  if (in.U < 1 || in.U > 32)
+    return fail(TITAN_ERR_UNSUPPORTED, "%d genotype states: the warp-per-chunk kernels cover up to 32", in.U);
+  if (!in.ZS || in.nZS < in.U) return fail(TITAN_ERR_ARG, "zygosityKey must have %d entries", in.U);
+  if (!(in.txnExpLen > 0) || !(in.zStrength > 0))
+    return fail(TITAN_ERR_ARG, "txnExpLen / zStrength must be positive scalars (length-0 arguments are rejected, "
+                               "cf. R/utils.R:1514-1516)");
+  if (in.chr_start[0] != 0 || in.chr_start[in.nChr] != in.N)
+    return fail(TITAN_ERR_ARG, "chr_start must run from 0 to N");
+  for (int c = 0; c < in.nChr; ++c)
+    if (in.chr_start[c + 1] < in.chr_start[c]) return fail(TITAN_ERR_ARG, "chr_start must be non-decreasing");
+  for (int a = 0; a < in.U; ++a)
+    for (int b = a + 1; b < in.U; ++b)
+      if (in.ZS[a] == in.ZS[b] && in.ZS[a] != -1)
+        return fail(TITAN_ERR_UNSUPPORTED, "zygosityKey entries %d and %d are equal (%g): the structured transition "
+                                           "needs distinct zygosity classes", a, b, in.ZS[a]);
+  int ndev = 0;
+  int rc = titan_device_count(&ndev);
+  if (rc != TITAN_OK) return rc;
+
+  std::unique_ptr<titan_solver> S(new titan_solver());
+  titan_solver *s = S.get();
+  try {
+    CK(cudaGetDevice(&s->device));
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    for (auto &e : s->ev) CK(cudaEventCreate(&e));
+    s->N = in.N; s->nChr = in.nChr; s->U = in.U; s->Z = in.Z; s->K = in.U * in.Z;
+    s->chr_start.assign(in.chr_start, in.chr_start + in.nChr + 1);
+    s->het.resize(in.U);
+    s->h = 0;
+    for (int u = 0; u < in.U; ++u) { s->het[u] = (in.ZS[u] == -1); s->h += s->het[u]; }
+    s->legacy_py = in.py != nullptr;
+    const int64_t N = in.N;
+    const int K = s->K;
+
+    // host-exact transition terms (parameter independent)
+    s->rhoG_h.assign(N, 1.0);
+    s->rhoZ_h.assign(N, 1.0);
+    for (int c = 0; c < in.nChr; ++c)
+      for (int64_t t = in.chr_start[c] + 1; t < in.chr_start[c + 1]; ++t) {
+        s->rhoG_h[t] = th::rho_keep(in.posn[t - 1], in.posn[t], in.txnExpLen);
+        s->rhoZ_h[t] = th::rho_keep(in.posn[t - 1], in.posn[t], in.zStrength);
+      }
+    {
+      DevBuf<double> dG, dZ;
+      dG.alloc(N); dZ.alloc(N);
+      CK(cudaMemcpy(dG.p, s->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dZ.p, s->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+      s->txn.alloc(N);
+      txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h, s->txn.p);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(s->stream));
+      s->tm.kernel_launches++;
+    }
+    if (s->legacy_py) {
+      s->py.alloc((size_t)N * K);
+      CK(cudaMemcpy(s->py.p, in.py, sizeof(double) * N * K, cudaMemcpyHostToDevice));
+      s->snp.alloc(1);
+    } else {
+      if (!in.ref || !in.depth || !in.logR) return fail(TITAN_ERR_ARG, "ref, tumDepth and logR columns are required");
+      std::vector<SnpRec> rec((size_t)N);
+      th::LgammaTable tab;
+      for (int64_t t = 0; t < N; ++t) {
+        double x = in.ref[t], d = in.depth[t];
+        if (!(x == x) || !(d == d) || !(in.logR[t] == in.logR[t]))
+          return fail(TITAN_ERR_ARG, "NA/NaN in the data columns at SNP %lld (filterData removes these, R/utils.R:273-310)",
+                      (long long)t);
+        rec[t].x = x;
+        rec[t].nx = d - x;
+        rec[t].lr = in.logR[t];
+        rec[t].lb = th::binom_log_norm(x, d, tab);
+      }
+      s->snp.alloc(N);
+      CK(cudaMemcpy(s->snp.p, rec.data(), sizeof(SnpRec) * N, cudaMemcpyHostToDevice));
+    }
+    s->alpha.alloc((size_t)N * K);
+    s->het_d.alloc(s->U);
+    CK(cudaMemcpy(s->het_d.p, s->het.data(), s->U, cudaMemcpyHostToDevice));
+    s->model.alloc(5 * (size_t)K + 3 * (size_t)s->U);
+    s->model_h.alloc(5 * (size_t)K + 3 * (size_t)s->U);
+    s->out.alloc(6 * (size_t)K + s->nChr);
+    s->rhoG0.alloc((size_t)s->nChr * s->U);
+    s->rhoZ0.alloc((size_t)s->nChr * s->Z);
+    s->out_h.alloc(6 * (size_t)K + s->nChr + (size_t)s->nChr * (s->U + s->Z));
+    s->rerun.alloc(2 * kRoundSlots);
+    s->rerun_h.alloc(2 * kRoundSlots);
+    build_chunks(s);
+  } catch (const CudaFail &f) {
+    return f.code;
+  } catch (const std::bad_alloc &) {
+    return fail(TITAN_ERR_ARG, "host allocation failed");
+  }
+  *out = S.release();
+  return TITAN_OK;
+}
+
+extern "C" int titan_solver_create(const titan_data_desc *d, titan_solver **out) {
+  if (!d) return fail(TITAN_ERR_ARG, "titan_solver_create: desc is NULL");
+  SolverInit in{d->N, d->nChr, d->chr_start, d->posn, d->ref, d->tumDepth, d->logR, nullptr,
+                d->txnExpLen, d->txnZstrength * d->txnExpLen, d->U, d->Z, d->ZS, d->U};
+  return solver_create_impl(in, out);
+}
+
+extern "C" void titan_solver_destroy(titan_solver *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  delete s;
+}
+
+extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup_len, double rel_tol, int max_rounds) {
+  if (!s) return fail(TITAN_ERR_ARG, "solver is NULL");
+  try {
+    s->chunk_len = chunk_len;
+    s->warm = std::max(1, warmup_len);
+    if (rel_tol > 0) s->rtol = rel_tol;
+    if (max_rounds > 0) s->max_rounds = max_rounds;
+    CK(cudaSetDevice(s->device));
+    build_chunks(s);
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+  return TITAN_OK;
+}
+
+extern "C" int titan_solver_set_stream(titan_solver *s, void *cuda_stream) {
+  if (!s) return fail(TITAN_ERR_ARG, "solver is NULL");
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  if (cuda_stream) {
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(TITAN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    s->own_stream = true;
+  }
+  return TITAN_OK;
+}
+
+extern "C" int titan_solver_timing(const titan_solver *s, titan_timing *t) {
+  if (!s || !t) return fail(TITAN_ERR_ARG, "NULL argument");
+  *t = s->tm;
+  return TITAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model constants
+// ---------------------------------------------------------------------------------------------
+static ModelConsts model_layout(const titan_solver *s, double *base) {
+  const size_t K = s->K, U = s->U;
+  ModelConsts M;
+  M.lmu = base;
+  M.l1mu = base + K;
+  M.muC = base + 2 * K;
+  M.pi = base + 3 * K;
+  M.logpi = base + 4 * K;
+  M.cN = base + 5 * K;
+  M.i2v = base + 5 * K + U;
+  M.tv = base + 5 * K + 2 * U;
+  return M;
+}
+
+// host part of the emission (R/hmmClonal.R:579-603,617-634): K logs of the mixture means and the
+// U Gaussian constants, evaluated with the host libm so the Viterbi emission is bit-exact.
+static int upload_model(titan_solver *s, const titan_params *p, double *muR_out, double *muC_out) {
+  const int U = s->U, Z = s->Z, K = s->K;
+  double *hb = s->model_h.p;
+  ModelConsts H = model_layout(s, hb);
+  double *lmu = (double *)H.lmu, *l1mu = (double *)H.l1mu, *muC = (double *)H.muC, *pi = (double *)H.pi,
+         *logpi = (double *)H.logpi, *cN = (double *)H.cN, *i2v = (double *)H.i2v, *tv = (double *)H.tv;
+  if (p->piG && p->piZ) {
+    for (int z = 0; z < Z; ++z)
+      for (int u = 0; u < U; ++u) {
+        pi[u + z * U] = p->piG[u] * p->piZ[z];            // R/hmmClonal.R:196
+        logpi[u + z * U] = std::log(pi[u + z * U]);       // :210 log(piGiZi[c, ])
+      }
+  }
+  if (!s->legacy_py) {
+    if (!p->s || !p->var || !p->rt || !p->ct) return fail(TITAN_ERR_ARG, "titan_params: s, var, rt and ct are required");
+    std::vector<double> muR((size_t)K);
+    th::mixture_means(U, Z, p->rt, p->rn, p->n, p->s, p->ct, p->phi, muR.data(), muC);
+    for (int j = 0; j < K; ++j) {
+      if (!(muR[j] > 0) || !(muR[j] <= 1) || !std::isfinite(muC[j]))
+        return fail(TITAN_ERR_NUMERIC, "mixture mean out of range at state %d (muR=%g muC=%g)", j, muR[j], muC[j]);
+      lmu[j] = std::log(muR[j]);
+      l1mu[j] = std::log(1 - muR[j]);
+    }
+    for (int u = 0; u < U; ++u) {
+      if (!(p->var[u] > 0)) return fail(TITAN_ERR_NUMERIC, "non-positive variance var[%d]=%g", u, p->var[u]);
+      cN[u] = std::log(1 / (std::sqrt(p->var[u]) * std::sqrt(2 * th::kPi)));
+      tv[u] = 2 * p->var[u];
+      i2v[u] = 1.0 / tv[u];
+    }
+    if (muR_out) std::copy(muR.begin(), muR.end(), muR_out);
+    if (muC_out) std::copy(muC, muC + K, muC_out);
+  }
+  CK(cudaMemcpyAsync(s->model.p, hb, sizeof(double) * (5 * (size_t)K + 3 * (size_t)U), cudaMemcpyHostToDevice, s->stream));
+  return TITAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// E-step launch sequence
+// ---------------------------------------------------------------------------------------------
+template <int Z>
+static void launch_fwd(const titan_solver *s, const FbArgs &A) {
+  const int wpb = 4;
+  dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
+  if (s->legacy_py) fwd_chunk_kernel<Z, true><<<grid, block, 0, s->stream>>>(A);
+  else fwd_chunk_kernel<Z, false><<<grid, block, 0, s->stream>>>(A);
+}
+
+template <int Z>
+static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post) {
+  const int wpb = 4;
+  dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
+  if (s->legacy_py) bwd_chunk_kernel<Z, true, false><<<grid, block, 0, s->stream>>>(A);
+  else if (write_post) bwd_chunk_kernel<Z, false, true><<<grid, block, 0, s->stream>>>(A);
+  else bwd_chunk_kernel<Z, false, false><<<grid, block, 0, s->stream>>>(A);
+}
+
+#define Z_DISPATCH(Zv, CALL)            \
+  switch (Zv) {                         \
+    case 1: { constexpr int ZZ = 1; CALL; } break; \
+    case 2: { constexpr int ZZ = 2; CALL; } break; \
+    case 3: { constexpr int ZZ = 3; CALL; } break; \
+    case 4: { constexpr int ZZ = 4; CALL; } break; \
+    case 5: { constexpr int ZZ = 5; CALL; } break; \
+    case 6: { constexpr int ZZ = 6; CALL; } break; \
+    case 7: { constexpr int ZZ = 7; CALL; } break; \
+    case 8: { constexpr int ZZ = 8; CALL; } break; \
+    default: break;                     \
+  }
+
+// runs verification rounds of one direction until no chunk had to be re-run
+static int run_rounds(titan_solver *s, FbArgs &A, bool backward, bool write_post, int *rounds_out, int64_t *runs_out) {
+  unsigned int *ctr = s->rerun.p + (backward ? kRoundSlots : 0);
+  unsigned int *ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
+  const int hard_cap = std::min(kRoundSlots - 1, s->maxChunksPerChr + 2);
+  CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 1), s->stream));
+  A.rerun = ctr;
+  A.startv = backward ? s->startb.p : s->startf.p;
+  A.endv = backward ? s->endb.p : s->endf.p;
+  int64_t runs = 0;
+  int r = 0;
+  auto launch = [&](int round) {
+    A.round = round;
+    if (backward) { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post)); }
+    else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A)); }
+    s->tm.kernel_launches++;
+  };
+  cudaEvent_t e0 = s->ev[backward ? 8 : 6], e1 = s->ev[backward ? 9 : 7];
+  CK(cudaEventRecord(e0, s->stream));
+  launch(0);
+  CK(cudaEventRecord(e1, s->stream));
+  CK(cudaGetLastError());
+  if (s->maxChunksPerChr <= 1) {   // plain sequential recursion: nothing to verify
+    *rounds_out = 1;
+    *runs_out = s->nChunks;
+    return TITAN_OK;
+  }
+  runs = s->nChunks;
+  for (r = 1; r <= hard_cap; ++r) {
+    launch(r);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctr_h + r, ctr + r, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (ctr_h[r] == 0) break;
+    runs += ctr_h[r];
+  }
+  if (r > hard_cap) return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
+  *rounds_out = r + 1;
+  *runs_out = runs;
+  return TITAN_OK;
+}
+
+static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o, bool want_post, double *loggamma_out) {
+  const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
+  const int64_t N = s->N;
+  CK(cudaSetDevice(s->device));
+  int rc = upload_model(s, p, o ? o->muR : nullptr, o ? o->muC : nullptr);
+  if (rc != TITAN_OK) return rc;
+  const bool post = want_post || (o && (o->rhoG || o->rhoZ));
+  if (post && !s->legacy_py) {
+    if (s->rhoG.n < (size_t)N * U) s->rhoG.alloc((size_t)N * U);
+    if (s->rhoZ.n < (size_t)N * Z) s->rhoZ.alloc((size_t)N * Z);
+  }
+  if (s->legacy_py && loggamma_out && s->loggamma.n < (size_t)N * K) s->loggamma.alloc((size_t)N * K);
+
+  FbArgs A{};
+  A.snp = s->snp.p;
+  A.txn = s->txn.p;
+  A.chunks = s->chunks.p;
+  A.nChunks = s->nChunks;
+  A.U = U;
+  A.warm = s->warm;
+  A.rtol = s->rtol;
+  A.atol = s->atol;
+  A.M = model_layout(s, s->model.p);
+  A.het = s->het_d.p;
+  A.py = s->legacy_py ? s->py.p : nullptr;
+  A.alpha = s->alpha.p;
+  A.chunk_ll = s->chunk_ll.p;
+  A.part = s->part.p;
+  A.rhoG0 = s->rhoG0.p;
+  A.rhoZ0 = s->rhoZ0.p;
+  A.rhoG = (post && !s->legacy_py) ? s->rhoG.p : nullptr;
+  A.rhoZ = (post && !s->legacy_py) ? s->rhoZ.p : nullptr;
+  A.loggamma = (s->legacy_py && loggamma_out) ? s->loggamma.p : nullptr;
+
+  CK(cudaEventRecord(s->ev[0], s->stream));
+  int fr = 0, br = 0;
+  int64_t fruns = 0, bruns = 0;
+  rc = run_rounds(s, A, false, false, &fr, &fruns);
+  if (rc != TITAN_OK) return rc;
+  CK(cudaEventRecord(s->ev[1], s->stream));
+  rc = run_rounds(s, A, true, post, &br, &bruns);
+  if (rc != TITAN_OK) return rc;
+  CK(cudaEventRecord(s->ev[2], s->stream));
+  const int width = 6 * K;
+  {
+    dim3 g1((width + 127) / 128, s->nSlices);
+    reduce_slices_kernel<<<g1, 128, 0, s->stream>>>(s->part.p, s->nChunks, width, s->slice, s->tmp.p);
+    reduce_final_kernel<<<(width + nChr + 127) / 128, 128, 0, s->stream>>>(s->tmp.p, s->nSlices, width, s->chunk_ll.p,
+                                                                          s->chunks.p, s->nChunks, nChr, s->out.p);
+    s->tm.kernel_launches += 2;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s->ev[3], s->stream));
+  double *oh = s->out_h.p;
+  CK(cudaMemcpyAsync(oh, s->out.p, sizeof(double) * (width + nChr), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(oh + width + nChr, s->rhoG0.p, sizeof(double) * (size_t)nChr * U, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(oh + width + nChr + (size_t)nChr * U, s->rhoZ0.p, sizeof(double) * (size_t)nChr * Z,
+                     cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1])); s->tm.last_fwd_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[1], s->ev[2])); s->tm.last_bwd_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3])); s->tm.last_reduce_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[3])); s->tm.last_estep_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[6], s->ev[7])); s->tm.last_fwd_r0_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[8], s->ev[9])); s->tm.last_bwd_r0_ms = ms;
+  s->tm.last_fwd_rounds = fr; s->tm.last_bwd_rounds = br;
+  s->tm.last_fwd_chunk_runs = fruns; s->tm.last_bwd_chunk_runs = bruns;
+  if (o) {
+    if (o->stats) std::copy(oh, oh + width, o->stats);
+    if (o->loglik_chr) std::copy(oh + width, oh + width + nChr, o->loglik_chr);
+    if (o->rhoG0) std::copy(oh + width + nChr, oh + width + nChr + (size_t)nChr * U, o->rhoG0);
+    if (o->rhoZ0)
+      std::copy(oh + width + nChr + (size_t)nChr * U, oh + width + nChr + (size_t)nChr * (U + Z), o->rhoZ0);
+    if (o->rhoG && !s->legacy_py) CK(cudaMemcpy(o->rhoG, s->rhoG.p, sizeof(double) * (size_t)N * U, cudaMemcpyDeviceToHost));
+    if (o->rhoZ && !s->legacy_py) CK(cudaMemcpy(o->rhoZ, s->rhoZ.p, sizeof(double) * (size_t)N * Z, cudaMemcpyDeviceToHost));
+  }
+  if (loggamma_out && s->legacy_py)
+    CK(cudaMemcpy(loggamma_out, s->loggamma.p, sizeof(double) * (size_t)N * K, cudaMemcpyDeviceToHost));
+  return TITAN_OK;
+}
+
+extern "C" int titan_estep(titan_solver *s, const titan_params *p, titan_estep_out *out) {
+  if (!s || !p) return fail(TITAN_ERR_ARG, "titan_estep: NULL argument");
+  if (s->legacy_py) return fail(TITAN_ERR_ARG, "titan_estep: solver was created for materialised emissions");
+  if (!p->piG || !p->piZ) return fail(TITAN_ERR_ARG, "titan_estep: piG and piZ are required");
+  try {
+    return estep_impl(s, p, out, false, nullptr);
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Viterbi
+// ---------------------------------------------------------------------------------------------
+static int viterbi_prepare(titan_solver *s) {
+  if (s->vit_ready) return TITAN_OK;
+  const int64_t N = s->N;
+  const int K = s->K;
+  if (K > 256) return fail(TITAN_ERR_UNSUPPORTED, "Viterbi back-pointers are 8-bit: K=%d > 256", K);
+  std::vector<int> cs32(s->nChr + 1);
+  for (int c = 0; c <= s->nChr; ++c) cs32[c] = (int)s->chr_start[c];
+  s->chr_start32.alloc(s->nChr + 1);
+  CK(cudaMemcpy(s->chr_start32.p, cs32.data(), sizeof(int) * (s->nChr + 1), cudaMemcpyHostToDevice));
+  // distinct (rhoG, rhoZ) pairs -> exact log-transition tables
+  std::unordered_map<std::pair<uint64_t, uint64_t>, int, th::PairHash> ids;
+  std::vector<int> id((size_t)N, 0);
+  std::vector<std::pair<double, double>> distinct;
+  for (int c = 0; c < s->nChr; ++c)
+    for (int64_t t = s->chr_start[c] + 1; t < s->chr_start[c + 1]; ++t) {
+      auto key = std::make_pair(th::bits_of(s->rhoG_h[t]), th::bits_of(s->rhoZ_h[t]));
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        it = ids.emplace(key, (int)distinct.size()).first;
+        distinct.emplace_back(s->rhoG_h[t], s->rhoZ_h[t]);
+      }
+      id[t] = it->second;
+    }
+  std::vector<double> tab(std::max<size_t>(1, distinct.size()) * 4 * (size_t)K);
+  for (size_t q = 0; q < distinct.size(); ++q)
+    th::viterbi_log_table(K, s->U, s->het.data(), distinct[q].first, distinct[q].second, tab.data() + q * 4 * (size_t)K);
+  s->txn_id.alloc(N);
+  CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+  s->ltab.alloc(tab.size());
+  CK(cudaMemcpy(s->ltab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+  s->psi.alloc((size_t)N * K);
+  s->path.alloc(N);
+  s->vit_ready = true;
+  return TITAN_OK;
+}
+
+static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_out) {
+  CK(cudaSetDevice(s->device));
+  int rc = viterbi_prepare(s);
+  if (rc != TITAN_OK) return rc;
+  rc = upload_model(s, p, nullptr, nullptr);
+  if (rc != TITAN_OK) return rc;
+  VitArgs A{};
+  A.snp = s->snp.p;
+  A.chr_start = s->chr_start32.p;
+  A.txn_id = s->txn_id.p;
+  A.ltab = s->ltab.p;
+  A.M = model_layout(s, s->model.p);
+  A.het = s->het_d.p;
+  A.py = s->legacy_py ? s->py.p : nullptr;
+  A.U = s->U; A.Z = s->Z; A.K = s->K;
+  A.psi = s->psi.p;
+  A.path = s->path.p;
+  const int K = s->K;
+  const int threads = ((K + 31) / 32) * 32;
+  const size_t smem = sizeof(double) * 6 * (size_t)K;
+  CK(cudaEventRecord(s->ev[4], s->stream));
+  if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A);
+  else viterbi_forward_kernel<false><<<s->nChr, threads, smem, s->stream>>>(A);
+  CK(cudaGetLastError());
+  viterbi_backtrace_kernel<<<s->nChr, 128, 128 * (size_t)K, s->stream>>>(A);
+  CK(cudaGetLastError());
+  s->tm.kernel_launches += 2;
+  CK(cudaEventRecord(s->ev[5], s->stream));
+  CK(cudaMemcpyAsync(path_out, s->path.p, sizeof(int) * s->N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]));
+  s->tm.last_viterbi_ms = ms;
+  return TITAN_OK;
+}
+
+extern "C" int titan_viterbi(titan_solver *s, const titan_params *p, int32_t *path_out) {
+  if (!s || !p || !path_out) return fail(TITAN_ERR_ARG, "titan_viterbi: NULL argument");
+  if (!p->piG || !p->piZ) return fail(TITAN_ERR_ARG, "titan_viterbi: piG and piZ are required");
+  try {
+    return viterbi_impl(s, p, path_out);
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// legacy-compatible entries (one chromosome, materialised log emissions)
+// ---------------------------------------------------------------------------------------------
+static int legacy_create(const char *who, const double *log_pi, int K, const double *py, int T, const double *zs, int nZS,
+                         int numClust, const double *positions, double zStrength, double txnLen, int useOutlier,
+                         titan_solver **out) {
+  if (!log_pi || !py || !zs || !positions) return fail(TITAN_ERR_ARG, "%s: NULL argument", who);
+  if (K <= 0 || T <= 0) return fail(TITAN_ERR_ARG, "%s: The obslik must be %d-by-%d dimension.", who, K, T);
+  if (numClust <= 0) return fail(TITAN_ERR_ARG, "%s: numClust must be a positive scalar", who);
+  if (useOutlier)
+    return fail(TITAN_ERR_UNSUPPORTED, "%s: useOutlier=1 is not covered by the structured kernels (no shipped driver "
+                                       "enables it; SURVEY.md section 0)", who);
+  const int U = K / numClust;   // src/fwd_backC_clonalCN.c:71
+  if (U * numClust != K)
+    return fail(TITAN_ERR_UNSUPPORTED, "%s: K=%d is not a multiple of numClust=%d", who, K, numClust);
+  if (nZS < U) return fail(TITAN_ERR_ARG, "%s: zygosityKey has %d entries, %d unit states", who, nZS, U);
+  int64_t cs[2] = {0, T};
+  SolverInit in{T, 1, cs, positions, nullptr, nullptr, nullptr, py, txnLen, zStrength, U, numClust, zs, nZS};
+  return solver_create_impl(in, out);
+}
+
+extern "C" int titan_fwd_back_clonalCN(const double *log_piGiZi, int K, const double *py, int T, const double *copyNumKey,
+                                       int nCT, const double *zygosityKey, int nZS, int numClust, const double *positions,
+                                       double zStrength, double txnLen, int useOutlier, double *rho_out,
+                                       double *loglik_out) {
+  (void)copyNumKey; (void)nCT;   // unused by the reference's maths as well (fwd_backC_clonalCN.c:266)
+  if (!rho_out || !loglik_out) return fail(TITAN_ERR_ARG, "fwd_backC_clonalCN: NULL output");
+  titan_solver *s = nullptr;
+  int rc = legacy_create("fwd_backC_clonalCN", log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength,
+                         txnLen, useOutlier, &s);
+  if (rc != TITAN_OK) return rc;
+  try {
+    // the initial distribution arrives in log space: pi = exp(log pi)
+    ModelConsts H = model_layout(s, s->model_h.p);
+    for (int j = 0; j < K; ++j) { ((double *)H.logpi)[j] = log_piGiZi[j]; ((double *)H.pi)[j] = std::exp(log_piGiZi[j]); }
+    titan_params p{};
+    titan_estep_out o{};
+    o.loglik_chr = loglik_out;
+    rc = estep_impl(s, &p, &o, false, rho_out);
+  } catch (const CudaFail &f) {
+    rc = f.code;
+  }
+  titan_solver_destroy(s);
+  return rc;
+}
+
+extern "C" int titan_viterbi_clonalCN(const double *log_piGiZi, int K, const double *py, int T, const double *copyNumKey,
+                                      int nCT, const double *zygosityKey, int nZS, int numClust, const double *positions,
+                                      double zStrength, double txnLen, int useOutlier, int *path_out) {
+  (void)copyNumKey; (void)nCT;
+  if (!path_out) return fail(TITAN_ERR_ARG, "viterbiC_clonalCN: NULL output");
+  titan_solver *s = nullptr;
+  int rc = legacy_create("viterbiC_clonalCN", log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength,
+                         txnLen, useOutlier, &s);
+  if (rc != TITAN_OK) return rc;
+  try {
+    ModelConsts H = model_layout(s, s->model_h.p);
+    for (int j = 0; j < K; ++j) { ((double *)H.logpi)[j] = log_piGiZi[j]; ((double *)H.pi)[j] = std::exp(log_piGiZi[j]); }
+    titan_params p{};
+    rc = viterbi_impl(s, &p, path_out);
+  } catch (const CudaFail &f) {
+    rc = f.code;
+  }
+  titan_solver_destroy(s);
+  return rc;
+}
+
+// reference: src/getPositionOverlapC.c:19-50 (host-side; registered but dead in the reference)
+extern "C" int titan_get_position_overlap(const double *posn, int T, const double *start, const double *stop, int Tcn,
+                                          double *out) {
+  if (!posn || !start || !stop || !out) return fail(TITAN_ERR_ARG, "getPositionOverlapC: NULL argument");
+  for (int i = 0; i < T; ++i) {
+    out[i] = 0;
+    for (int j = 0; j < Tcn; ++j)
+      if ((int)start[j] <= (int)posn[i] && (int)posn[i] <= (int)stop[j]) { out[i] = j + 1; break; }
+  }
+  return TITAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// M-step and the EM driver
+// ---------------------------------------------------------------------------------------------
+static int hyper_from_c(const titan_hyper *h, int U, int Z, th::Hyper *H) {
+  if (!h || !h->rt || !h->ct || !h->var_0 || !h->alphaKHyper || !h->betaKHyper || !h->kappaGHyper || !h->piG_0 ||
+      !h->s_0 || !h->alphaSHyper || !h->betaSHyper || !h->kappaZHyper || !h->piZ_0)
+    return fail(TITAN_ERR_ARG, "params must include genotypeParams, ploidyParams, normalParams, cellPrevParams.");
+  H->U = U; H->Z = Z;
+  H->rt.assign(h->rt, h->rt + U); H->ct.assign(h->ct, h->ct + U); H->var_0.assign(h->var_0, h->var_0 + U);
+  H->alphaK.assign(h->alphaKHyper, h->alphaKHyper + U); H->betaK.assign(h->betaKHyper, h->betaKHyper + U);
+  H->kappaG.assign(h->kappaGHyper, h->kappaGHyper + U); H->piG_0.assign(h->piG_0, h->piG_0 + U);
+  H->s_0.assign(h->s_0, h->s_0 + Z); H->alphaS.assign(h->alphaSHyper, h->alphaSHyper + Z);
+  H->betaS.assign(h->betaSHyper, h->betaSHyper + Z); H->kappaZ.assign(h->kappaZHyper, h->kappaZHyper + Z);
+  H->piZ_0.assign(h->piZ_0, h->piZ_0 + Z);
+  H->rn = h->rn; H->n_0 = h->n_0; H->alphaN = h->alphaNHyper; H->betaN = h->betaNHyper;
+  H->phi_0 = h->phi_0; H->alphaP = h->alphaPHyper; H->betaP = h->betaPHyper;
+  return TITAN_OK;
+}
+
+// estimateClonalCNParamsMap, R/paramEstimation.R:10-70 given the six sums and the posteriors at chrPos_0
+static int mstep_core(const th::Hyper &H, int nChr, int maxiterUpdate, bool normal_map, bool estS, bool estP,
+                      const double *stats, const double *rhoG0, const double *rhoZ0, double prev_n, const double *prev_s,
+                      const double *prev_var, double prev_phi, const double *prev_piG, const double *prev_piZ,
+                      double *out_n, double *out_s, double *out_var, double *out_phi, double *out_piG, double *out_piZ,
+                      int *out_sweeps) {
+  const int U = H.U, Z = H.Z, K = U * Z;
+  th::Stats st{stats, stats + K, stats + 2 * K, stats + 3 * K, stats + 4 * K, stats + 5 * K};
+  // likInitG/Z: sum(t(log(pi_0)) %*% rho[, chrPos_0])  (:43-44)
+  double likG = 0, likZ = 0, totG = 0, totZ = 0;
+  for (int c = 0; c < nChr; ++c) {
+    double acc = 0;
+    for (int u = 0; u < U; ++u) { acc += std::log(prev_piG[u]) * rhoG0[(size_t)c * U + u]; totG += rhoG0[(size_t)c * U + u]; }
+    likG += acc;
+    acc = 0;
+    for (int z = 0; z < Z; ++z) { acc += std::log(prev_piZ[z]) * rhoZ0[(size_t)c * Z + z]; totZ += rhoZ0[(size_t)c * Z + z]; }
+    likZ += acc;
+  }
+  th::MStepOut mo = th::update_parameters(H, st, prev_n, prev_s, prev_var, prev_phi, prev_piG, prev_piZ, likG, likZ,
+                                          normal_map, estS, estP, maxiterUpdate, 10);
+  *out_n = mo.n; *out_phi = mo.phi;
+  std::copy(mo.s.begin(), mo.s.end(), out_s);
+  std::copy(mo.var.begin(), mo.var.end(), out_var);
+  // pi updates: sum() over the whole sub-matrix (R/paramEstimation.R:533-547)
+  double skZ = 0, skG = 0;
+  for (int z = 0; z < Z; ++z) skZ += H.kappaZ[z];
+  for (int u = 0; u < U; ++u) skG += H.kappaG[u];
+  for (int z = 0; z < Z; ++z) out_piZ[z] = (totZ + H.kappaZ[z] - 1) / (totZ + skZ - Z);
+  for (int u = 0; u < U; ++u) out_piG[u] = (totG + H.kappaG[u] - 1) / (totG + skG - U);
+  if (out_sweeps) *out_sweeps = mo.sweeps;
+  return TITAN_OK;
+}
+
+extern "C" int titan_mstep(const titan_hyper *h, int U, int Z, int nChr, int maxiterUpdate, int normal_map, int estimateS,
+                           int estimatePloidy, const double *stats, const double *rhoG0, const double *rhoZ0, double prev_n,
+                           const double *prev_s, const double *prev_var, double prev_phi, const double *prev_piG,
+                           const double *prev_piZ, double *out_n, double *out_s, double *out_var, double *out_phi,
+                           double *out_piG, double *out_piZ, int *out_sweeps, double *out_prior) {
+  th::Hyper H;
+  int rc = hyper_from_c(h, U, Z, &H);
+  if (rc != TITAN_OK) return rc;
+  if (!stats || !rhoG0 || !rhoZ0 || !prev_s || !prev_var || !prev_piG || !prev_piZ || !out_n || !out_s || !out_var ||
+      !out_phi || !out_piG || !out_piZ)
+    return fail(TITAN_ERR_ARG, "titan_mstep: NULL argument");
+  rc = mstep_core(H, nChr, maxiterUpdate, normal_map != 0, estimateS != 0, estimatePloidy != 0, stats, rhoG0, rhoZ0, prev_n,
+                  prev_s, prev_var, prev_phi, prev_piG, prev_piZ, out_n, out_s, out_var, out_phi, out_piG, out_piZ,
+                  out_sweeps);
+  if (rc == TITAN_OK && out_prior) {
+    th::Priors pr = th::prior_probs(H, *out_n, out_s, *out_phi, out_var, out_piG, out_piZ, normal_map != 0, estimateS != 0,
+                                    estimatePloidy != 0);
+    *out_prior = pr.prior;
+  }
+  return rc;
+}
+
+// runEMclonalCN, R/hmmClonal.R:8-368 (binomial allele model, useOutlierState = FALSE)
+extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_em_opts *o, titan_em_out *out) {
+  if (!s || !h || !o || !out) return fail(TITAN_ERR_ARG, "titan_em_run: NULL argument");
+  if (s->legacy_py) return fail(TITAN_ERR_ARG, "titan_em_run: solver was created for materialised emissions");
+  const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
+  th::Hyper H;
+  int rc = hyper_from_c(h, U, Z, &H);
+  if (rc != TITAN_OK) return rc;
+  if (!out->n || !out->phi || !out->loglik || !out->s || !out->piZ || !out->var || !out->piG || !out->muR || !out->muC)
+    return fail(TITAN_ERR_ARG, "titan_em_run: output arrays are required");
+  const int maxit = o->maxiter + 1;   // :92
+  const bool nmap = o->normal_map != 0, estS = o->estimateS != 0, estP = o->estimatePloidy != 0;
+  double *n = out->n, *phi = out->phi, *loglik = out->loglik;
+  auto col = [](double *base, int rows, int i) { return base + (size_t)rows * i; };
+  int i = 0;
+  loglik[0] = -std::numeric_limits<double>::infinity();
+  std::copy(H.s_0.begin(), H.s_0.end(), col(out->s, Z, 0));
+  std::copy(H.var_0.begin(), H.var_0.end(), col(out->var, U, 0));
+  phi[0] = H.phi_0;
+  n[0] = H.n_0;
+  std::copy(H.piG_0.begin(), H.piG_0.end(), col(out->piG, U, 0));
+  std::copy(H.piZ_0.begin(), H.piZ_0.end(), col(out->piZ, Z, 0));
+  th::mixture_means(U, Z, H.rt.data(), H.rn, n[0], col(out->s, Z, 0), H.ct.data(), phi[0], col(out->muR, K, 0),
+                    col(out->muC, K, 0));
+  std::vector<double> stats(6 * (size_t)K), llc(nChr), rG0((size_t)nChr * U), rZ0((size_t)nChr * Z);
+  bool converged = false;
+  out->estep_ms = 0;
+  out->mstep_ms = 0;
+  titan_params last_p{};
+  bool have_last = false;
+  try {
+    while (!converged && (i + 1) < maxit) {
+      ++i;
+      titan_params p{};
+      p.n = n[i - 1]; p.phi = phi[i - 1]; p.s = col(out->s, Z, i - 1); p.var = col(out->var, U, i - 1);
+      p.piG = col(out->piG, U, i - 1); p.piZ = col(out->piZ, Z, i - 1);
+      p.rt = H.rt.data(); p.ct = H.ct.data(); p.rn = H.rn;
+      titan_estep_out eo{};
+      eo.loglik_chr = llc.data(); eo.stats = stats.data(); eo.rhoG0 = rG0.data(); eo.rhoZ0 = rZ0.data();
+      rc = estep_impl(s, &p, &eo, false, nullptr);
+      if (rc != TITAN_OK) return rc;
+      last_p = p;
+      have_last = true;
+      out->estep_ms += s->tm.last_estep_ms;
+      double ll = 0;
+      for (int c = 0; c < nChr; ++c) ll += llc[c];        // :218 sum over chromosomes
+      if (!std::isfinite(ll)) return fail(TITAN_ERR_NUMERIC, "non-finite log-likelihood in EM iteration %d", i);
+      auto t0 = std::chrono::steady_clock::now();
+      int sweeps = 0;
+      rc = mstep_core(H, nChr, o->maxiterUpdate, nmap, estS, estP, stats.data(), rG0.data(), rZ0.data(), n[i - 1],
+                      col(out->s, Z, i - 1), col(out->var, U, i - 1), phi[i - 1], col(out->piG, U, i - 1),
+                      col(out->piZ, Z, i - 1), &n[i], col(out->s, Z, i), col(out->var, U, i), &phi[i], col(out->piG, U, i),
+                      col(out->piZ, Z, i), &sweeps);
+      if (rc != TITAN_OK) return rc;
+      if (out->cd_sweeps) out->cd_sweeps[i] = sweeps;
+      th::mixture_means(U, Z, H.rt.data(), H.rn, n[i], col(out->s, Z, i), H.ct.data(), phi[i], col(out->muR, K, i),
+                        col(out->muC, K, i));
+      th::Priors pr = th::prior_probs(H, n[i], col(out->s, Z, i), phi[i], col(out->var, U, i), col(out->piG, U, i),
+                                      col(out->piZ, Z, i), nmap, estS, estP);
+      loglik[i] = ll + pr.prior;                          // :311
+      out->mstep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (o->verbose)
+        fprintf(stderr, "fwdBack: EM iteration %d complete loglik=%0.4f n=%0.4f phi=%0.4f (cd sweeps %d, fwd/bwd rounds %d/%d)\n",
+                i, loglik[i], n[i], phi[i], sweeps, s->tm.last_fwd_rounds, s->tm.last_bwd_rounds);
+      if ((std::fabs(loglik[i] - loglik[i - 1]) / std::fabs(loglik[i])) <= o->likChangeThreshold && loglik[i] >= loglik[i - 1]) {
+        converged = true;                                 // :316-318
+      } else if (loglik[i] < loglik[i - 1]) {
+        converged = true;                                 // :319-325 roll back one column
+        --i;
+      }
+    }
+    out->iters = i + 1;
+    // rhoG / rhoZ of the last executed E-step (R/hmmClonal.R:356-357): the per-iteration passes do not
+    // write the N-sized marginals, so that E-step is repeated once with the output switched on.
+    if (o->want_posteriors && have_last && (out->rhoG || out->rhoZ)) {
+      titan_estep_out eo{};
+      eo.rhoG = out->rhoG;
+      eo.rhoZ = out->rhoZ;
+      rc = estep_impl(s, &last_p, &eo, true, nullptr);
+      if (rc != TITAN_OK) return rc;
+      out->estep_ms += s->tm.last_estep_ms;
+    }
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+  return TITAN_OK;
+}
