@@ -12,11 +12,12 @@ static struct shim_sexp names_symbol, nil_value;
 SEXP R_NamesSymbol = &names_symbol;
 SEXP R_NilValue = &nil_value;
 
-static void **arena = NULL;
-static size_t arena_n = 0, arena_cap = 0;
-static jmp_buf shim_jmp;
-static int shim_jmp_armed = 0;
-static char shim_msg[1024];
+/* per-thread state: bench.py drives one chromosome per worker thread (foreach %dopar% analogue) */
+static __thread void **arena = NULL;
+static __thread size_t arena_n = 0, arena_cap = 0;
+static __thread jmp_buf shim_jmp;
+static __thread int shim_jmp_armed = 0;
+static __thread char shim_msg[1024];
 static const R_CallMethodDef *shim_registered = NULL;
 
 static void *arena_calloc(size_t n, size_t sz) {

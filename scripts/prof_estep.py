@@ -1,0 +1,30 @@
+"""Small driver for ncu: a few E-steps (and optionally a Viterbi pass) at a chosen size / chunking."""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import titancna_b200 as T
+from tests import synth
+import bench
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--snps", type=int, default=200000)
+ap.add_argument("--clusters", type=int, default=3)
+ap.add_argument("--chunk", type=int, default=512)
+ap.add_argument("--warm", type=int, default=160)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--viterbi", action="store_true")
+a = ap.parse_args()
+data, _ = synth.make_data(a.snps, Z=a.clusters, maxCN=8, n_chr=23, seed=bench.SEED)
+p = bench.production_params(T.loadDefaultParameters, data, a.clusters)
+g, sP = p["genotypeParams"], p["cellPrevParams"]
+sol = T.Solver(data, g, a.clusters, 1e15, 1.0)
+sol.configure(a.chunk, a.warm, 1e-10)
+args = (0.45, sP["s_0"], 2.04, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+for _ in range(a.steps):
+    out = sol.estep(*args)
+tm = sol.timing()
+print("estep ms", tm["last_estep_ms"], "fwd r0", tm["last_fwd_r0_ms"], "bwd r0", tm["last_bwd_r0_ms"], "rounds", tm["last_fwd_rounds"], tm["last_bwd_rounds"], "ll", out["loglik"])
+if a.viterbi:
+    path = sol.viterbi(*args)
+    print("viterbi ms", sol.timing()["last_viterbi_ms"], "segments", 1 + np.count_nonzero(np.diff(path)))
+sol.close()

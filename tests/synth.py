@@ -10,7 +10,7 @@ HG19_LEN = [249250621, 243199373, 198022430, 191154276, 180915260, 171115067, 15
             141213431, 135534747, 135006516, 133851895, 115169878, 107349540, 102531392, 90354753,
             81195210, 78077248, 59128983, 63025520, 48129895, 51304566, 155270560]
 CHR_NAMES = [str(i) for i in range(1, 23)] + ["X"]
-S_TRUE = (0.0, 0.35, 0.6, 0.75, 0.85)
+S_TRUE = (0.0, 0.35, 0.6, 0.75, 0.85, 0.9, 0.93, 0.96)   # first five: SURVEY.md 8d
 
 # symmetric genotype table for CN 0..8 (same content as loadDefaultParameters: ct, major fraction)
 _CT, _RT = [0, 1], [0.5, 1.0]

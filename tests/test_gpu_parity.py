@@ -122,7 +122,7 @@ def test_fused_viterbi_bit_exact(N, Z, maxCN, n_chr, txn, zfac):
         p = T.loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z, hetBaselineSkew=skew)
         g, sP = p["genotypeParams"], p["cellPrevParams"]
         n, phi = 0.3, 2.0
-        s = np.array((synth.S_TRUE + (0.9, 0.93, 0.96))[:Z]) * 0.95 + 0.01
+        s = np.array(synth.S_TRUE[:Z]) * 0.95 + 0.01
         muR, muC = O.clonal_two_component_mixture(g["rt"], g["rn"], n, s, g["ct"], phi)
         py = O.compute_py_c(data["ref"], data["tumDepth"], data["logR"], muR, muC, g["var_0"])
         lp = np.vectorize(math.log)(np.outer(g["piG_0"], sP["piZ_0"]).reshape(-1, order="F"))

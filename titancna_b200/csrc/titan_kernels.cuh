@@ -171,12 +171,119 @@ __device__ __forceinline__ bool vec_mismatch(const double (&a)[Z], const double 
 }
 
 // ------------------------------------------------------------------------------------------
+// Record streaming.  The recursion is a dependent chain, so every cycle of load latency inside
+// a step is paid 10^5 times per chromosome.  Each warp therefore stages its per-SNP records
+// (SnpRec 32 B + TxnRec 64 B) through a private shared-memory ring of two 16-step tiles: a
+// tile is fetched from HBM with coalesced 16-byte loads one-and-a-half tiles ahead of its use,
+// parked in registers, and dropped into the ring when the tile before it retires.  Steps then
+// read their records with broadcast shared-memory loads one step ahead of the recursion.
+// DIR = +1 walks t upwards (forward pass), -1 downwards (backward pass).
+// ------------------------------------------------------------------------------------------
+constexpr int kTile = 16;
+constexpr int kTileBytes = kTile * (32 + 64);          // 1536
+constexpr int kWarpSmem = 2 * kTileBytes;              // 3072 B per warp
+
+template <int DIR>
+struct RecStream {
+  const SnpRec *snp;
+  const TxnRec *txn;
+  char *sm;
+  int tbeg, lo, hi, lane;
+  uint4 r0, r1, r2;
+
+  __device__ __forceinline__ int gidx(int q) const { return min(max(tbeg + DIR * q, lo), hi); }
+  __device__ __forceinline__ void gload(int k) {
+    r0 = __ldg(reinterpret_cast<const uint4 *>(snp + gidx(kTile * k + (lane >> 1))) + (lane & 1));
+    r1 = __ldg(reinterpret_cast<const uint4 *>(txn + gidx(kTile * k + (lane >> 2))) + (lane & 3));
+    r2 = __ldg(reinterpret_cast<const uint4 *>(txn + gidx(kTile * k + 8 + (lane >> 2))) + (lane & 3));
+  }
+  __device__ __forceinline__ void sstore(int k) {
+    char *b = sm + (k & 1) * kTileBytes;
+    reinterpret_cast<uint4 *>(b)[lane] = r0;
+    reinterpret_cast<uint4 *>(b + kTile * 32)[lane] = r1;
+    reinterpret_cast<uint4 *>(b + kTile * 32)[32 + lane] = r2;
+  }
+  __device__ __forceinline__ void init(const SnpRec *s, const TxnRec *t, char *smem, int tbeg_, int lo_, int hi_, int lane_) {
+    snp = s; txn = t; sm = smem; tbeg = tbeg_; lo = lo_; hi = hi_; lane = lane_;
+    gload(0); sstore(0);
+    gload(1); sstore(1);
+    gload(2);
+    __syncwarp();
+  }
+  // call at the top of step q: when a new tile starts, retire the previous one
+  __device__ __forceinline__ void advance(int q) {
+    if ((q & (kTile - 1)) == 0 && q > 0) {
+      const int k = q / kTile;
+      __syncwarp();
+      sstore(k + 1);
+      gload(k + 2);
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ void get(int q, SnpRec &s, TxnRec &t) const {
+    const char *b = sm + ((q / kTile) & 1) * kTileBytes;
+    const int i = q & (kTile - 1);
+    s = *reinterpret_cast<const SnpRec *>(b + 32 * i);
+    t = *reinterpret_cast<const TxnRec *>(b + kTile * 32 + 64 * i);
+  }
+};
+
+// one structured forward step: a <- (A_t^T applied to a) .* (B * 2^-e)
+template <int Z>
+__device__ __forceinline__ void fwd_step(double (&a)[Z], const double (&B)[Z], const TxnRec &tr, bool het, int &e) {
+  const double irs = het ? tr.irh : tr.irn;
+  double w[Z], Wz[Z];
+  double Wg = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) { w[z] = a[z] * irs; Wg += w[z]; }
+#pragma unroll
+  for (int z = 0; z < Z; ++z) Wz[z] = warp_sum(w[z]);
+  double W = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) W += Wz[z];
+  const double sc = pow2_rescale(W, e);
+  const double base = het ? (tr.cB * W + tr.k4 * Wg) : (tr.k0 * W + tr.k2 * Wg);
+#pragma unroll
+  for (int z = 0; z < Z; ++z) {
+    const double o = het ? base : (base + tr.k1 * Wz[z] + tr.k3 * w[z]);
+    a[z] = o * (B[z] * sc);
+  }
+}
+
+// one structured backward step: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two
+template <int Z>
+__device__ __forceinline__ void bwd_step(double (&b)[Z], const double (&B)[Z], const TxnRec &tr, bool het, bool active) {
+  double bb[Z], Wzn[Z];
+  double loc = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) { bb[z] = b[z] * B[z]; loc += bb[z]; }
+#pragma unroll
+  for (int z = 0; z < Z; ++z) Wzn[z] = warp_sum(het ? 0.0 : bb[z]);
+  const double H = warp_sum(het ? loc : 0.0);
+  double Wn = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) Wn += Wzn[z];
+  int e;
+  const double sc = pow2_rescale(Wn + H, e);
+  const double irs = (het ? tr.irh : tr.irn) * sc;
+  const double base = tr.k0 * Wn + tr.cB * H + (het ? tr.k4 * loc : tr.k2 * loc);
+#pragma unroll
+  for (int z = 0; z < Z; ++z) {
+    const double o = base + tr.k1 * Wzn[z] + (het ? 0.0 : tr.k3 * bb[z]);
+    b[z] = active ? o * irs : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Forward pass over one chunk per warp.
 // reference recursion: src/fwd_backC_clonalCN.c:111-142 (log space, dense) -- here scaled linear
 // space with the structured O(K) step; log-likelihood pieces are exact for any scaling.
+// The loop body holds two independent instruction streams -- the recursion for SNP t and the
+// emission (exp) for SNP t+1 -- so that their latencies overlap.
 // ------------------------------------------------------------------------------------------
 template <int Z, bool FROM_PY>
 __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
+  __shared__ __align__(16) char smem_all[4 * kWarpSmem];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= A.nChunks) return;
@@ -186,9 +293,10 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
   const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   double *endv_cur = A.endv + cur + (size_t)warp * K;
   const double *endv_prv_self = A.endv + prv + (size_t)warp * K;
+  double *startv = A.startv + (size_t)warp * K;
 
   double a[Z];
-  int tb;               // first SNP index processed by the loop below
+  int tb;               // first SNP index processed
   bool have_start;      // a[] already holds alpha~_{tb-1}
   if (A.round > 0) {
     if (c.t0 == c.cs) {   // chromosome-leading chunks start from pi: exact in round 0
@@ -201,7 +309,7 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
     const double *pe = A.endv + prv + (size_t)(warp - 1) * K;
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
-      used[z] = active ? A.startv[(size_t)warp * K + lane + z * U] : 0.0;
+      used[z] = active ? startv[lane + z * U] : 0.0;
       want[z] = active ? pe[lane + z * U] : 0.0;
     }
     if (!vec_mismatch<Z>(used, want, A.rtol, A.atol)) {
@@ -225,74 +333,100 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
   LaneModel<Z> L;
   if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
   const bool het = active && A.het[lane];
-  double pi[Z];
-#pragma unroll
-  for (int z = 0; z < Z; ++z) pi[z] = active ? A.M.pi[lane + z * U] : 0.0;
+
+  RecStream<1> rs;
+  rs.init(A.snp, A.txn, smem_all + (threadIdx.x >> 5) * kWarpSmem, tb, c.cs, c.ce - 1, lane);
+  const int n = c.t1 - tb;           // steps q = 0..n-1, t = tb + q
+  const int q0 = c.t0 - tb;          // first owned step
+
+  SnpRec rec;
+  TxnRec tr;
+  double B[Z];
+  double m;
+  rs.get(0, rec, tr);
+  if (FROM_PY) m = emission_from_py<Z>(A.py + (size_t)tb * K, U, lane, active, B);
+  else m = emission<Z>(L, rec, B);
 
   double acc_m = 0.0;     // sum of emission shifts over the owned range
   long long acc_e = 0;    // sum of power-of-two rescale exponents over the owned range
-  double s_start = 1.0;   // sum of alpha~ at t0-1 (1 for a chromosome-leading chunk)
-
-  for (int t = tb; t < c.t1; ++t) {
-    double B[Z];
-    double m;
-    if (FROM_PY) m = emission_from_py<Z>(A.py + (size_t)t * K, U, lane, active, B);
-    else m = emission<Z>(L, A.snp[t], B);
-    int e = 0;
-    if (t == c.cs) {
+  double s_start = 1.0;   // mass of the vector entering the owned range (1 for a chromosome-leading chunk)
+  int q = 0;
+  // ---- step q = 0 without a predecessor vector (chromosome start or speculative flat start) ----
+  if (!have_start) {
+    if (tb == c.cs) {
 #pragma unroll
-      for (int z = 0; z < Z; ++z) a[z] = pi[z] * B[z];
-    } else if (!have_start && t == tb) {
-      // speculative start: flat prior over the states at the first warm-up SNP
+      for (int z = 0; z < Z; ++z) a[z] = (active ? A.M.pi[lane + z * U] : 0.0) * B[z];
+    } else {
 #pragma unroll
       for (int z = 0; z < Z; ++z) a[z] = B[z];
-    } else {
-      if (t == c.t0) {   // entering the owned range: record the mass of the incoming vector
-        double loc = 0.0;
-#pragma unroll
-        for (int z = 0; z < Z; ++z) loc += a[z];
-        s_start = warp_sum(loc);
-        if (!have_start) {   // publish the warm-started guess, normalised
-          double inv = 1.0 / s_start;
-#pragma unroll
-          for (int z = 0; z < Z; ++z) {
-            a[z] *= inv;
-            if (active) A.startv[(size_t)warp * K + lane + z * U] = a[z];
-          }
-          s_start = 1.0;
-        } else if (active) {
-#pragma unroll
-          for (int z = 0; z < Z; ++z) A.startv[(size_t)warp * K + lane + z * U] = a[z];
-        }
-      }
-      const TxnRec tr = A.txn[t];
-      const double irs = het ? tr.irh : tr.irn;
-      double w[Z], Wz[Z];
-      double Wg = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) { w[z] = a[z] * irs; Wg += w[z]; }
-#pragma unroll
-      for (int z = 0; z < Z; ++z) Wz[z] = warp_sum(w[z]);
-      double W = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) W += Wz[z];
-      const double sc = pow2_rescale(W, e);
-      const double base_h = tr.cB * W + tr.k4 * Wg;
-      const double base_n = tr.k0 * W + tr.k2 * Wg;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        double o = het ? base_h : (base_n + tr.k1 * Wz[z] + tr.k3 * w[z]);
-        a[z] = o * (B[z] * sc);
-      }
     }
-    if (t >= c.t0) {
+    if (q0 == 0) {        // only a chromosome-leading chunk owns its very first step
       acc_m += m;
-      acc_e += e;
-      if (active) {
+      if (active)
 #pragma unroll
-        for (int z = 0; z < Z; ++z) A.alpha[(size_t)t * K + lane + z * U] = a[z];
-      }
+        for (int z = 0; z < Z; ++z) A.alpha[(size_t)tb * K + lane + z * U] = a[z];
     }
+    q = 1;
+    if (n > 1) {
+      rs.get(1, rec, tr);
+      if (FROM_PY) m = emission_from_py<Z>(A.py + (size_t)(tb + 1) * K, U, lane, active, B);
+      else m = emission<Z>(L, rec, B);
+    }
+  }
+  // ---- warm-up steps (not owned, nothing stored) ----
+  for (; q < q0; ++q) {
+    rs.advance(q);
+    SnpRec recn;
+    TxnRec trn;
+    rs.get(min(q + 1, n - 1), recn, trn);
+    double Bn[Z];
+    double mn;
+    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)min(tb + q + 1, c.t1 - 1) * K, U, lane, active, Bn);
+    else mn = emission<Z>(L, recn, Bn);
+    int e;
+    fwd_step<Z>(a, B, tr, het, e);
+    tr = trn; m = mn;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
+  }
+  // ---- entering the owned range: record / publish the boundary vector alpha~_{t0-1} ----
+  if (c.t0 != c.cs) {
+    double loc = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) loc += a[z];
+    s_start = warp_sum(loc);
+    if (!have_start) {
+      const double inv = 1.0 / s_start;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) a[z] *= inv;
+      s_start = 1.0;
+    }
+    if (active)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) startv[lane + z * U] = a[z];
+  }
+  // ---- owned steps ----
+  for (; q < n; ++q) {
+    rs.advance(q);
+    SnpRec recn;
+    TxnRec trn;
+    rs.get(min(q + 1, n - 1), recn, trn);
+    double Bn[Z];
+    double mn;
+    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)min(tb + q + 1, c.t1 - 1) * K, U, lane, active, Bn);
+    else mn = emission<Z>(L, recn, Bn);
+    int e;
+    fwd_step<Z>(a, B, tr, het, e);
+    acc_m += m;
+    acc_e += e;
+    if (active) {
+      double *dst = A.alpha + (size_t)(tb + q) * K + lane;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) dst[z * U] = a[z];
+    }
+    tr = trn; m = mn;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
   }
   // chunk end: boundary vector (normalised) + log-likelihood piece
   double loc = 0.0;
@@ -312,9 +446,12 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
 // Backward pass + posteriors + sufficient statistics over one chunk per warp.
 // reference: src/fwd_backC_clonalCN.c:148-192 (beta, gamma); R/hmmClonal.R:230-234 (exp, marginals);
 // R/paramEstimation.R:34-40 (a,b,c,d,e,g)
+// Iteration for SNP t (descending): beta~_t from beta~_{t+1} and B_{t+1} (carried), posterior at t,
+// and -- independent of both -- the emission B_t for the next iteration.
 // ------------------------------------------------------------------------------------------
 template <int Z, bool FROM_PY, bool WRITE_POST>
 __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
+  __shared__ __align__(16) char smem_all[4 * kWarpSmem];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= A.nChunks) return;
@@ -324,11 +461,12 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   double *endv_cur = A.endv + cur + (size_t)warp * K;
   const double *endv_prv_self = A.endv + prv + (size_t)warp * K;
+  double *startv = A.startv + (size_t)warp * K;
 
-  // b[] holds beta~_{tn} where tn is the SNP after the one being produced
+  // b[] holds beta~_{tn}; tn == c.ce means "past the end" (beta_{ce-1} = 1)
   double b[Z];
-  int tn;               // index whose beta~ is held in b (c.ce means "past the end": beta = 1)
-  bool have_start;
+  int tn;
+  bool from_boundary;   // b[] was read from the next chunk's published boundary vector
   if (A.round > 0) {
     if (c.t1 == c.ce) {
       if (active)
@@ -340,7 +478,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     const double *pe = A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
-      used[z] = active ? A.startv[(size_t)warp * K + lane + z * U] : 0.0;
+      used[z] = active ? startv[lane + z * U] : 0.0;
       want[z] = active ? pe[lane + z * U] : 0.0;
     }
     if (!vec_mismatch<Z>(used, want, A.rtol, A.atol)) {
@@ -352,10 +490,10 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
 #pragma unroll
     for (int z = 0; z < Z; ++z) b[z] = want[z];
     tn = c.t1;
-    have_start = true;
+    from_boundary = true;
   } else {
     tn = min(c.t1 + A.warm, c.ce);
-    have_start = (tn == c.ce);   // chromosome end: beta = 1 exactly
+    from_boundary = false;
 #pragma unroll
     for (int z = 0; z < Z; ++z) b[z] = active ? 1.0 : 0.0;
   }
@@ -365,75 +503,87 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
   const bool het = active && A.het[lane];
 
+  // stream position q <-> SNP index t = (tn - 1) - q + 1 = tn - q : q = 0 is SNP tn (clamped when tn == ce)
+  RecStream<-1> rs;
+  rs.init(A.snp, A.txn, smem_all + (threadIdx.x >> 5) * kWarpSmem, tn, c.cs, c.ce - 1, lane);
+  SnpRec rec;          // record of SNP t+1 (emission input of the beta step)
+  TxnRec tr;           // transition between t and t+1
+  double B[Z];         // B_{t+1}
+  rs.get(0, rec, tr);
+  if (tn < c.ce) {
+    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)tn * K, U, lane, active, B);
+    else emission<Z>(L, rec, B);
+  } else {
+#pragma unroll
+    for (int z = 0; z < Z; ++z) B[z] = 0.0;
+  }
+
   double st[6][Z];
 #pragma unroll
-  for (int q = 0; q < 6; ++q)
+  for (int qq = 0; qq < 6; ++qq)
 #pragma unroll
-    for (int z = 0; z < Z; ++z) st[q][z] = 0.0;
+    for (int z = 0; z < Z; ++z) st[qq][z] = 0.0;
 
-  for (int t = tn - 1; t >= c.t0; --t) {
-    // ---- beta~_t from beta~_{t+1} ----
-    if (t + 1 < c.ce) {
-      if (t + 1 == c.t1) {   // leaving the warm-up: publish / record the boundary vector beta~_{t1}
-        if (!have_start || A.round == 0) {
-          double loc = 0.0;
+  int q = 1;           // step q produces beta~ at SNP t = tn - q
+  // ---- warm-up steps: t = tn-1 .. t1 ----
+  for (; tn - q >= c.t1; ++q) {
+    rs.advance(q);
+    SnpRec recn;
+    TxnRec trn;
+    rs.get(q, recn, trn);                 // record of SNP t (next iteration's emission input)
+    double Bn[Z];
+    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)(tn - q) * K, U, lane, active, Bn);
+    else emission<Z>(L, recn, Bn);
+    if (tn - q + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active);
+    tr = trn;
 #pragma unroll
-          for (int z = 0; z < Z; ++z) loc += b[z];
-          double inv = 1.0 / warp_sum(loc);
-#pragma unroll
-          for (int z = 0; z < Z; ++z) b[z] *= inv;
-        }
-        if (active)
-#pragma unroll
-          for (int z = 0; z < Z; ++z) A.startv[(size_t)warp * K + lane + z * U] = b[z];
-      }
-      double B[Z];
-      if (FROM_PY) emission_from_py<Z>(A.py + (size_t)(t + 1) * K, U, lane, active, B);
-      else emission<Z>(L, A.snp[t + 1], B);
-      const TxnRec tr = A.txn[t + 1];
-      double bb[Z], Wzn[Z];
+    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
+  }
+  // ---- boundary: b[] is beta~_{t1}; normalise what the warm-up produced and publish it ----
+  if (c.t1 < c.ce) {
+    if (!from_boundary) {
       double loc = 0.0;
 #pragma unroll
-      for (int z = 0; z < Z; ++z) { bb[z] = b[z] * B[z]; loc += bb[z]; }
+      for (int z = 0; z < Z; ++z) loc += b[z];
+      const double inv = 1.0 / warp_sum(loc);
 #pragma unroll
-      for (int z = 0; z < Z; ++z) Wzn[z] = warp_sum(het ? 0.0 : bb[z]);
-      const double H = warp_sum(het ? loc : 0.0);
-      double Wn = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) Wn += Wzn[z];
-      int e;
-      const double sc = pow2_rescale(Wn + H, e);
-      const double irs = (het ? tr.irh : tr.irn) * sc;
-      const double base = tr.k0 * Wn + tr.cB * H + (het ? tr.k4 * loc : tr.k2 * loc);
-#pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        double o = base + tr.k1 * Wzn[z] + (het ? 0.0 : tr.k3 * bb[z]);
-        b[z] = active ? o * irs : 0.0;
-      }
+      for (int z = 0; z < Z; ++z) b[z] *= inv;
     }
-    if (t >= c.t1) continue;   // still warming up
+    if (active)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) startv[lane + z * U] = b[z];
+  }
+  // ---- owned steps: t = t1-1 .. t0 ----
+  for (; tn - q >= c.t0; ++q) {
+    const int t = tn - q;
+    rs.advance(q);
+    SnpRec recn;
+    TxnRec trn;
+    rs.get(q, recn, trn);                 // record of SNP t: statistics now, emission input next iteration
+    double Bn[Z];
+    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)t * K, U, lane, active, Bn);
+    else emission<Z>(L, recn, Bn);
+    double al[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) al[z] = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
+    if (t + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active);
     // ---- posterior gamma_t ~ alpha~_t * beta~_t ----
     double p[Z];
     double loc = 0.0;
 #pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      double al = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
-      p[z] = al * b[z];
-      loc += p[z];
-    }
+    for (int z = 0; z < Z; ++z) { p[z] = al[z] * b[z]; loc += p[z]; }
     const double inv = 1.0 / warp_sum(loc);
     double gsum = 0.0;
 #pragma unroll
     for (int z = 0; z < Z; ++z) { p[z] *= inv; gsum += p[z]; }
     if (!FROM_PY) {
-      const SnpRec r = A.snp[t];
-      const double l2 = r.lr * r.lr;
+      const double l2 = recn.lr * recn.lr;
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
-        st[0][z] += r.x * p[z];
-        st[1][z] += r.nx * p[z];
-        st[2][z] += r.lr * p[z];
-        st[3][z] += r.lb * p[z];
+        st[0][z] += recn.x * p[z];
+        st[1][z] += recn.nx * p[z];
+        st[2][z] += recn.lr * p[z];
+        st[3][z] += recn.lb * p[z];
         st[4][z] += p[z];
         st[5][z] += l2 * p[z];
       }
@@ -459,6 +609,9 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
           if (lane == z) A.rhoZ0[(size_t)c.chr * Z + z] = rz[z];
       }
     }
+    tr = trn;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
   }
   // boundary vector for the previous chunk: beta~ at this chunk's first SNP, normalised
   {
@@ -473,9 +626,9 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   if (!FROM_PY && active) {
     double *dst = A.part + (size_t)warp * 6 * K;
 #pragma unroll
-    for (int q = 0; q < 6; ++q)
+    for (int qq = 0; qq < 6; ++qq)
 #pragma unroll
-      for (int z = 0; z < Z; ++z) dst[q * K + lane + z * U] = st[q][z];
+      for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
   }
 }
 
