@@ -238,3 +238,32 @@ def test_edge_cases_and_errors():
         T.fwd_back_clonalCN(np.zeros(5), np.zeros((5, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15, 1)
     with pytest.raises(T.TitanError, match="positive"):
         T.Solver(data, g, 2, 0.0, 1.0)
+
+
+@pytest.mark.parametrize("env", [{"TITAN_WS_MODE": "0"}, {"TITAN_WS_MODE": "2"}, {"TITAN_ACCEL": "1"},
+                                 {"TITAN_ACCEL": "1", "TITAN_ACCEL_EVERY": "2", "TITAN_ACCEL_TOL": "1e-8"}])
+def test_kernel_variants_agree(env, monkeypatch):
+    """Every execution strategy (warp-per-chunk only, warp-specialised only, history extrapolation of
+    the chunk boundaries) is the same function of the inputs: compare each against the plain
+    sequential recursion on a genome whose boundaries need several verification rounds."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    N, Z = 60000, 3
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=5, seed=77, mean_seg=2000)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=Z)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    s = np.array([0.01, 0.30, 0.32])          # two nearly identical clusters: slow forgetting
+    sol = T.Solver(data, g, Z, 1e15, 1.0)
+    args = (0.4, s, 2.0, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    sol.configure(0, 1, 1e-10)
+    seq = sol.estep(*args, posteriors=True)
+    sol.configure(256, 64, 1e-10)
+    par = sol.estep(*args, posteriors=True)
+    tm = sol.timing()
+    sol.close()
+    assert tm["last_fwd_rounds"] >= 2
+    assert np.allclose(par["loglik_chr"], seq["loglik_chr"], rtol=1e-11, atol=0)
+    assert np.abs(par["rhoG"] - seq["rhoG"]).max() < 1e-7
+    assert np.abs(par["rhoZ"] - seq["rhoZ"]).max() < 1e-7
+    for k in "abcdeg":
+        assert np.allclose(par["stats"][k], seq["stats"][k], rtol=1e-8, atol=1e-6), k

@@ -125,7 +125,8 @@ struct titan_solver {
   std::vector<double> rhoG_h, rhoZ_h;   // host-exact transition terms between t-1 and t
 
   // configuration
-  int chunk_len = 512, warm = 160, max_rounds = 64;
+  int chunk_len = 1024, warm = 192, max_rounds = 64;
+  int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
   double rtol = 1e-10, atol = 1e-290;
 
   // device data
@@ -136,6 +137,13 @@ struct titan_solver {
   std::vector<Chunk> chunks_h;
   int nChunks = 0, maxChunksPerChr = 1;
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
+  DevBuf<double> histQ[2], histE[2], histLL[2], solved[2];   // per direction: run history + solved starts
+  DevBuf<int> hist_n[2];
+  DevBuf<int> chr_chunk0;          // [nChr+1]
+  int accel = 0;                   // experimental: boundary extrapolation from the round history (TITAN_ACCEL=1); off = plain fixed-point rounds
+  int accel_every = 3;
+  double accel_tol = 1e-12;
+  int accel_max = 4;               // extrapolations per direction and E-step; plain rounds afterwards
   DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
   DevBuf<double> model;            // packed ModelConsts arrays
   DevBuf<unsigned char> het_d;
@@ -192,6 +200,18 @@ static void build_chunks(titan_solver *s) {
   s->nSlices = (s->nChunks + s->slice - 1) / s->slice;
   s->tmp.alloc((size_t)s->nSlices * 6 * K);
   s->tm.n_chunks = s->nChunks;
+  for (int d = 0; d < 2; ++d) {
+    s->histQ[d].alloc(nc * kHist * K);
+    s->histE[d].alloc(nc * kHist * K);
+    s->histLL[d].alloc(nc * kHist);
+    s->solved[d].alloc(nc * K);
+    s->hist_n[d].alloc(nc);
+  }
+  std::vector<int> cc0(s->nChr + 1, 0);
+  for (const Chunk &ch : s->chunks_h) cc0[ch.chr + 1]++;
+  for (int c = 0; c < s->nChr; ++c) cc0[c + 1] += cc0[c];
+  s->chr_chunk0.alloc(s->nChr + 1);
+  CK(cudaMemcpy(s->chr_chunk0.p, cc0.data(), sizeof(int) * (s->nChr + 1), cudaMemcpyHostToDevice));
 }
 
 struct SolverInit {
@@ -234,6 +254,11 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
 
   std::unique_ptr<titan_solver> S(new titan_solver());
   titan_solver *s = S.get();
+  if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
+  if (const char *e = getenv("TITAN_ACCEL")) s->accel = atoi(e);
+  if (const char *e = getenv("TITAN_ACCEL_EVERY")) s->accel_every = std::max(2, atoi(e));
+  if (const char *e = getenv("TITAN_ACCEL_TOL")) s->accel_tol = atof(e);
+  if (const char *e = getenv("TITAN_ACCEL_MAX")) s->accel_max = atoi(e);
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -329,6 +354,7 @@ extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup
     s->warm = std::max(1, warmup_len);
     if (rel_tol > 0) s->rtol = rel_tol;
     if (max_rounds > 0) s->max_rounds = max_rounds;
+    if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
     CK(cudaSetDevice(s->device));
     build_chunks(s);
   } catch (const CudaFail &f) {
@@ -432,6 +458,41 @@ static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post) 
   else bwd_chunk_kernel<Z, false, false><<<grid, block, 0, s->stream>>>(A);
 }
 
+template <int Z>
+static void launch_fwd_ws(const titan_solver *s, const FbArgs &A) {
+  static bool attr_set[2] = {false, false};
+  const size_t smem = ws_fwd_smem<Z>();
+  if (s->legacy_py) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
+    fwd_chunk_ws_kernel<Z, true><<<A.nChunks, 128, smem, s->stream>>>(A);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
+    fwd_chunk_ws_kernel<Z, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+  }
+}
+
+template <int Z>
+static void launch_bwd_ws(const titan_solver *s, const FbArgs &A, bool write_post) {
+  static bool attr_set[3] = {false, false, false};
+  const size_t smem = ws_bwd_smem<Z>();
+  if (s->legacy_py) {
+    if (!attr_set[2]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[2] = true; }
+    bwd_chunk_ws_kernel<Z, true, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+  } else if (write_post) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
+    bwd_chunk_ws_kernel<Z, false, true><<<A.nChunks, 128, smem, s->stream>>>(A);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
+    bwd_chunk_ws_kernel<Z, false, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+  }
+}
+
+template <int Z>
+static void launch_solve(const titan_solver *s, const FbArgs &A, bool backward) {
+  if (backward) boundary_solve_kernel<Z, -1><<<s->nChr, 32, 0, s->stream>>>(A, s->chr_chunk0.p);
+  else boundary_solve_kernel<Z, 1><<<s->nChr, 32, 0, s->stream>>>(A, s->chr_chunk0.p);
+}
+
 #define Z_DISPATCH(Zv, CALL)            \
   switch (Zv) {                         \
     case 1: { constexpr int ZZ = 1; CALL; } break; \
@@ -449,7 +510,7 @@ static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post) 
 static int run_rounds(titan_solver *s, FbArgs &A, bool backward, bool write_post, int *rounds_out, int64_t *runs_out) {
   unsigned int *ctr = s->rerun.p + (backward ? kRoundSlots : 0);
   unsigned int *ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
-  const int hard_cap = std::min(kRoundSlots - 1, s->maxChunksPerChr + 2);
+  const int hard_cap = std::min(kRoundSlots - 1, 2 * s->maxChunksPerChr + 4);
   CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 1), s->stream));
   A.rerun = ctr;
   A.startv = backward ? s->startb.p : s->startf.p;
@@ -458,11 +519,28 @@ static int run_rounds(titan_solver *s, FbArgs &A, bool backward, bool write_post
   int r = 0;
   auto launch = [&](int round) {
     A.round = round;
-    if (backward) { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post)); }
-    else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A)); }
+    // round 0 with many chunks is throughput-bound: one warp per chunk.  Verification rounds (few
+    // chunks re-run) and the plain sequential mode are latency-bound: one warp-specialised CTA per chunk.
+    const bool ws = s->ws_mode == 2 || (s->ws_mode == 1 && (round > 0 || s->nChunks < 4 * 148));
+    if (backward) {
+      if (ws) { Z_DISPATCH(s->Z, launch_bwd_ws<ZZ>(s, A, write_post)); }
+      else { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post)); }
+    } else {
+      if (ws) { Z_DISPATCH(s->Z, launch_fwd_ws<ZZ>(s, A)); }
+      else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A)); }
+    }
     s->tm.kernel_launches++;
   };
   cudaEvent_t e0 = s->ev[backward ? 8 : 6], e1 = s->ev[backward ? 9 : 7];
+  const int dir = backward ? 1 : 0;
+  A.solved = nullptr;
+  A.solved_w = s->solved[dir].p;
+  A.histQ = s->histQ[dir].p;
+  A.histE = s->histE[dir].p;
+  A.histLL = s->histLL[dir].p;
+  A.hist_n = s->hist_n[dir].p;
+  A.accel_tol = s->accel_tol;
+  CK(cudaMemsetAsync(A.hist_n, 0, sizeof(int) * (size_t)s->nChunks, s->stream));
   CK(cudaEventRecord(e0, s->stream));
   launch(0);
   CK(cudaEventRecord(e1, s->stream));
@@ -474,11 +552,21 @@ static int run_rounds(titan_solver *s, FbArgs &A, bool backward, bool write_post
   }
   runs = s->nChunks;
   for (r = 1; r <= hard_cap; ++r) {
+    // every accel_every-th round the chunk starts come from the history-based boundary solve
+    // instead of the neighbour's last end vector; verification always uses actual end vectors.
+    const bool solve = s->accel && r >= s->accel_every && (r % s->accel_every) == 0 && (r / s->accel_every) <= s->accel_max;
+    if (solve) {
+      A.round = r;
+      Z_DISPATCH(s->Z, launch_solve<ZZ>(s, A, backward));
+      s->tm.kernel_launches++;
+      A.solved = s->solved[dir].p;
+    }
     launch(r);
+    A.solved = nullptr;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctr_h + r, ctr + r, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    if (ctr_h[r] == 0) break;
+    if (ctr_h[r] == 0 && !solve) break;   // a round that re-ran nothing against ACTUAL end vectors: fixed point
     runs += ctr_h[r];
   }
   if (r > hard_cap) return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);

@@ -60,13 +60,13 @@ __device__ __forceinline__ float warp_maxf(float v) {
   return v;
 }
 
-// 2^-exponent(v) for positive finite v (exact power of two; 1.0 for 0 / non-finite input)
+// 2^-exponent(v) for positive finite v (exact power of two; 1.0 for 0 / subnormal / non-finite input).
+// Branch-free: it sits on the recursion's critical path.
 __device__ __forceinline__ double pow2_rescale(double v, int &e_out) {
-  int hi = __double2hiint(v);
-  int be = (hi >> 20) & 0x7ff;
-  if (be == 0 || be == 0x7ff) { e_out = 0; return 1.0; }
-  e_out = be - 1023;
-  return __hiloint2double((2046 - be) << 20, 0);   // biased exponent 1023 - e
+  const int be = (__double2hiint(v) >> 20) & 0x7ff;
+  const bool ok = (unsigned)(be - 1) < 0x7feu;
+  e_out = ok ? be - 1023 : 0;
+  return __hiloint2double(ok ? ((2046 - be) << 20) : 0x3ff00000, 0);   // biased exponent 1023 - e
 }
 
 // ------------------------------------------------------------------------------------------
@@ -134,6 +134,8 @@ __device__ __forceinline__ double emission_from_py(const double *__restrict__ py
   return m;
 }
 
+constexpr int kHist = 4;
+
 struct FbArgs {
   const SnpRec *snp;          // [N]
   const TxnRec *txn;          // [N]
@@ -142,6 +144,11 @@ struct FbArgs {
   int U;
   int warm;                   // warm-up length (SNPs) for speculative chunk starts
   int round;                  // 0 = first pass; >0 = verification / re-run pass
+  const double *solved;       // round > 0: when non-null, chunk starts come from here instead of the neighbour's end vector
+  double *solved_w;           // boundary_solve_kernel output (same buffer)
+  double *histQ, *histE, *histLL;   // [nChunks][kHist][K], [nChunks][kHist][K], [nChunks][kHist]: last runs of each chunk
+  int *hist_n;                // [nChunks] runs recorded so far
+  double accel_tol;           // largest relative fit residual for which a solved start is trusted
   double rtol, atol;
   ModelConsts M;
   const unsigned char *het;   // [U]
@@ -228,50 +235,66 @@ struct RecStream {
   }
 };
 
-// one structured forward step: a <- (A_t^T applied to a) .* (B * 2^-e)
+// one structured forward step: a <- (A_t^T applied to a) .* (B * 2^-e).
+// HET destinations differ only in their coefficients (select, no divergent branch):
+//   o = cW*W + cG*Wg + cZ*Wz[z] + cw*w[z]
 template <int Z>
 __device__ __forceinline__ void fwd_step(double (&a)[Z], const double (&B)[Z], const TxnRec &tr, bool het, int &e) {
   const double irs = het ? tr.irh : tr.irn;
+  const double cW = het ? tr.cB : tr.k0, cG = het ? tr.k4 : tr.k2, cZ = het ? 0.0 : tr.k1, cw = het ? 0.0 : tr.k3;
   double w[Z], Wz[Z];
-  double Wg = 0.0;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) { w[z] = a[z] * irs; Wg += w[z]; }
+  for (int z = 0; z < Z; ++z) { w[z] = a[z] * irs; Wz[z] = w[z]; }
 #pragma unroll
-  for (int z = 0; z < Z; ++z) Wz[z] = warp_sum(w[z]);
-  double W = 0.0;
+  for (int o = 16; o > 0; o >>= 1)      // Z interleaved butterflies: Z independent shuffles per stage
 #pragma unroll
-  for (int z = 0; z < Z; ++z) W += Wz[z];
+    for (int z = 0; z < Z; ++z) Wz[z] += __shfl_xor_sync(0xffffffffu, Wz[z], o);
+  double Wg = 0.0, W = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) { Wg += w[z]; W += Wz[z]; }
   const double sc = pow2_rescale(W, e);
-  const double base = het ? (tr.cB * W + tr.k4 * Wg) : (tr.k0 * W + tr.k2 * Wg);
+  const double base = cW * W + cG * Wg;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    const double o = het ? base : (base + tr.k1 * Wz[z] + tr.k3 * w[z]);
-    a[z] = o * (B[z] * sc);
-  }
+  for (int z = 0; z < Z; ++z) a[z] = (base + cZ * Wz[z] + cw * w[z]) * (B[z] * sc);
 }
 
 // one structured backward step: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two
 template <int Z>
-__device__ __forceinline__ void bwd_step(double (&b)[Z], const double (&B)[Z], const TxnRec &tr, bool het, bool active) {
-  double bb[Z], Wzn[Z];
+__device__ __forceinline__ void bwd_step(double (&b)[Z], const double (&B)[Z], const TxnRec &tr, bool het, bool active, int &e) {
+  const double cG = het ? tr.k4 : tr.k2, cw = het ? 0.0 : tr.k3;
+  double bb[Z], red[Z + 1];
   double loc = 0.0;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) { bb[z] = b[z] * B[z]; loc += bb[z]; }
+  for (int z = 0; z < Z; ++z) { bb[z] = b[z] * B[z]; loc += bb[z]; red[z] = het ? 0.0 : bb[z]; }
+  red[Z] = het ? loc : 0.0;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) Wzn[z] = warp_sum(het ? 0.0 : bb[z]);
-  const double H = warp_sum(het ? loc : 0.0);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int z = 0; z <= Z; ++z) red[z] += __shfl_xor_sync(0xffffffffu, red[z], o);
+  const double H = red[Z];
   double Wn = 0.0;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) Wn += Wzn[z];
-  int e;
+  for (int z = 0; z < Z; ++z) Wn += red[z];
   const double sc = pow2_rescale(Wn + H, e);
-  const double irs = (het ? tr.irh : tr.irn) * sc;
-  const double base = tr.k0 * Wn + tr.cB * H + (het ? tr.k4 * loc : tr.k2 * loc);
+  const double irs = active ? (het ? tr.irh : tr.irn) * sc : 0.0;
+  const double base = tr.k0 * Wn + tr.cB * H + cG * loc;
 #pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    const double o = base + tr.k1 * Wzn[z] + (het ? 0.0 : tr.k3 * bb[z]);
-    b[z] = active ? o * irs : 0.0;
-  }
+  for (int z = 0; z < Z; ++z) b[z] = (base + tr.k1 * red[z] + cw * bb[z]) * irs;
+}
+
+// append (start, end, log-scale) of a finished chunk run to the chunk's history ring
+template <int Z>
+__device__ __forceinline__ void record_history(const FbArgs &A, int chunk, int U, int lane, bool active, const double *startv,
+                                               const double (&endn)[Z], double ll) {
+  if (A.histQ == nullptr) return;
+  const int K = U * Z;
+  const int slot = A.hist_n[chunk] % kHist;
+  double *q = A.histQ + ((size_t)chunk * kHist + slot) * K, *e = A.histE + ((size_t)chunk * kHist + slot) * K;
+  if (active)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) { q[lane + z * U] = startv[lane + z * U]; e[lane + z * U] = endn[z]; }
+  __syncwarp();
+  if (lane == 0) { A.histLL[(size_t)chunk * kHist + slot] = ll; A.hist_n[chunk] += 1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,7 +329,8 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
       return;
     }
     double used[Z], want[Z];
-    const double *pe = A.endv + prv + (size_t)(warp - 1) * K;
+    const bool use_solved = A.solved != nullptr && A.solved[(size_t)warp * K] == A.solved[(size_t)warp * K];
+    const double *pe = use_solved ? A.solved + (size_t)warp * K : A.endv + prv + (size_t)(warp - 1) * K;
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       used[z] = active ? startv[lane + z * U] : 0.0;
@@ -438,8 +462,14 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
 #pragma unroll
     for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = a[z] * inv;
   }
-  if (lane == 0)
-    A.chunk_ll[warp] = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
+  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
+  if (lane == 0) A.chunk_ll[warp] = ll;
+  if (c.t0 != c.cs) {
+    double endn[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) endn[z] = a[z] * inv;
+    record_history<Z>(A, warp, U, lane, active, startv, endn, ll);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -475,7 +505,8 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
       return;
     }
     double used[Z], want[Z];
-    const double *pe = A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
+    const bool use_solved = A.solved != nullptr && A.solved[(size_t)warp * K] == A.solved[(size_t)warp * K];
+    const double *pe = use_solved ? A.solved + (size_t)warp * K : A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       used[z] = active ? startv[lane + z * U] : 0.0;
@@ -509,10 +540,12 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   SnpRec rec;          // record of SNP t+1 (emission input of the beta step)
   TxnRec tr;           // transition between t and t+1
   double B[Z];         // B_{t+1}
+  double mB = 0.0;     // its emission shift
+  double acc_s = 0.0;  // log-scale of the owned part of the recursion (history only)
   rs.get(0, rec, tr);
   if (tn < c.ce) {
-    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)tn * K, U, lane, active, B);
-    else emission<Z>(L, rec, B);
+    if (FROM_PY) mB = emission_from_py<Z>(A.py + (size_t)tn * K, U, lane, active, B);
+    else mB = emission<Z>(L, rec, B);
   } else {
 #pragma unroll
     for (int z = 0; z < Z; ++z) B[z] = 0.0;
@@ -532,10 +565,12 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     TxnRec trn;
     rs.get(q, recn, trn);                 // record of SNP t (next iteration's emission input)
     double Bn[Z];
-    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)(tn - q) * K, U, lane, active, Bn);
-    else emission<Z>(L, recn, Bn);
-    if (tn - q + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active);
-    tr = trn;
+    double mn;
+    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)(tn - q) * K, U, lane, active, Bn);
+    else mn = emission<Z>(L, recn, Bn);
+    int e;
+    if (tn - q + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active, e);
+    tr = trn; mB = mn;
 #pragma unroll
     for (int z = 0; z < Z; ++z) B[z] = Bn[z];
   }
@@ -561,12 +596,18 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     TxnRec trn;
     rs.get(q, recn, trn);                 // record of SNP t: statistics now, emission input next iteration
     double Bn[Z];
-    if (FROM_PY) emission_from_py<Z>(A.py + (size_t)t * K, U, lane, active, Bn);
-    else emission<Z>(L, recn, Bn);
+    double mn;
+    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)t * K, U, lane, active, Bn);
+    else mn = emission<Z>(L, recn, Bn);
     double al[Z];
 #pragma unroll
     for (int z = 0; z < Z; ++z) al[z] = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
-    if (t + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active);
+    if (t + 1 < c.ce) {
+      int e;
+      bwd_step<Z>(b, B, tr, het, active, e);
+      acc_s += mB + (double)e * 0.6931471805599453094;
+    }
+    mB = mn;
     // ---- posterior gamma_t ~ alpha~_t * beta~_t ----
     double p[Z];
     double loc = 0.0;
@@ -618,10 +659,15 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     double loc = 0.0;
 #pragma unroll
     for (int z = 0; z < Z; ++z) loc += b[z];
-    const double inv = 1.0 / warp_sum(loc);
+    const double s_end = warp_sum(loc);
+    const double inv = 1.0 / s_end;
+    double endn[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) endn[z] = b[z] * inv;
     if (active)
 #pragma unroll
-      for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = b[z] * inv;
+      for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
+    if (c.t1 < c.ce) record_history<Z>(A, warp, U, lane, active, startv, endn, log(s_end) + acc_s);
   }
   if (!FROM_PY && active) {
     double *dst = A.part + (size_t)warp * 6 * K;
@@ -629,6 +675,606 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     for (int qq = 0; qq < 6; ++qq)
 #pragma unroll
       for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised chunk kernels: one CTA per chunk.
+//
+// A lone warp running emission + recursion issues ~365 instructions per SNP at ~4 cycles each
+// (ncu: stall_wait dominates): the dependent chain, not the pipes, sets the pace.  When few
+// chunks are in flight (verification rounds >= 1, or the plain sequential mode) the SM is
+// otherwise idle, so the step is split by dependence class across the warps of a CTA:
+//   producers   evaluate emission tiles B = exp(py - m) (no dependence on the recursion) into a
+//               shared-memory ring, together with the tile's transition records;
+//   consumer    (warp 0) runs nothing but the structured recursion, ~100 instructions per SNP;
+//   posterior   (backward only, warp 1) turns beta~ tiles handed over by the consumer into
+//               posteriors and sufficient statistics, off the recursion's critical path.
+// Hand-off is by volatile shared-memory counters; every warp of the CTA is resident, so the
+// spins cannot deadlock.
+// ------------------------------------------------------------------------------------------
+template <int Z>
+struct WsCfg {
+  static constexpr int TS = (Z <= 5) ? 8 : 4;              // steps per tile
+  static constexpr int NS = 4;                              // emission ring slots
+  static constexpr int NSB = 3;                             // beta ring slots (backward)
+  static constexpr int SLOT_DOUBLES = TS * Z * 32 + TS + TS * 8;   // B, m, TxnRec
+  static constexpr int BETA_DOUBLES = TS * Z * 32;
+};
+template <int Z> __host__ __device__ constexpr size_t ws_fwd_smem() { return sizeof(double) * WsCfg<Z>::NS * WsCfg<Z>::SLOT_DOUBLES + 64; }
+template <int Z> __host__ __device__ constexpr size_t ws_bwd_smem() {
+  return sizeof(double) * (WsCfg<Z>::NS * WsCfg<Z>::SLOT_DOUBLES + WsCfg<Z>::NSB * WsCfg<Z>::BETA_DOUBLES) + 64;
+}
+
+struct WsFlags {            // lives at the end of the dynamic shared memory block
+  volatile int full[4];     // emission slot s holds tile (full[s] - 1)
+  volatile int consumed;    // emission tiles retired by the consumer
+  volatile int bfull[3];    // beta slot s holds tile (bfull[s] - 1)
+  volatile int bconsumed;   // beta tiles retired by the posterior warp
+};
+
+__device__ __forceinline__ void spin_until_ge(volatile int *p, int v) {
+  while (*p < v) { }
+  __threadfence_block();
+}
+__device__ __forceinline__ void spin_until_eq(volatile int *p, int v) {
+  while (*p != v) { }
+  __threadfence_block();
+}
+
+// producer: emission tiles k = first, first+stride, ... for stream positions q <-> SNP tbeg + DIR*q
+template <int Z, int DIR, bool FROM_PY>
+__device__ __forceinline__ void ws_produce(const FbArgs &A, const LaneModel<Z> &L, double *ring, WsFlags *F, int first,
+                                           int stride, int ntiles, int n, int tbeg, int lo, int hi, int lane, bool active) {
+  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, SD = WsCfg<Z>::SLOT_DOUBLES;
+  constexpr int SB = 4;
+  const int U = A.U, K = U * Z;
+  for (int k = first; k < ntiles; k += stride) {
+    double *slot = ring + (size_t)(k % NS) * SD;
+    double *Bs = slot, *ms = slot + TS * Z * 32;
+    uint4 *txs = reinterpret_cast<uint4 *>(slot + TS * Z * 32 + TS);
+    spin_until_ge(&F->consumed, k - NS + 1);
+    if (lane < TS * 4) {     // transition records of the tile, 16-byte pieces
+      const int t = min(max(tbeg + DIR * min(k * TS + (lane >> 2), n - 1), lo), hi);
+      txs[lane] = __ldg(reinterpret_cast<const uint4 *>(A.txn + t) + (lane & 3));
+    }
+#pragma unroll
+    for (int s0 = 0; s0 < TS; s0 += SB) {
+      double v[SB][Z];
+      float mf[SB];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const int t = min(max(tbeg + DIR * min(k * TS + s0 + i, n - 1), lo), hi);
+        double mx = -CUDART_INF;
+        if (FROM_PY) {
+          const double *row = A.py + (size_t)t * K;
+#pragma unroll
+          for (int z = 0; z < Z; ++z) {
+            v[i][z] = active ? __ldg(row + lane + z * U) : -CUDART_INF;
+            mx = fmax(mx, v[i][z]);
+          }
+        } else {
+          const SnpRec r = A.snp[t];
+#pragma unroll
+          for (int z = 0; z < Z; ++z) {
+            const double d = r.lr - L.muC[z];
+            const double e = (r.lb + (r.x * L.lmu[z] + r.nx * L.l1mu[z])) + (L.cN - d * d * L.i2v);
+            v[i][z] = active ? e : -CUDART_INF;
+            mx = fmax(mx, v[i][z]);
+          }
+        }
+        mf[i] = __double2float_rn(mx);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < SB; ++i) mf[i] = fmaxf(mf[i], __shfl_xor_sync(0xffffffffu, mf[i], o));
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const double m = (mf[i] == -CUDART_INF_F) ? 0.0 : (double)mf[i];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) Bs[((s0 + i) * Z + z) * 32 + lane] = active ? exp(v[i][z] - m) : 0.0;
+        if (lane == 0) ms[s0 + i] = m;
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) F->full[k % NS] = k + 1;
+  }
+}
+
+template <int Z, bool FROM_PY>
+__global__ void __launch_bounds__(128) fwd_chunk_ws_kernel(FbArgs A) {
+  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, SD = WsCfg<Z>::SLOT_DOUBLES;
+  extern __shared__ __align__(16) double ws_smem[];
+  WsFlags *F = reinterpret_cast<WsFlags *>(ws_smem + NS * SD);
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Chunk c = A.chunks[chunk];
+  const int U = A.U, K = U * Z;
+  const bool active = lane < U;
+  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  double *endv_cur = A.endv + cur + (size_t)chunk * K;
+  const double *endv_prv_self = A.endv + prv + (size_t)chunk * K;
+  double *startv = A.startv + (size_t)chunk * K;
+
+  double a[Z];
+  int tb;
+  bool have_start;
+  if (A.round > 0) {
+    bool skip = (c.t0 == c.cs);
+    if (!skip) {
+      double used[Z], want[Z];
+      const bool use_solved = A.solved != nullptr && A.solved[(size_t)chunk * K] == A.solved[(size_t)chunk * K];
+      const double *pe = use_solved ? A.solved + (size_t)chunk * K : A.endv + prv + (size_t)(chunk - 1) * K;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        used[z] = active ? startv[lane + z * U] : 0.0;
+        want[z] = active ? pe[lane + z * U] : 0.0;
+        a[z] = want[z];
+      }
+      skip = !vec_mismatch<Z>(used, want, A.rtol, A.atol);
+    }
+    if (skip) {   // uniform over the CTA: every warp read the same values
+      if (warp == 0 && active)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
+      return;
+    }
+    tb = c.t0;
+    have_start = true;
+  } else {
+    tb = max(c.t0 - A.warm, c.cs);
+    have_start = false;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) a[z] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(A.rerun + A.round, 1u);
+    for (int i = 0; i < 4; ++i) F->full[i] = 0;
+    F->consumed = 0;
+  }
+  __syncthreads();   // nothing above wrote startv / endv; flags are initialised
+
+  const int n = c.t1 - tb, q0 = c.t0 - tb;
+  const int ntiles = (n + TS - 1) / TS;
+  if (warp > 0) {
+    LaneModel<Z> L;
+    if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
+    else { L.active = active; L.het = false; }
+    ws_produce<Z, 1, FROM_PY>(A, L, ws_smem, F, warp - 1, 3, ntiles, n, tb, c.cs, c.ce - 1, lane, active);
+    return;
+  }
+  // ---------------- consumer: the recursion alone ----------------
+  const bool het = active && A.het[lane];
+  double acc_m = 0.0;
+  long long acc_e = 0;
+  double s_start = 1.0;
+  double *arow = A.alpha + (size_t)tb * K + lane;
+  int q = 0;
+  for (int k = 0; k < ntiles; ++k) {
+    const double *slot = ws_smem + (size_t)(k % NS) * SD;
+    const double *ms = slot + TS * Z * 32;
+    const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
+    spin_until_eq(&F->full[k % NS], k + 1);
+    const int ns = min(TS, n - k * TS);
+    for (int s = 0; s < ns; ++s, ++q, arow += K) {
+      double B[Z];
+#pragma unroll
+      for (int z = 0; z < Z; ++z) B[z] = slot[(s * Z + z) * 32 + lane];
+      int e = 0;
+      if (q == 0 && !have_start) {
+        const bool at_start = (tb == c.cs);
+#pragma unroll
+        for (int z = 0; z < Z; ++z) a[z] = (at_start ? (active ? A.M.pi[lane + z * U] : 0.0) : 1.0) * B[z];
+      } else {
+        if (q == q0) {   // entering the owned range: record / publish alpha~_{t0-1}
+          double loc = 0.0;
+#pragma unroll
+          for (int z = 0; z < Z; ++z) loc += a[z];
+          s_start = warp_sum(loc);
+          if (!have_start) {
+            const double inv = 1.0 / s_start;
+#pragma unroll
+            for (int z = 0; z < Z; ++z) a[z] *= inv;
+            s_start = 1.0;
+          }
+          if (active)
+#pragma unroll
+            for (int z = 0; z < Z; ++z) startv[lane + z * U] = a[z];
+        }
+        fwd_step<Z>(a, B, txs[s], het, e);
+      }
+      if (q >= q0) {
+        acc_m += ms[s];
+        acc_e += e;
+        if (active)
+#pragma unroll
+          for (int z = 0; z < Z; ++z) arow[z * U] = a[z];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) F->consumed = k + 1;
+  }
+  double loc = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) loc += a[z];
+  const double s_end = warp_sum(loc);
+  const double inv = 1.0 / s_end;
+  if (active)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = a[z] * inv;
+  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
+  if (lane == 0) A.chunk_ll[chunk] = ll;
+  if (c.t0 != c.cs) {
+    double endn[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) endn[z] = a[z] * inv;
+    record_history<Z>(A, chunk, U, lane, active, startv, endn, ll);
+  }
+}
+
+// backward: warp 0 = beta recursion, warp 1 = posteriors + statistics, warps 2-3 = emission producers
+template <int Z, bool FROM_PY, bool WRITE_POST>
+__global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
+  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, NSB = WsCfg<Z>::NSB, SD = WsCfg<Z>::SLOT_DOUBLES,
+                BD = WsCfg<Z>::BETA_DOUBLES;
+  extern __shared__ __align__(16) double ws_smem[];
+  double *bring = ws_smem + NS * SD;
+  WsFlags *F = reinterpret_cast<WsFlags *>(bring + NSB * BD);
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Chunk c = A.chunks[chunk];
+  const int U = A.U, K = U * Z;
+  const bool active = lane < U;
+  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  double *endv_cur = A.endv + cur + (size_t)chunk * K;
+  const double *endv_prv_self = A.endv + prv + (size_t)chunk * K;
+  double *startv = A.startv + (size_t)chunk * K;
+
+  double b[Z];
+  int tn;
+  bool from_boundary;
+  if (A.round > 0) {
+    bool skip = (c.t1 == c.ce);
+    if (!skip) {
+      double used[Z], want[Z];
+      const bool use_solved = A.solved != nullptr && A.solved[(size_t)chunk * K] == A.solved[(size_t)chunk * K];
+      const double *pe = use_solved ? A.solved + (size_t)chunk * K : A.endv + prv + (size_t)(chunk + 1) * K;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        used[z] = active ? startv[lane + z * U] : 0.0;
+        want[z] = active ? pe[lane + z * U] : 0.0;
+        b[z] = want[z];
+      }
+      skip = !vec_mismatch<Z>(used, want, A.rtol, A.atol);
+    }
+    if (skip) {
+      if (warp == 0 && active)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
+      return;
+    }
+    tn = c.t1;
+    from_boundary = true;
+  } else {
+    tn = min(c.t1 + A.warm, c.ce);
+    from_boundary = false;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) b[z] = active ? 1.0 : 0.0;
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(A.rerun + A.round, 1u);
+    for (int i = 0; i < 4; ++i) F->full[i] = 0;
+    for (int i = 0; i < 3; ++i) F->bfull[i] = 0;
+    F->consumed = 0;
+    F->bconsumed = 0;
+  }
+  __syncthreads();
+
+  // step j = 0..n-1 produces beta~ at SNP t = tn - j - 1 from B at stream position j (SNP tn - j)
+  const int n = tn - c.t0, jb = tn - c.t1;
+  const int ntiles = (n + TS - 1) / TS;
+  if (warp >= 2) {
+    LaneModel<Z> L;
+    if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
+    else { L.active = active; L.het = false; }
+    ws_produce<Z, -1, FROM_PY>(A, L, ws_smem, F, warp - 2, 2, ntiles, n, tn, c.cs, c.ce - 1, lane, active);
+    return;
+  }
+  if (warp == 0) {
+    // ---------------- beta recursion ----------------
+    const bool het = active && A.het[lane];
+    double acc_s = 0.0;   // log-scale of the owned part of the recursion (history only)
+    int j = 0;
+    for (int k = 0; k < ntiles; ++k) {
+      const double *slot = ws_smem + (size_t)(k % NS) * SD;
+      const double *ms = slot + TS * Z * 32;
+      const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
+      double *bslot = bring + (size_t)(k % NSB) * BD;
+      spin_until_eq(&F->full[k % NS], k + 1);
+      spin_until_ge(&F->bconsumed, k - NSB + 1);
+      const int ns = min(TS, n - k * TS);
+      for (int s = 0; s < ns; ++s, ++j) {
+        if (j == jb && c.t1 < c.ce) {   // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
+          if (!from_boundary) {
+            double loc = 0.0;
+#pragma unroll
+            for (int z = 0; z < Z; ++z) loc += b[z];
+            const double inv = 1.0 / warp_sum(loc);
+#pragma unroll
+            for (int z = 0; z < Z; ++z) b[z] *= inv;
+          }
+          if (active)
+#pragma unroll
+            for (int z = 0; z < Z; ++z) startv[lane + z * U] = b[z];
+        }
+        if (tn - j < c.ce) {
+          double B[Z];
+#pragma unroll
+          for (int z = 0; z < Z; ++z) B[z] = slot[(s * Z + z) * 32 + lane];
+          int e;
+          bwd_step<Z>(b, B, txs[s], het, active, e);
+          if (j >= jb) acc_s += ms[s] + (double)e * 0.6931471805599453094;
+        }
+#pragma unroll
+        for (int z = 0; z < Z; ++z) bslot[(s * Z + z) * 32 + lane] = b[z];
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) { F->consumed = k + 1; F->bfull[k % NSB] = k + 1; }
+    }
+    double loc = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) loc += b[z];
+    const double s_end = warp_sum(loc);
+    const double inv = 1.0 / s_end;
+    double endn[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) endn[z] = b[z] * inv;
+    if (active)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
+    if (c.t1 < c.ce) record_history<Z>(A, chunk, U, lane, active, startv, endn, log(s_end) + acc_s);
+    return;
+  }
+  // ---------------- warp 1: posteriors + sufficient statistics ----------------
+  double st[6][Z];
+#pragma unroll
+  for (int qq = 0; qq < 6; ++qq)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) st[qq][z] = 0.0;
+  for (int k = 0; k < ntiles; ++k) {
+    const double *bslot = bring + (size_t)(k % NSB) * BD;
+    const int ns = min(TS, n - k * TS);
+    // alpha rows and records of the tile's owned SNPs: independent loads, issued before the wait
+    double al[TS][Z];
+    SnpRec rec[TS];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      const int t = min(max(tn - (k * TS + s) - 1, c.t0), c.t1 - 1);
+#pragma unroll
+      for (int z = 0; z < Z; ++z) al[s][z] = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
+      if (!FROM_PY) rec[s] = A.snp[t];
+    }
+    spin_until_eq(&F->bfull[k % NSB], k + 1);
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      const int t = tn - (k * TS + s) - 1;
+      if (s >= ns || t >= c.t1) continue;
+      double p[Z];
+      double loc = 0.0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) { p[z] = al[s][z] * bslot[(s * Z + z) * 32 + lane]; loc += p[z]; }
+      const double inv = 1.0 / warp_sum(loc);
+      double gsum = 0.0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) { p[z] *= inv; gsum += p[z]; }
+      if (!FROM_PY) {
+        const double l2 = rec[s].lr * rec[s].lr;
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          st[0][z] += rec[s].x * p[z];
+          st[1][z] += rec[s].nx * p[z];
+          st[2][z] += rec[s].lr * p[z];
+          st[3][z] += rec[s].lb * p[z];
+          st[4][z] += p[z];
+          st[5][z] += l2 * p[z];
+        }
+      } else if (A.loggamma != nullptr && active) {
+#pragma unroll
+        for (int z = 0; z < Z; ++z) A.loggamma[(size_t)t * K + lane + z * U] = log(p[z]);
+      }
+      const bool first = (t == c.cs);
+      if (WRITE_POST || first) {
+        double rz[Z];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) rz[z] = warp_sum(p[z]);
+        if (WRITE_POST && A.rhoG != nullptr) {
+          if (active) A.rhoG[(size_t)t * U + lane] = gsum;
+#pragma unroll
+          for (int z = 0; z < Z; ++z)
+            if (lane == z) A.rhoZ[(size_t)t * Z + z] = rz[z];
+        }
+        if (first && A.rhoG0 != nullptr) {
+          if (active) A.rhoG0[(size_t)c.chr * U + lane] = gsum;
+#pragma unroll
+          for (int z = 0; z < Z; ++z)
+            if (lane == z) A.rhoZ0[(size_t)c.chr * Z + z] = rz[z];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) F->bconsumed = k + 1;
+  }
+  if (!FROM_PY && active) {
+    double *dst = A.part + (size_t)chunk * 6 * K;
+#pragma unroll
+    for (int qq = 0; qq < 6; ++qq)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Boundary acceleration from the round history.
+//
+// Fixed-point verification alone needs one round per chunk length of *forgetting time*: where two
+// states are nearly indistinguishable (two clonal clusters of close prevalence) a boundary vector
+// remembers ~10^4 SNPs, i.e. dozens of rounds, although after two or three rounds only a couple of
+// slow directions are still moving.  Every run of a chunk is a sample of its LINEAR transfer
+// operator: (start_i, end_i * exp(ll_i)) = (q_i, P_c q_i).  One warp per chromosome walks the chunk
+// boundaries: the true start a of chunk c is fitted in the affine span of the chunk's last kHist
+// starts (relative least squares) and pushed through P_c by the same combination of the recorded
+// ends -- a chain-wise Anderson step.  Solved starts go to a side buffer; the next round re-runs
+// the chunks whose start changed, and the ordinary verification against ACTUAL end vectors decides
+// when the scan is exact, so the extrapolation can only save rounds, never change the answer.
+// ------------------------------------------------------------------------------------------
+template <int Z, int DIR>
+__global__ void __launch_bounds__(32) boundary_solve_kernel(FbArgs A, const int *__restrict__ chr_chunk0) {
+  constexpr int R = kHist, M = R - 1;
+  const int chr = blockIdx.x, lane = threadIdx.x;
+  const int c_lo = chr_chunk0[chr], c_hi = chr_chunk0[chr + 1];   // chunks [c_lo, c_hi)
+  if (c_hi - c_lo < 2) return;
+  const int U = A.U, K = U * Z;
+  const bool active = lane < U;
+  const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;   // buffer holding the latest ACTUAL end vectors
+  int c = (DIR > 0) ? c_lo : c_hi - 1;
+  double a[Z];
+  bool trusted = true;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) a[z] = active ? A.endv[prv + (size_t)c * K + lane + z * U] : 0.0;   // exact (leading chunk)
+  for (int step = 1; step < c_hi - c_lo; ++step) {
+    c += DIR;
+    if (active)
+#pragma unroll
+      for (int z = 0; z < Z; ++z)
+        A.solved_w[(size_t)c * K + lane + z * U] = trusted ? a[z] : __longlong_as_double(0x7ff8000000000000LL);
+    if (step == c_hi - c_lo - 1) break;
+    const int nh = min(A.hist_n[c], R);
+    const double *Qc = A.histQ + (size_t)c * R * K, *Ec = A.histE + (size_t)c * R * K;
+    const double *LLc = A.histLL + (size_t)c * R;
+    const int ref = (A.hist_n[c] + R - 1) % R;            // most recent run = closest to the truth
+    double q0[Z], e0[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      q0[z] = active ? Qc[(size_t)ref * K + lane + z * U] : 0.0;
+      e0[z] = active ? Ec[(size_t)ref * K + lane + z * U] : 0.0;
+    }
+    const double ll0 = LLc[ref];
+    double amax = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) amax = fmax(amax, a[z]);
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    double d[M][Z], f[M][Z], r0[Z];
+    bool keep[M];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      const double wgt = (a[z] > 1e-280 * amax) ? 1.0 / a[z] : 0.0;
+      r0[z] = (a[z] - q0[z]) * wgt;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        const int slot = (ref + R - 1 - i) % R;             // older runs
+        const bool have = (i + 1) < nh;
+        const double qi = (have && active) ? Qc[(size_t)slot * K + lane + z * U] : q0[z];
+        const double ei = (have && active) ? Ec[(size_t)slot * K + lane + z * U] * exp(LLc[slot] - ll0) : e0[z];
+        d[i][z] = (qi - q0[z]) * wgt;
+        f[i][z] = ei - e0[z];
+      }
+    }
+    double G[M][M], rhs[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) sacc += d[i][z] * r0[z];
+      rhs[i] = sacc;
+#pragma unroll
+      for (int j = i; j < M; ++j) {
+        double g = 0.0;
+#pragma unroll
+        for (int z = 0; z < Z; ++z) g += d[i][z] * d[j][z];
+        G[i][j] = g;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        rhs[i] += __shfl_xor_sync(0xffffffffu, rhs[i], o);
+#pragma unroll
+        for (int j = i; j < M; ++j) G[i][j] += __shfl_xor_sync(0xffffffffu, G[i][j], o);
+      }
+    }
+    // column-scaled Cholesky with a pivot floor: directions the history does not separate are dropped
+    double sc[M], y[M], t[M], Lc[M][M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) { keep[i] = G[i][i] > 1e-24; sc[i] = keep[i] ? rsqrt(G[i][i]) : 0.0; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double sacc = G[j][i] * sc[i] * sc[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) sacc -= Lc[i][k] * Lc[j][k];
+        if (j == i) {
+          if (!keep[i] || sacc < 1e-8) { keep[i] = false; Lc[i][i] = 1.0; }
+          else Lc[i][i] = sqrt(sacc);
+        } else {
+          Lc[i][j] = (keep[i] && keep[j]) ? sacc / Lc[j][j] : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double sacc = keep[i] ? rhs[i] * sc[i] : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) sacc -= Lc[i][k] * t[k];
+      t[i] = keep[i] ? sacc / Lc[i][i] : 0.0;
+    }
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i) {
+      double sacc = t[i];
+#pragma unroll
+      for (int k = i + 1; k < M; ++k) sacc -= Lc[k][i] * y[k];
+      y[i] = keep[i] ? (sacc / Lc[i][i]) * sc[i] : 0.0;
+    }
+    // accept the extrapolation only when the start really lies in the span of the history
+    // (max relative residual below A.rtol-ish) and the combination is tame; otherwise this chunk
+    // is left to the plain fixed-point update and the walk restarts from its latest actual end.
+    double resid = 0.0, ymax = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      double rr = r0[z];
+#pragma unroll
+      for (int i = 0; i < M; ++i) rr -= y[i] * d[i][z];
+      resid = fmax(resid, fabs(rr));
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) ymax = fmax(ymax, fabs(y[i]));
+    for (int o = 16; o > 0; o >>= 1) resid = fmax(resid, __shfl_xor_sync(0xffffffffu, resid, o));
+    double nxt[Z];
+    double loc = 0.0;
+    bool bad = !(resid <= A.accel_tol) || !(ymax <= 1e4);
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      double v = e0[z];
+#pragma unroll
+      for (int i = 0; i < M; ++i) v += y[i] * f[i][z];
+      bad |= !(v >= 0.0) || (v == 0.0 && e0[z] > 0.0);
+      nxt[z] = v;
+      loc += v;
+    }
+    trusted = !__any_sync(0xffffffffu, bad);
+    if (!trusted) {
+      // not trustworthy: the next chunk keeps the plain fixed-point update (its solved start is
+      // poisoned, the main kernel then uses this chunk's actual end vector); the walk continues
+      // from that actual end
+      loc = 0.0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) { nxt[z] = active ? A.endv[prv + (size_t)c * K + lane + z * U] : 0.0; loc += nxt[z]; }
+    }
+    const double inv = 1.0 / warp_sum(loc);
+#pragma unroll
+    for (int z = 0; z < Z; ++z) a[z] = nxt[z] * inv;
   }
 }
 
