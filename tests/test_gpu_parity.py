@@ -267,3 +267,27 @@ def test_kernel_variants_agree(env, monkeypatch):
     assert np.abs(par["rhoZ"] - seq["rhoZ"]).max() < 1e-7
     for k in "abcdeg":
         assert np.allclose(par["stats"][k], seq["stats"][k], rtol=1e-8, atol=1e-6), k
+
+
+def test_r_call_glue_is_a_drop_in_for_the_reference_so(golden):
+    """The .Call boundary itself: the same ctypes driver (oracle/refshim.py) loads the reference's own
+    TitanCNA shared object and this repo's r_glue.c build, registers both through R_init_TitanCNA,
+    looks the routines up by name, and passes identical SEXPs to both."""
+    from oracle import refshim
+    from titancna_b200 import build as B
+    glue = refshim.ShimLibrary(B.GLUE)
+    g, py, lp = _fixture(golden)
+    posn = golden["data_posn"].astype(float)
+    sl = slice(0, 4000)
+    got = glue.fwd_back(lp, py[:, sl], g["ct"], g["ZS"], 2, posn[sl], 1e18, 1e9, 0)
+    gpath = glue.viterbi(lp, py[:, sl], g["ct"], g["ZS"], 2, posn[sl], 1e18, 1e9, 0)
+    if refshim.have_reference():
+        want = refshim.reference().fwd_back(lp, py[:, sl], g["ct"], g["ZS"], 2, posn[sl], 1e18, 1e9, 0)
+        wpath = refshim.reference().viterbi(lp, py[:, sl], g["ct"], g["ZS"], 2, posn[sl], 1e18, 1e9, 0)
+    else:
+        rho, ll = O.fwd_back(lp, py[:, sl], g["ZS"], 2, posn[sl], 1e18, 1e9)
+        want, wpath = {"rho": rho, "loglik": ll}, O.viterbi(lp, py[:, sl], g["ZS"], 2, posn[sl], 1e18, 1e9)
+    assert got["rho"].shape == want["rho"].shape
+    assert abs(got["loglik"] - want["loglik"]) <= 1e-11 * abs(want["loglik"])
+    assert np.abs(np.exp(got["rho"]) - np.exp(want["rho"])).max() < 1e-9
+    assert gpath.dtype == np.int32 and np.array_equal(gpath, wpath)

@@ -134,3 +134,22 @@ def test_position_overlap_host_entry():
     st, sp = np.array([1.0, 40.0]), np.array([10.0, 60.0])
     assert T.lib().titan_get_position_overlap(P(posn), 3, P(st), P(sp), 2, P(out)) == 0
     assert out.tolist() == [1.0, 2.0, 0.0]
+
+
+def test_r_glue_registers_the_reference_call_table():
+    """titancna_b200/csrc/r_glue.c compiled against the shim R.h: same routine names and arities as the
+    reference's src/register.c:8-13, reference error() text on a mis-shaped obslik, and a loud failure
+    (not a CPU fallback) when no device exists."""
+    from oracle import refshim
+    glue = refshim.ShimLibrary(B.GLUE)
+    assert glue.registered() == {"getPositionOverlapC": 3, "fwd_backC_clonalCN": 9, "viterbiC_clonalCN": 9}
+    if refshim.have_reference():
+        assert glue.registered() == refshim.reference().registered()
+    with pytest.raises(refshim.RError, match="The obslik must be 4-by-5 dimension"):
+        glue.fwd_back(np.zeros(4), np.zeros((3, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15)
+    with pytest.raises(refshim.RError, match="The obslik must be 4-by-5 dimension"):
+        glue.viterbi(np.zeros(4), np.zeros((3, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15)
+    assert glue.position_overlap([5, 50, 500], [1, 40], [10, 60]).tolist() == [1.0, 2.0, 0.0]
+    if T.device_count() == 0:
+        with pytest.raises(refshim.RError, match="CUDA"):
+            glue.fwd_back(np.zeros(4), np.zeros((4, 5)), np.zeros(2), np.array([0.0, -1.0]), 2, np.arange(5.0), 1e15, 1e15)
