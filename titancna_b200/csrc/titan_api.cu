@@ -725,11 +725,13 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   A.psi = s->psi.p;
   A.path = s->path.p;
   const int K = s->K;
-  const int threads = ((K + 31) / 32) * 32;
-  const size_t smem = sizeof(double) * 6 * (size_t)K;
+  int P = 8;                                   // threads per destination state (power of two)
+  while (P > 1 && K * P > 1024) P >>= 1;
+  const int threads = ((K * P + 31) / 32) * 32;
+  const size_t smem = sizeof(double) * 9 * (size_t)K;
   CK(cudaEventRecord(s->ev[4], s->stream));
-  if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A);
-  else viterbi_forward_kernel<false><<<s->nChr, threads, smem, s->stream>>>(A);
+  if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A, P);
+  else viterbi_forward_kernel<false><<<s->nChr, threads, smem, s->stream>>>(A, P);
   CK(cudaGetLastError());
   viterbi_backtrace_kernel<<<s->nChr, 128, 128 * (size_t)K, s->stream>>>(A);
   CK(cudaGetLastError());

@@ -1364,62 +1364,105 @@ __device__ __forceinline__ double emission_exact(const SnpRec &r, double lmu, do
   return __dadd_rn(__dadd_rn(pyR, pyC), 1e-300);
 }
 
+// Thread layout: P = blockDim/K' threads per destination state (P a power of two <= 32, consecutive
+// lanes), each scanning a contiguous ascending slice of the sources.  Per step:
+//   phase A  thread i < K forms the four class values v[c][i] = delta[i] (+) logA_class_c(i)  -- 4K
+//            roundings instead of K^2: every destination sharing class c with source i would add
+//            the very same two doubles;
+//   phase B  destination j takes the first-index arg-max over i of v[class(i,j)][i]: slice-local
+//            strict '<' scans, then a butterfly over the P slices ordered by (value desc, index asc),
+//            which is exactly the reference's left-to-right scan with strict '<' (:210-229).
 template <bool FROM_PY>
-__global__ void viterbi_forward_kernel(VitArgs A) {
+__global__ void viterbi_forward_kernel(VitArgs A, int P) {
   extern __shared__ double sm[];
   const int K = A.K, U = A.U;
-  double *delta0 = sm, *delta1 = sm + K;
-  double *lt = sm + 2 * K;            // [K][4] current transition table
+  double *delta = sm;                 // [K]
+  double *v = sm + K;                 // [4][K] class values of the current step
+  double *lt = sm + 5 * K;            // [K][4] current transition table
   __shared__ int cur_id;
   const int chr = blockIdx.x;
   const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
-  const int j = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int j = tid / P, p = tid % P;               // destination state, slice
   const bool on = j < K;
   const int gj = on ? j % U : 0, zj = on ? j / U : 0;
   const bool hetj = on && A.het[gj];
+  const bool lead = on && p == 0;
+  const int per = (K + P - 1) / P;
+  const int i0 = min(p * per, K), i1 = min(i0 + per, K);
   double lmu = 0, l1mu = 0, muC = 0, cN = 0, tv = 1;
-  if (on && !FROM_PY) {
+  if (lead && !FROM_PY) {
     lmu = A.M.lmu[j]; l1mu = A.M.l1mu[j]; muC = A.M.muC[j]; cN = A.M.cN[gj]; tv = A.M.tv[gj];
   }
-  if (threadIdx.x == 0) cur_id = -1;
+  if (tid == 0) cur_id = -1;
   if (cs >= ce) return;
-  {
-    double e0 = 0.0;
-    if (on) e0 = FROM_PY ? A.py[(size_t)cs * K + j] : emission_exact(A.snp[cs], lmu, l1mu, muC, cN, tv);
-    if (on) { delta0[j] = __dadd_rn(A.M.logpi[j], e0); A.psi[(size_t)cs * K + j] = 0; }
+  if (lead) {
+    const double e0 = FROM_PY ? A.py[(size_t)cs * K + j] : emission_exact(A.snp[cs], lmu, l1mu, muC, cN, tv);
+    delta[j] = __dadd_rn(A.M.logpi[j], e0);
+    A.psi[(size_t)cs * K + j] = 0;
   }
   __syncthreads();
-  double *dp = delta0, *dc = delta1;
+  // the table id and the emission of step t+1 do not depend on the recursion: they are fetched /
+  // evaluated one step ahead so that their global-memory latency hides behind phases A and B
+  int id = (cs + 1 < ce) ? A.txn_id[cs + 1] : 0;
+  double e = 0.0;
+  if (lead && cs + 1 < ce)
+    e = FROM_PY ? A.py[(size_t)(cs + 1) * K + j] : emission_exact(A.snp[cs + 1], lmu, l1mu, muC, cN, tv);
   for (int t = cs + 1; t < ce; ++t) {
-    const int id = A.txn_id[t];
-    if (id != cur_id) {            // uniform across the CTA (cur_id read after the barrier below)
-      for (int q = threadIdx.x; q < 4 * K; q += blockDim.x) lt[q] = A.ltab[(size_t)id * 4 * K + q];
+    const int tn = min(t + 1, ce - 1);
+    const int id_n = A.txn_id[tn];
+    SnpRec rec_n;
+    double py_n = 0.0;
+    if (lead) {
+      if (FROM_PY) py_n = A.py[(size_t)tn * K + j];
+      else rec_n = A.snp[tn];
     }
-    double e = 0.0;
-    if (on) e = FROM_PY ? A.py[(size_t)t * K + j] : emission_exact(A.snp[t], lmu, l1mu, muC, cN, tv);
+    if (id != cur_id) {            // uniform across the CTA (cur_id is rewritten between barriers)
+      for (int q = tid; q < 4 * K; q += blockDim.x) lt[q] = A.ltab[(size_t)id * 4 * K + q];
+      __syncthreads();
+    }
+    // phase A
+    if (tid < K) {
+      const double d = delta[tid];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c * K + tid] = __dadd_rn(d, lt[tid * 4 + c]);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) cur_id = id;
-    if (on) {
-      double best = 0.0;
-      int arg = 0;
-      int gi = 0, zi = 0;
-      for (int i = 0; i < K; ++i) {
+    if (tid == 0) cur_id = id;
+    // phase B
+    double best = -CUDART_INF;
+    int arg = 0x7fffffff;
+    if (on && i0 < i1) {
+      int gi = i0 % U, zi = i0 / U;
+      best = v[(((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0)) * K + i0];
+      arg = i0;
+      if (++gi == U) { gi = 0; ++zi; }
+      for (int i = i0 + 1; i < i1; ++i) {
         const int cls = ((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0);
-        const double cand = __dadd_rn(dp[i], lt[i * 4 + cls]);
-        if (i == 0 || best < cand) { best = cand; arg = i; }
+        const double cand = v[cls * K + i];
+        if (best < cand) { best = cand; arg = i; }
         if (++gi == U) { gi = 0; ++zi; }
       }
-      dc[j] = __dadd_rn(best, e);
-      A.psi[(size_t)t * K + j] = (unsigned char)arg;
     }
+    for (int o = 1; o < P; o <<= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    // delta was last read in phase A (before the barrier above), so it can be overwritten here
+    if (lead) {
+      delta[j] = __dadd_rn(best, e);
+      A.psi[(size_t)t * K + j] = (unsigned char)arg;
+      e = FROM_PY ? py_n : emission_exact(rec_n, lmu, l1mu, muC, cN, tv);
+    }
+    id = id_n;
     __syncthreads();
-    double *sw = dp; dp = dc; dc = sw;
   }
   // first-index arg-max of the last delta (viterbiC_clonalCN.c:118) and its publication
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     int arg = 0;
     for (int i = 1; i < K; ++i)
-      if (dp[arg] < dp[i]) arg = i;
+      if (delta[arg] < delta[i]) arg = i;
     A.path[ce - 1] = arg;            // 0-based for now; the backtrace adds 1
   }
 }
