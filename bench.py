@@ -228,7 +228,7 @@ def main():
     sol = T.Solver(data, g, Z, 1e15, 1.0, device=local)
     upload_ms = (time.perf_counter() - t0) * 1e3
     if a.chunk is not None or a.warm is not None:
-        sol.configure(1024 if a.chunk is None else a.chunk, 192 if a.warm is None else a.warm, 1e-10)
+        sol.configure(1024 if a.chunk is None else a.chunk, 192 if a.warm is None else a.warm, 1e-8)
     sol.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # representative parameters: two EM iterations from the production initial values (untimed)

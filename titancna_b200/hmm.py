@@ -67,7 +67,7 @@ class Solver:
 
     __del__ = close
 
-    def configure(self, chunk_len=1024, warmup_len=192, rel_tol=1e-10, max_rounds=64):
+    def configure(self, chunk_len=1024, warmup_len=192, rel_tol=1e-8, max_rounds=64):
         check(lib().titan_solver_configure(self._h, int(chunk_len), int(warmup_len), float(rel_tol), int(max_rounds)))
 
     def set_stream(self, cuda_stream_ptr):
@@ -177,7 +177,7 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
     try:
         if chunk_len is not None or warmup_len is not None or rel_tol is not None:
             solver.configure(1024 if chunk_len is None else chunk_len, 192 if warmup_len is None else warmup_len,
-                             1e-10 if rel_tol is None else rel_tol)
+                             1e-8 if rel_tol is None else rel_tol)
         N, K, M = solver.N, U * Z, int(maxiter) + 1
         keep = []
         h = _hyper(params, keep)
