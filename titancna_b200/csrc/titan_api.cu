@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -123,9 +124,12 @@ struct titan_solver {
   std::vector<int64_t> chr_start;
   std::vector<unsigned char> het;
   std::vector<double> rhoG_h, rhoZ_h;   // host-exact transition terms between t-1 and t
+  std::vector<double> pairG, pairZ;     // the distinct (rhoG, rhoZ) pairs of this data set
+  std::vector<int> pair_id;             // [N] which pair sits between SNP t-1 and t
 
   // configuration
   int chunk_len = 1024, warm = 192, max_rounds = 64;
+  int vit_mode = -1;               // 1: structured O(K*Z) Viterbi step, 0: dense sliced scan, -1: by K (TITAN_VIT_MODE)
   int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
   double rtol = 1e-8, atol = 1e-290;   // 100x inside the 1e-6 posterior tolerance; errors do not amplify
 
@@ -255,6 +259,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   std::unique_ptr<titan_solver> S(new titan_solver());
   titan_solver *s = S.get();
   if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
+  if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
   if (const char *e = getenv("TITAN_ACCEL")) s->accel = atoi(e);
   if (const char *e = getenv("TITAN_ACCEL_EVERY")) s->accel_every = std::max(2, atoi(e));
   if (const char *e = getenv("TITAN_ACCEL_TOL")) s->accel_tol = atof(e);
@@ -273,14 +278,63 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     const int64_t N = in.N;
     const int K = s->K;
 
-    // host-exact transition terms (parameter independent)
+    // host-exact transition terms (parameter independent).  exp() is evaluated once per DISTINCT gap
+    // length (an open-addressing table keyed on the gap's bit pattern), then gaps that round to the
+    // same (rhoG, rhoZ) pair are merged: the Viterbi tables are built per distinct pair.
     s->rhoG_h.assign(N, 1.0);
     s->rhoZ_h.assign(N, 1.0);
-    for (int c = 0; c < in.nChr; ++c)
-      for (int64_t t = in.chr_start[c] + 1; t < in.chr_start[c + 1]; ++t) {
-        s->rhoG_h[t] = th::rho_keep(in.posn[t - 1], in.posn[t], in.txnExpLen);
-        s->rhoZ_h[t] = th::rho_keep(in.posn[t - 1], in.posn[t], in.zStrength);
-      }
+    s->pair_id.assign(N, 0);
+    {
+      size_t cap = 1;
+      int lg = 0;
+      while (cap < (size_t)std::max<int64_t>(1024, N / 4)) { cap <<= 1; ++lg; }
+      // multiplicative hash on the HIGH product bits: gap lengths are small integers stored as
+      // doubles, so their low mantissa bits (and the low product bits) are all zero
+      auto slot_of = [](uint64_t key, int bits) { return (size_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - bits)); };
+      std::vector<uint64_t> keys(cap, ~0ull);
+      std::vector<int> vals(cap, -1);
+      std::unordered_map<std::pair<uint64_t, uint64_t>, int, th::PairHash> pairs;
+      size_t used = 0;
+      auto grow = [&]() {
+        std::vector<uint64_t> k2(cap * 2, ~0ull);
+        std::vector<int> v2(cap * 2, -1);
+        for (size_t q = 0; q < cap; ++q)
+          if (keys[q] != ~0ull) {
+            size_t h = slot_of(keys[q], lg + 1);
+            while (k2[h] != ~0ull) h = (h + 1) & (cap * 2 - 1);
+            k2[h] = keys[q]; v2[h] = vals[q];
+          }
+        keys.swap(k2); vals.swap(v2); cap *= 2; ++lg;
+      };
+      for (int c = 0; c < in.nChr; ++c)
+        for (int64_t t = in.chr_start[c] + 1; t < in.chr_start[c + 1]; ++t) {
+          const double gap = in.posn[t] - in.posn[t - 1];      // rho_keep adds the +1.0 itself
+          const uint64_t key = th::bits_of(gap);
+          size_t h = slot_of(key, lg);
+          while (keys[h] != ~0ull && keys[h] != key) h = (h + 1) & (cap - 1);
+          if (keys[h] == ~0ull) {
+            const double rG = th::rho_keep(in.posn[t - 1], in.posn[t], in.txnExpLen);
+            const double rZ = th::rho_keep(in.posn[t - 1], in.posn[t], in.zStrength);
+            auto pk = std::make_pair(th::bits_of(rG), th::bits_of(rZ));
+            auto it = pairs.find(pk);
+            if (it == pairs.end()) {
+              it = pairs.emplace(pk, (int)s->pairG.size()).first;
+              s->pairG.push_back(rG);
+              s->pairZ.push_back(rZ);
+            }
+            keys[h] = key; vals[h] = it->second;
+            if (++used * 2 > cap) {
+              grow();
+              h = slot_of(key, lg);
+              while (keys[h] != key) h = (h + 1) & (cap - 1);
+            }
+          }
+          const int id = vals[h];
+          s->pair_id[t] = id;
+          s->rhoG_h[t] = s->pairG[id];
+          s->rhoZ_h[t] = s->pairZ[id];
+        }
+    }
     {
       DevBuf<double> dG, dZ;
       dG.alloc(N); dZ.alloc(N);
@@ -680,23 +734,21 @@ static int viterbi_prepare(titan_solver *s) {
   for (int c = 0; c <= s->nChr; ++c) cs32[c] = (int)s->chr_start[c];
   s->chr_start32.alloc(s->nChr + 1);
   CK(cudaMemcpy(s->chr_start32.p, cs32.data(), sizeof(int) * (s->nChr + 1), cudaMemcpyHostToDevice));
-  // distinct (rhoG, rhoZ) pairs -> exact log-transition tables
-  std::unordered_map<std::pair<uint64_t, uint64_t>, int, th::PairHash> ids;
-  std::vector<int> id((size_t)N, 0);
-  std::vector<std::pair<double, double>> distinct;
-  for (int c = 0; c < s->nChr; ++c)
-    for (int64_t t = s->chr_start[c] + 1; t < s->chr_start[c + 1]; ++t) {
-      auto key = std::make_pair(th::bits_of(s->rhoG_h[t]), th::bits_of(s->rhoZ_h[t]));
-      auto it = ids.find(key);
-      if (it == ids.end()) {
-        it = ids.emplace(key, (int)distinct.size()).first;
-        distinct.emplace_back(s->rhoG_h[t], s->rhoZ_h[t]);
-      }
-      id[t] = it->second;
-    }
-  std::vector<double> tab(std::max<size_t>(1, distinct.size()) * 4 * (size_t)K);
-  for (size_t q = 0; q < distinct.size(); ++q)
-    th::viterbi_log_table(K, s->U, s->het.data(), distinct[q].first, distinct[q].second, tab.data() + q * 4 * (size_t)K);
+  // exact log-transition tables, one per distinct (rhoG, rhoZ) pair (host libm, sequential row sums);
+  // independent per pair, so they are spread over the host threads
+  const size_t np = std::max<size_t>(1, s->pairG.size());
+  std::vector<double> tab(np * 4 * (size_t)K);
+  {
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->pairG.size() + 255) / 256)));
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < nt; ++w)
+      pool.emplace_back([&, w]() {
+        for (size_t q = w; q < s->pairG.size(); q += nt)
+          th::viterbi_log_table(K, s->U, s->het.data(), s->pairG[q], s->pairZ[q], tab.data() + q * 4 * (size_t)K);
+      });
+    for (auto &t : pool) t.join();
+  }
+  const std::vector<int> &id = s->pair_id;
   s->txn_id.alloc(N);
   CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
   s->ltab.alloc(tab.size());
@@ -725,13 +777,19 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   A.psi = s->psi.p;
   A.path = s->path.p;
   const int K = s->K;
-  int P = 8;                                   // threads per destination state (power of two)
+  int P = 4;                                   // threads per destination state (power of two)
   if (const char *e = getenv("TITAN_VIT_P")) P = std::max(1, std::min(32, atoi(e)));
   while (P > 1 && K * P > 1024) P >>= 1;
-  const int threads = ((K * P + 31) / 32) * 32;
-  const size_t smem = sizeof(double) * 9 * (size_t)K;
+  const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);   // >= 2K so two loads per thread cover a 4K-entry table
+  const size_t smem = sizeof(double) * 13 * (size_t)K;
   CK(cudaEventRecord(s->ev[4], s->stream));
-  if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A, P);
+  // the structured step costs O(K*Z) per SNP but runs in Z warps; measured crossover with the dense sliced scan is K ~ 120
+  const bool structured = (s->vit_mode == 1 || (s->vit_mode < 0 && K >= 120)) && s->Z * 32 <= 256;
+  if (structured) {
+    const size_t smem2 = sizeof(double) * (4 * (size_t)K + 16 * (size_t)s->Z);
+    if (s->legacy_py) viterbi_struct_kernel<true><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
+    else viterbi_struct_kernel<false><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
+  } else if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A, P);
   else viterbi_forward_kernel<false><<<s->nChr, threads, smem, s->stream>>>(A, P);
   CK(cudaGetLastError());
   viterbi_backtrace_kernel<<<s->nChr, 128, 128 * (size_t)K, s->stream>>>(A);
