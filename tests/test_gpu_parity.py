@@ -240,12 +240,13 @@ def test_edge_cases_and_errors():
         T.Solver(data, g, 2, 0.0, 1.0)
 
 
-@pytest.mark.parametrize("env", [{"TITAN_WS_MODE": "0"}, {"TITAN_WS_MODE": "2"}, {"TITAN_ACCEL": "1"},
-                                 {"TITAN_ACCEL": "1", "TITAN_ACCEL_EVERY": "2", "TITAN_ACCEL_TOL": "1e-8"}])
+@pytest.mark.parametrize("env", [{"TITAN_WS_MODE": "0"}, {"TITAN_WS_MODE": "2"}, {"TITAN_OVERLAP": "0"},
+                                 {"TITAN_OVERLAP": "0", "TITAN_WS_MODE": "0"}, {"TITAN_VIT_MODE": "1"}])
 def test_kernel_variants_agree(env, monkeypatch):
-    """Every execution strategy (warp-per-chunk only, warp-specialised only, history extrapolation of
-    the chunk boundaries) is the same function of the inputs: compare each against the plain
-    sequential recursion on a genome whose boundaries need several verification rounds."""
+    """Every execution strategy (warp-per-chunk only, warp-specialised only, forward/backward rounds
+    overlapped on two streams or run back to back) is the same function of the inputs: compare each
+    against the plain sequential recursion on a genome whose boundaries need several verification
+    rounds (two nearly identical clusters: slow forgetting)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     N, Z = 60000, 3
@@ -260,7 +261,13 @@ def test_kernel_variants_agree(env, monkeypatch):
     sol.configure(256, 64, 1e-10)
     par = sol.estep(*args, posteriors=True)
     tm = sol.timing()
+    p1 = sol.viterbi(*args)
     sol.close()
+    monkeypatch.setenv("TITAN_VIT_MODE", "0")
+    ref_sol = T.Solver(data, g, Z, 1e15, 1.0)
+    p0 = ref_sol.viterbi(*args)
+    ref_sol.close()
+    assert np.array_equal(p0, p1)                     # dense and structured Viterbi steps: identical paths
     assert tm["last_fwd_rounds"] >= 2
     assert np.allclose(par["loglik_chr"], seq["loglik_chr"], rtol=1e-11, atol=0)
     assert np.abs(par["rhoG"] - seq["rhoG"]).max() < 1e-7

@@ -141,13 +141,10 @@ struct titan_solver {
   std::vector<Chunk> chunks_h;
   int nChunks = 0, maxChunksPerChr = 1;
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
-  DevBuf<double> histQ[2], histE[2], histLL[2], solved[2];   // per direction: run history + solved starts
-  DevBuf<int> hist_n[2];
   DevBuf<int> chr_chunk0;          // [nChr+1]
-  int accel = 0;                   // experimental: boundary extrapolation from the round history (TITAN_ACCEL=1); off = plain fixed-point rounds
-  int accel_every = 3;
-  double accel_tol = 1e-12;
-  int accel_max = 4;               // extrapolations per direction and E-step; plain rounds afterwards
+  int overlap = 1;                 // run the forward and the backward boundary rounds concurrently on two streams
+  cudaStream_t stream_b = nullptr; // second stream (backward boundary rounds)
+  cudaEvent_t ev_sync[2] = {nullptr, nullptr};
   DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
   DevBuf<double> model;            // packed ModelConsts arrays
   DevBuf<unsigned char> het_d;
@@ -167,6 +164,9 @@ struct titan_solver {
   ~titan_solver() {
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
+    for (auto &e : ev_sync)
+      if (e) cudaEventDestroy(e);
+    if (stream_b) cudaStreamDestroy(stream_b);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -204,13 +204,6 @@ static void build_chunks(titan_solver *s) {
   s->nSlices = (s->nChunks + s->slice - 1) / s->slice;
   s->tmp.alloc((size_t)s->nSlices * 6 * K);
   s->tm.n_chunks = s->nChunks;
-  for (int d = 0; d < 2; ++d) {
-    s->histQ[d].alloc(nc * kHist * K);
-    s->histE[d].alloc(nc * kHist * K);
-    s->histLL[d].alloc(nc * kHist);
-    s->solved[d].alloc(nc * K);
-    s->hist_n[d].alloc(nc);
-  }
   std::vector<int> cc0(s->nChr + 1, 0);
   for (const Chunk &ch : s->chunks_h) cc0[ch.chr + 1]++;
   for (int c = 0; c < s->nChr; ++c) cc0[c + 1] += cc0[c];
@@ -260,15 +253,14 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   titan_solver *s = S.get();
   if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
-  if (const char *e = getenv("TITAN_ACCEL")) s->accel = atoi(e);
-  if (const char *e = getenv("TITAN_ACCEL_EVERY")) s->accel_every = std::max(2, atoi(e));
-  if (const char *e = getenv("TITAN_ACCEL_TOL")) s->accel_tol = atof(e);
-  if (const char *e = getenv("TITAN_ACCEL_MAX")) s->accel_max = atoi(e);
+  if (const char *e = getenv("TITAN_OVERLAP")) s->overlap = atoi(e);
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
     for (auto &e : s->ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
+    for (auto &e : s->ev_sync) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     s->N = in.N; s->nChr = in.nChr; s->U = in.U; s->Z = in.Z; s->K = in.U * in.Z;
     s->chr_start.assign(in.chr_start, in.chr_start + in.nChr + 1);
     s->het.resize(in.U);
@@ -496,55 +488,49 @@ static int upload_model(titan_solver *s, const titan_params *p, double *muR_out,
 // E-step launch sequence
 // ---------------------------------------------------------------------------------------------
 template <int Z>
-static void launch_fwd(const titan_solver *s, const FbArgs &A) {
+static void launch_fwd(const titan_solver *s, const FbArgs &A, cudaStream_t st) {
   const int wpb = 4;
   dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
-  if (s->legacy_py) fwd_chunk_kernel<Z, true><<<grid, block, 0, s->stream>>>(A);
-  else fwd_chunk_kernel<Z, false><<<grid, block, 0, s->stream>>>(A);
+  if (s->legacy_py) fwd_chunk_kernel<Z, true><<<grid, block, 0, st>>>(A);
+  else fwd_chunk_kernel<Z, false><<<grid, block, 0, st>>>(A);
 }
 
 template <int Z>
-static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post) {
+static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post, cudaStream_t st) {
   const int wpb = 4;
   dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
-  if (s->legacy_py) bwd_chunk_kernel<Z, true, false><<<grid, block, 0, s->stream>>>(A);
-  else if (write_post) bwd_chunk_kernel<Z, false, true><<<grid, block, 0, s->stream>>>(A);
-  else bwd_chunk_kernel<Z, false, false><<<grid, block, 0, s->stream>>>(A);
+  if (s->legacy_py) bwd_chunk_kernel<Z, true, false><<<grid, block, 0, st>>>(A);
+  else if (write_post) bwd_chunk_kernel<Z, false, true><<<grid, block, 0, st>>>(A);
+  else bwd_chunk_kernel<Z, false, false><<<grid, block, 0, st>>>(A);
 }
 
 template <int Z>
-static void launch_fwd_ws(const titan_solver *s, const FbArgs &A) {
+static void launch_fwd_ws(const titan_solver *s, const FbArgs &A, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
   const size_t smem = ws_fwd_smem<Z>();
   if (s->legacy_py) {
     if (!attr_set[1]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
-    fwd_chunk_ws_kernel<Z, true><<<A.nChunks, 128, smem, s->stream>>>(A);
+    fwd_chunk_ws_kernel<Z, true><<<A.nChunks, 128, smem, st>>>(A);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
-    fwd_chunk_ws_kernel<Z, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+    fwd_chunk_ws_kernel<Z, false><<<A.nChunks, 128, smem, st>>>(A);
   }
 }
 
 template <int Z>
-static void launch_bwd_ws(const titan_solver *s, const FbArgs &A, bool write_post) {
+static void launch_bwd_ws(const titan_solver *s, const FbArgs &A, bool write_post, cudaStream_t st) {
   static bool attr_set[3] = {false, false, false};
   const size_t smem = ws_bwd_smem<Z>();
   if (s->legacy_py) {
     if (!attr_set[2]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[2] = true; }
-    bwd_chunk_ws_kernel<Z, true, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+    bwd_chunk_ws_kernel<Z, true, false><<<A.nChunks, 128, smem, st>>>(A);
   } else if (write_post) {
     if (!attr_set[1]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
-    bwd_chunk_ws_kernel<Z, false, true><<<A.nChunks, 128, smem, s->stream>>>(A);
+    bwd_chunk_ws_kernel<Z, false, true><<<A.nChunks, 128, smem, st>>>(A);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
-    bwd_chunk_ws_kernel<Z, false, false><<<A.nChunks, 128, smem, s->stream>>>(A);
+    bwd_chunk_ws_kernel<Z, false, false><<<A.nChunks, 128, smem, st>>>(A);
   }
-}
-
-template <int Z>
-static void launch_solve(const titan_solver *s, const FbArgs &A, bool backward) {
-  if (backward) boundary_solve_kernel<Z, -1><<<s->nChr, 32, 0, s->stream>>>(A, s->chr_chunk0.p);
-  else boundary_solve_kernel<Z, 1><<<s->nChr, 32, 0, s->stream>>>(A, s->chr_chunk0.p);
 }
 
 #define Z_DISPATCH(Zv, CALL)            \
@@ -560,74 +546,63 @@ static void launch_solve(const titan_solver *s, const FbArgs &A, bool backward) 
     default: break;                     \
   }
 
-// runs verification rounds of one direction until no chunk had to be re-run
-static int run_rounds(titan_solver *s, FbArgs &A, bool backward, bool write_post, int *rounds_out, int64_t *runs_out) {
-  unsigned int *ctr = s->rerun.p + (backward ? kRoundSlots : 0);
-  unsigned int *ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
-  const int hard_cap = std::min(kRoundSlots - 1, 2 * s->maxChunksPerChr + 4);
-  CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 1), s->stream));
-  A.rerun = ctr;
-  A.startv = backward ? s->startb.p : s->startf.p;
-  A.endv = backward ? s->endb.p : s->endf.p;
+// One direction of the chunked scan: round 0, then verification rounds until a round re-runs nothing.
+// The object only LAUNCHES; the caller drives both directions so that their (latency-bound)
+// verification rounds can overlap on two streams.
+struct Direction {
+  titan_solver *s;
+  FbArgs A;
+  bool backward, write_post;
+  cudaStream_t st;
+  unsigned int *ctr, *ctr_h;
+  int round = 0, hard_cap = 0;
   int64_t runs = 0;
-  int r = 0;
-  auto launch = [&](int round) {
-    A.round = round;
+  bool done = false;
+
+  void launch(int r) {
+    A.round = r;
     // round 0 with many chunks is throughput-bound: one warp per chunk.  Verification rounds (few
     // chunks re-run) and the plain sequential mode are latency-bound: one warp-specialised CTA per chunk.
-    const bool ws = s->ws_mode == 2 || (s->ws_mode == 1 && (round > 0 || s->nChunks < 4 * 148));
+    const bool ws = s->ws_mode == 2 || (s->ws_mode == 1 && (r > 0 || s->nChunks < 4 * 148));
     if (backward) {
-      if (ws) { Z_DISPATCH(s->Z, launch_bwd_ws<ZZ>(s, A, write_post)); }
-      else { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post)); }
+      if (ws) { Z_DISPATCH(s->Z, launch_bwd_ws<ZZ>(s, A, write_post, st)); }
+      else { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post, st)); }
     } else {
-      if (ws) { Z_DISPATCH(s->Z, launch_fwd_ws<ZZ>(s, A)); }
-      else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A)); }
+      if (ws) { Z_DISPATCH(s->Z, launch_fwd_ws<ZZ>(s, A, st)); }
+      else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A, st)); }
     }
     s->tm.kernel_launches++;
-  };
-  cudaEvent_t e0 = s->ev[backward ? 8 : 6], e1 = s->ev[backward ? 9 : 7];
-  const int dir = backward ? 1 : 0;
-  A.solved = nullptr;
-  A.solved_w = s->solved[dir].p;
-  A.histQ = s->histQ[dir].p;
-  A.histE = s->histE[dir].p;
-  A.histLL = s->histLL[dir].p;
-  A.hist_n = s->hist_n[dir].p;
-  A.accel_tol = s->accel_tol;
-  CK(cudaMemsetAsync(A.hist_n, 0, sizeof(int) * (size_t)s->nChunks, s->stream));
-  CK(cudaEventRecord(e0, s->stream));
-  launch(0);
-  CK(cudaEventRecord(e1, s->stream));
-  CK(cudaGetLastError());
-  if (s->maxChunksPerChr <= 1) {   // plain sequential recursion: nothing to verify
-    *rounds_out = 1;
-    *runs_out = s->nChunks;
+  }
+  void start(cudaEvent_t e0, cudaEvent_t e1) {
+    ctr = s->rerun.p + (backward ? kRoundSlots : 0);
+    ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
+    hard_cap = std::min(kRoundSlots - 1, s->maxChunksPerChr + 2);
+    CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 1), st));
+    A.rerun = ctr;
+    A.startv = backward ? s->startb.p : s->startf.p;
+    A.endv = backward ? s->endb.p : s->endf.p;
+    CK(cudaEventRecord(e0, st));
+    launch(0);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaGetLastError());
+    runs = s->nChunks;
+    round = 0;
+    done = s->maxChunksPerChr <= 1;      // plain sequential recursion: nothing to verify
+  }
+  void next_round() {                    // launch one verification round and queue the read-back of its counter
+    ++round;
+    launch(round);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctr_h + round, ctr + round, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  }
+  int finish_round() {                   // after the stream has been synchronised
+    if (ctr_h[round] == 0) done = true;
+    else runs += ctr_h[round];
+    if (!done && round >= hard_cap)
+      return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
     return TITAN_OK;
   }
-  runs = s->nChunks;
-  for (r = 1; r <= hard_cap; ++r) {
-    // every accel_every-th round the chunk starts come from the history-based boundary solve
-    // instead of the neighbour's last end vector; verification always uses actual end vectors.
-    const bool solve = s->accel && r >= s->accel_every && (r % s->accel_every) == 0 && (r / s->accel_every) <= s->accel_max;
-    if (solve) {
-      A.round = r;
-      Z_DISPATCH(s->Z, launch_solve<ZZ>(s, A, backward));
-      s->tm.kernel_launches++;
-      A.solved = s->solved[dir].p;
-    }
-    launch(r);
-    A.solved = nullptr;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctr_h + r, ctr + r, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    if (ctr_h[r] == 0 && !solve) break;   // a round that re-ran nothing against ACTUAL end vectors: fixed point
-    runs += ctr_h[r];
-  }
-  if (r > hard_cap) return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
-  *rounds_out = r + 1;
-  *runs_out = runs;
-  return TITAN_OK;
-}
+};
 
 static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o, bool want_post, double *loggamma_out) {
   const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
@@ -663,15 +638,62 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   A.rhoZ = (post && !s->legacy_py) ? s->rhoZ.p : nullptr;
   A.loggamma = (s->legacy_py && loggamma_out) ? s->loggamma.p : nullptr;
 
+  // Forward and backward recursions are independent chains (only the posteriors need both), so the
+  // backward BOUNDARY rounds (beta only) run concurrently with the forward rounds on a second
+  // stream; a final backward pass from the verified boundaries forms posteriors and statistics.
+  const bool chunked = s->maxChunksPerChr > 1;
+  const bool overlap = chunked && s->overlap != 0;
+  A.beta_only = 0;
+  A.final_pass = 0;
+  Direction F{s, A, false, false, s->stream}, B{s, A, true, post, overlap ? s->stream_b : s->stream};
   CK(cudaEventRecord(s->ev[0], s->stream));
-  int fr = 0, br = 0;
-  int64_t fruns = 0, bruns = 0;
-  rc = run_rounds(s, A, false, false, &fr, &fruns);
-  if (rc != TITAN_OK) return rc;
-  CK(cudaEventRecord(s->ev[1], s->stream));
-  rc = run_rounds(s, A, true, post, &br, &bruns);
-  if (rc != TITAN_OK) return rc;
+  if (overlap) {
+    CK(cudaEventRecord(s->ev_sync[0], s->stream));             // model constants are uploaded on the main stream
+    CK(cudaStreamWaitEvent(s->stream_b, s->ev_sync[0], 0));
+    B.A.beta_only = 1;
+    F.start(s->ev[6], s->ev[7]);
+    B.start(s->ev[8], s->ev[9]);
+    while (!F.done || !B.done) {
+      const bool f = !F.done, b = !B.done;
+      if (f) F.next_round();
+      if (b) B.next_round();
+      if (f) CK(cudaStreamSynchronize(F.st));
+      if (b) CK(cudaStreamSynchronize(B.st));
+      if (f && (rc = F.finish_round()) != TITAN_OK) return rc;
+      if (b && (rc = B.finish_round()) != TITAN_OK) return rc;
+    }
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    CK(cudaEventRecord(s->ev_sync[1], s->stream_b));
+    CK(cudaStreamWaitEvent(s->stream, s->ev_sync[1], 0));
+    // final pass: every chunk once from its verified boundary vector (one warp per chunk, all chunks)
+    B.st = s->stream;
+    B.A.beta_only = 0;
+    B.A.final_pass = 1;
+    B.A.round = B.round + 1;
+    CK(cudaEventRecord(s->ev[8], s->stream));
+    Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, B.A, post, s->stream));
+    CK(cudaEventRecord(s->ev[9], s->stream));
+    s->tm.kernel_launches++;
+    CK(cudaGetLastError());
+    B.runs += s->nChunks;
+  } else {
+    F.start(s->ev[6], s->ev[7]);
+    while (!F.done) {
+      F.next_round();
+      CK(cudaStreamSynchronize(F.st));
+      if ((rc = F.finish_round()) != TITAN_OK) return rc;
+    }
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    B.start(s->ev[8], s->ev[9]);
+    while (!B.done) {
+      B.next_round();
+      CK(cudaStreamSynchronize(B.st));
+      if ((rc = B.finish_round()) != TITAN_OK) return rc;
+    }
+  }
   CK(cudaEventRecord(s->ev[2], s->stream));
+  const int fr = F.round + 1, br = B.round + 1;
+  const int64_t fruns = F.runs, bruns = B.runs;
   const int width = 6 * K;
   {
     dim3 g1((width + 127) / 128, s->nSlices);

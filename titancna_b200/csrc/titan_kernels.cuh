@@ -134,8 +134,6 @@ __device__ __forceinline__ double emission_from_py(const double *__restrict__ py
   return m;
 }
 
-constexpr int kHist = 4;
-
 struct FbArgs {
   const SnpRec *snp;          // [N]
   const TxnRec *txn;          // [N]
@@ -144,11 +142,8 @@ struct FbArgs {
   int U;
   int warm;                   // warm-up length (SNPs) for speculative chunk starts
   int round;                  // 0 = first pass; >0 = verification / re-run pass
-  const double *solved;       // round > 0: when non-null, chunk starts come from here instead of the neighbour's end vector
-  double *solved_w;           // boundary_solve_kernel output (same buffer)
-  double *histQ, *histE, *histLL;   // [nChunks][kHist][K], [nChunks][kHist][K], [nChunks][kHist]: last runs of each chunk
-  int *hist_n;                // [nChunks] runs recorded so far
-  double accel_tol;           // largest relative fit residual for which a solved start is trusted
+  int beta_only;              // backward kernels: recursion + boundary vectors only (no alpha reads, posteriors, sums)
+  int final_pass;             // backward kernels: every chunk runs once from its own verified start vector
   double rtol, atol;
   ModelConsts M;
   const unsigned char *het;   // [U]
@@ -282,21 +277,6 @@ __device__ __forceinline__ void bwd_step(double (&b)[Z], const double (&B)[Z], c
   for (int z = 0; z < Z; ++z) b[z] = (base + tr.k1 * red[z] + cw * bb[z]) * irs;
 }
 
-// append (start, end, log-scale) of a finished chunk run to the chunk's history ring
-template <int Z>
-__device__ __forceinline__ void record_history(const FbArgs &A, int chunk, int U, int lane, bool active, const double *startv,
-                                               const double (&endn)[Z], double ll) {
-  if (A.histQ == nullptr) return;
-  const int K = U * Z;
-  const int slot = A.hist_n[chunk] % kHist;
-  double *q = A.histQ + ((size_t)chunk * kHist + slot) * K, *e = A.histE + ((size_t)chunk * kHist + slot) * K;
-  if (active)
-#pragma unroll
-    for (int z = 0; z < Z; ++z) { q[lane + z * U] = startv[lane + z * U]; e[lane + z * U] = endn[z]; }
-  __syncwarp();
-  if (lane == 0) { A.histLL[(size_t)chunk * kHist + slot] = ll; A.hist_n[chunk] += 1; }
-}
-
 // ------------------------------------------------------------------------------------------
 // Forward pass over one chunk per warp.
 // reference recursion: src/fwd_backC_clonalCN.c:111-142 (log space, dense) -- here scaled linear
@@ -329,8 +309,7 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
       return;
     }
     double used[Z], want[Z];
-    const bool use_solved = A.solved != nullptr && A.solved[(size_t)warp * K] == A.solved[(size_t)warp * K];
-    const double *pe = use_solved ? A.solved + (size_t)warp * K : A.endv + prv + (size_t)(warp - 1) * K;
+    const double *pe = A.endv + prv + (size_t)(warp - 1) * K;
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       used[z] = active ? startv[lane + z * U] : 0.0;
@@ -464,12 +443,6 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
   }
   const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
   if (lane == 0) A.chunk_ll[warp] = ll;
-  if (c.t0 != c.cs) {
-    double endn[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endn[z] = a[z] * inv;
-    record_history<Z>(A, warp, U, lane, active, startv, endn, ll);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -497,7 +470,14 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   double b[Z];
   int tn;
   bool from_boundary;   // b[] was read from the next chunk's published boundary vector
-  if (A.round > 0) {
+  const bool beta_only = A.beta_only != 0;
+  if (A.final_pass && c.t1 != c.ce) {
+    // posterior pass after the boundaries are verified: start from my own (exact) boundary vector
+#pragma unroll
+    for (int z = 0; z < Z; ++z) b[z] = active ? startv[lane + z * U] : 0.0;
+    tn = c.t1;
+    from_boundary = true;
+  } else if (A.round > 0 && !A.final_pass) {
     if (c.t1 == c.ce) {
       if (active)
 #pragma unroll
@@ -505,8 +485,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
       return;
     }
     double used[Z], want[Z];
-    const bool use_solved = A.solved != nullptr && A.solved[(size_t)warp * K] == A.solved[(size_t)warp * K];
-    const double *pe = use_solved ? A.solved + (size_t)warp * K : A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
+    const double *pe = A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       used[z] = active ? startv[lane + z * U] : 0.0;
@@ -541,7 +520,6 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   TxnRec tr;           // transition between t and t+1
   double B[Z];         // B_{t+1}
   double mB = 0.0;     // its emission shift
-  double acc_s = 0.0;  // log-scale of the owned part of the recursion (history only)
   rs.get(0, rec, tr);
   if (tn < c.ce) {
     if (FROM_PY) mB = emission_from_py<Z>(A.py + (size_t)tn * K, U, lane, active, B);
@@ -601,13 +579,18 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     else mn = emission<Z>(L, recn, Bn);
     double al[Z];
 #pragma unroll
-    for (int z = 0; z < Z; ++z) al[z] = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
+    for (int z = 0; z < Z; ++z) al[z] = (active && !beta_only) ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
     if (t + 1 < c.ce) {
       int e;
       bwd_step<Z>(b, B, tr, het, active, e);
-      acc_s += mB + (double)e * 0.6931471805599453094;
     }
     mB = mn;
+    if (beta_only) {
+      tr = trn;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) B[z] = Bn[z];
+      continue;
+    }
     // ---- posterior gamma_t ~ alpha~_t * beta~_t ----
     double p[Z];
     double loc = 0.0;
@@ -667,9 +650,8 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
     if (active)
 #pragma unroll
       for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
-    if (c.t1 < c.ce) record_history<Z>(A, warp, U, lane, active, startv, endn, log(s_end) + acc_s);
   }
-  if (!FROM_PY && active) {
+  if (!FROM_PY && active && !beta_only) {
     double *dst = A.part + (size_t)warp * 6 * K;
 #pragma unroll
     for (int qq = 0; qq < 6; ++qq)
@@ -804,8 +786,7 @@ __global__ void __launch_bounds__(128) fwd_chunk_ws_kernel(FbArgs A) {
     bool skip = (c.t0 == c.cs);
     if (!skip) {
       double used[Z], want[Z];
-      const bool use_solved = A.solved != nullptr && A.solved[(size_t)chunk * K] == A.solved[(size_t)chunk * K];
-      const double *pe = use_solved ? A.solved + (size_t)chunk * K : A.endv + prv + (size_t)(chunk - 1) * K;
+      const double *pe = A.endv + prv + (size_t)(chunk - 1) * K;
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         used[z] = active ? startv[lane + z * U] : 0.0;
@@ -905,12 +886,6 @@ __global__ void __launch_bounds__(128) fwd_chunk_ws_kernel(FbArgs A) {
     for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = a[z] * inv;
   const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
   if (lane == 0) A.chunk_ll[chunk] = ll;
-  if (c.t0 != c.cs) {
-    double endn[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endn[z] = a[z] * inv;
-    record_history<Z>(A, chunk, U, lane, active, startv, endn, ll);
-  }
 }
 
 // backward: warp 0 = beta recursion, warp 1 = posteriors + statistics, warps 2-3 = emission producers
@@ -937,8 +912,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
     bool skip = (c.t1 == c.ce);
     if (!skip) {
       double used[Z], want[Z];
-      const bool use_solved = A.solved != nullptr && A.solved[(size_t)chunk * K] == A.solved[(size_t)chunk * K];
-      const double *pe = use_solved ? A.solved + (size_t)chunk * K : A.endv + prv + (size_t)(chunk + 1) * K;
+      const double *pe = A.endv + prv + (size_t)(chunk + 1) * K;
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         used[z] = active ? startv[lane + z * U] : 0.0;
@@ -980,10 +954,11 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
     ws_produce<Z, -1, FROM_PY>(A, L, ws_smem, F, warp - 2, 2, ntiles, n, tn, c.cs, c.ce - 1, lane, active);
     return;
   }
+  const bool beta_only = A.beta_only != 0;
+  if (warp == 1 && beta_only) return;
   if (warp == 0) {
     // ---------------- beta recursion ----------------
     const bool het = active && A.het[lane];
-    double acc_s = 0.0;   // log-scale of the owned part of the recursion (history only)
     int j = 0;
     for (int k = 0; k < ntiles; ++k) {
       const double *slot = ws_smem + (size_t)(k % NS) * SD;
@@ -991,7 +966,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
       const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
       double *bslot = bring + (size_t)(k % NSB) * BD;
       spin_until_eq(&F->full[k % NS], k + 1);
-      spin_until_ge(&F->bconsumed, k - NSB + 1);
+      if (!beta_only) spin_until_ge(&F->bconsumed, k - NSB + 1);
       const int ns = min(TS, n - k * TS);
       for (int s = 0; s < ns; ++s, ++j) {
         if (j == jb && c.t1 < c.ce) {   // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
@@ -1013,10 +988,10 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
           for (int z = 0; z < Z; ++z) B[z] = slot[(s * Z + z) * 32 + lane];
           int e;
           bwd_step<Z>(b, B, txs[s], het, active, e);
-          if (j >= jb) acc_s += ms[s] + (double)e * 0.6931471805599453094;
         }
+        if (!beta_only)
 #pragma unroll
-        for (int z = 0; z < Z; ++z) bslot[(s * Z + z) * 32 + lane] = b[z];
+          for (int z = 0; z < Z; ++z) bslot[(s * Z + z) * 32 + lane] = b[z];
       }
       __threadfence_block();
       __syncwarp();
@@ -1033,7 +1008,6 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
     if (active)
 #pragma unroll
       for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
-    if (c.t1 < c.ce) record_history<Z>(A, chunk, U, lane, active, startv, endn, log(s_end) + acc_s);
     return;
   }
   // ---------------- warp 1: posteriors + sufficient statistics ----------------
@@ -1111,170 +1085,6 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
     for (int qq = 0; qq < 6; ++qq)
 #pragma unroll
       for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Boundary acceleration from the round history.
-//
-// Fixed-point verification alone needs one round per chunk length of *forgetting time*: where two
-// states are nearly indistinguishable (two clonal clusters of close prevalence) a boundary vector
-// remembers ~10^4 SNPs, i.e. dozens of rounds, although after two or three rounds only a couple of
-// slow directions are still moving.  Every run of a chunk is a sample of its LINEAR transfer
-// operator: (start_i, end_i * exp(ll_i)) = (q_i, P_c q_i).  One warp per chromosome walks the chunk
-// boundaries: the true start a of chunk c is fitted in the affine span of the chunk's last kHist
-// starts (relative least squares) and pushed through P_c by the same combination of the recorded
-// ends -- a chain-wise Anderson step.  Solved starts go to a side buffer; the next round re-runs
-// the chunks whose start changed, and the ordinary verification against ACTUAL end vectors decides
-// when the scan is exact, so the extrapolation can only save rounds, never change the answer.
-// ------------------------------------------------------------------------------------------
-template <int Z, int DIR>
-__global__ void __launch_bounds__(32) boundary_solve_kernel(FbArgs A, const int *__restrict__ chr_chunk0) {
-  constexpr int R = kHist, M = R - 1;
-  const int chr = blockIdx.x, lane = threadIdx.x;
-  const int c_lo = chr_chunk0[chr], c_hi = chr_chunk0[chr + 1];   // chunks [c_lo, c_hi)
-  if (c_hi - c_lo < 2) return;
-  const int U = A.U, K = U * Z;
-  const bool active = lane < U;
-  const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;   // buffer holding the latest ACTUAL end vectors
-  int c = (DIR > 0) ? c_lo : c_hi - 1;
-  double a[Z];
-  bool trusted = true;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) a[z] = active ? A.endv[prv + (size_t)c * K + lane + z * U] : 0.0;   // exact (leading chunk)
-  for (int step = 1; step < c_hi - c_lo; ++step) {
-    c += DIR;
-    if (active)
-#pragma unroll
-      for (int z = 0; z < Z; ++z)
-        A.solved_w[(size_t)c * K + lane + z * U] = trusted ? a[z] : __longlong_as_double(0x7ff8000000000000LL);
-    if (step == c_hi - c_lo - 1) break;
-    const int nh = min(A.hist_n[c], R);
-    const double *Qc = A.histQ + (size_t)c * R * K, *Ec = A.histE + (size_t)c * R * K;
-    const double *LLc = A.histLL + (size_t)c * R;
-    const int ref = (A.hist_n[c] + R - 1) % R;            // most recent run = closest to the truth
-    double q0[Z], e0[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      q0[z] = active ? Qc[(size_t)ref * K + lane + z * U] : 0.0;
-      e0[z] = active ? Ec[(size_t)ref * K + lane + z * U] : 0.0;
-    }
-    const double ll0 = LLc[ref];
-    double amax = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) amax = fmax(amax, a[z]);
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    double d[M][Z], f[M][Z], r0[Z];
-    bool keep[M];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      const double wgt = (a[z] > 1e-280 * amax) ? 1.0 / a[z] : 0.0;
-      r0[z] = (a[z] - q0[z]) * wgt;
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        const int slot = (ref + R - 1 - i) % R;             // older runs
-        const bool have = (i + 1) < nh;
-        const double qi = (have && active) ? Qc[(size_t)slot * K + lane + z * U] : q0[z];
-        const double ei = (have && active) ? Ec[(size_t)slot * K + lane + z * U] * exp(LLc[slot] - ll0) : e0[z];
-        d[i][z] = (qi - q0[z]) * wgt;
-        f[i][z] = ei - e0[z];
-      }
-    }
-    double G[M][M], rhs[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) sacc += d[i][z] * r0[z];
-      rhs[i] = sacc;
-#pragma unroll
-      for (int j = i; j < M; ++j) {
-        double g = 0.0;
-#pragma unroll
-        for (int z = 0; z < Z; ++z) g += d[i][z] * d[j][z];
-        G[i][j] = g;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        rhs[i] += __shfl_xor_sync(0xffffffffu, rhs[i], o);
-#pragma unroll
-        for (int j = i; j < M; ++j) G[i][j] += __shfl_xor_sync(0xffffffffu, G[i][j], o);
-      }
-    }
-    // column-scaled Cholesky with a pivot floor: directions the history does not separate are dropped
-    double sc[M], y[M], t[M], Lc[M][M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) { keep[i] = G[i][i] > 1e-24; sc[i] = keep[i] ? rsqrt(G[i][i]) : 0.0; }
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        double sacc = G[j][i] * sc[i] * sc[j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) sacc -= Lc[i][k] * Lc[j][k];
-        if (j == i) {
-          if (!keep[i] || sacc < 1e-8) { keep[i] = false; Lc[i][i] = 1.0; }
-          else Lc[i][i] = sqrt(sacc);
-        } else {
-          Lc[i][j] = (keep[i] && keep[j]) ? sacc / Lc[j][j] : 0.0;
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      double sacc = keep[i] ? rhs[i] * sc[i] : 0.0;
-#pragma unroll
-      for (int k = 0; k < i; ++k) sacc -= Lc[i][k] * t[k];
-      t[i] = keep[i] ? sacc / Lc[i][i] : 0.0;
-    }
-#pragma unroll
-    for (int i = M - 1; i >= 0; --i) {
-      double sacc = t[i];
-#pragma unroll
-      for (int k = i + 1; k < M; ++k) sacc -= Lc[k][i] * y[k];
-      y[i] = keep[i] ? (sacc / Lc[i][i]) * sc[i] : 0.0;
-    }
-    // accept the extrapolation only when the start really lies in the span of the history
-    // (max relative residual below A.rtol-ish) and the combination is tame; otherwise this chunk
-    // is left to the plain fixed-point update and the walk restarts from its latest actual end.
-    double resid = 0.0, ymax = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      double rr = r0[z];
-#pragma unroll
-      for (int i = 0; i < M; ++i) rr -= y[i] * d[i][z];
-      resid = fmax(resid, fabs(rr));
-    }
-#pragma unroll
-    for (int i = 0; i < M; ++i) ymax = fmax(ymax, fabs(y[i]));
-    for (int o = 16; o > 0; o >>= 1) resid = fmax(resid, __shfl_xor_sync(0xffffffffu, resid, o));
-    double nxt[Z];
-    double loc = 0.0;
-    bool bad = !(resid <= A.accel_tol) || !(ymax <= 1e4);
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      double v = e0[z];
-#pragma unroll
-      for (int i = 0; i < M; ++i) v += y[i] * f[i][z];
-      bad |= !(v >= 0.0) || (v == 0.0 && e0[z] > 0.0);
-      nxt[z] = v;
-      loc += v;
-    }
-    trusted = !__any_sync(0xffffffffu, bad);
-    if (!trusted) {
-      // not trustworthy: the next chunk keeps the plain fixed-point update (its solved start is
-      // poisoned, the main kernel then uses this chunk's actual end vector); the walk continues
-      // from that actual end
-      loc = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) { nxt[z] = active ? A.endv[prv + (size_t)c * K + lane + z * U] : 0.0; loc += nxt[z]; }
-    }
-    const double inv = 1.0 / warp_sum(loc);
-#pragma unroll
-    for (int z = 0; z < Z; ++z) a[z] = nxt[z] * inv;
   }
 }
 
