@@ -26,7 +26,7 @@ def test_results_and_segments_match_loop_restatement(Z, s):
         a = np.asarray(res[k], float)
         b = np.array([r[k] for r in rows], float)
         assert np.array_equal(np.isnan(a), np.isnan(b)), k
-        assert np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-14, atol=0), k   # numpy SIMD vs libm exp/log2: <= 2 ulp
+        assert np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-13, atol=1e-15), k   # numpy SIMD vs libm exp/log2: 1 ulp before the log2(exp(x)) cancellation
     assert list(res["TITANcall"]) == [r["TITANcall"] for r in rows]
     segs = R.outputTitanSegments(res, "test", cp)
     want = RO.output_segments(rows, "test")
