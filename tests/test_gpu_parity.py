@@ -182,7 +182,17 @@ def test_em_production_settings_synthetic():
     for k in ("n", "phi", "s", "var"):
         assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < POST_ATOL, k
     assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=LL_RTOL, atol=0)
-    assert np.array_equal(T.viterbiClonalCN(data, got), O.viterbi_clonal_cn(data, want, engine="port", threads=8))
+    gpath = T.viterbiClonalCN(data, got)
+    wpath = O.viterbi_clonal_cn(data, want, engine="port", threads=8)
+    assert np.array_equal(gpath, wpath)
+    # segment calls bit-exact (north_star): decode + segmenter on both paths
+    from oracle import results_oracle as RO
+    segs = T.outputTitanSegments(T.outputTitanResults(data, got, gpath), "synthetic", got)
+    wsegs = RO.output_segments(RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, want, wpath), "synthetic")
+    assert segs["Length.snp."].size == len(wsegs)
+    for k in ("Start_Position.bp.", "End_Position.bp.", "Length.snp.", "TITAN_state", "Copy_Number", "MinorCN", "MajorCN"):
+        assert np.array_equal(np.asarray(segs[k], float), np.array([w[k] for w in wsegs], float)), k
+    assert list(segs["TITAN_call"]) == [w["TITAN_call"] for w in wsegs]
 
 
 def test_chunked_scan_equals_sequential_recursion_at_scale():
