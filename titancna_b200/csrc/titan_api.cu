@@ -803,7 +803,15 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   if (const char *e = getenv("TITAN_VIT_P")) P = std::max(1, std::min(32, atoi(e)));
   while (P > 1 && K * P > 1024) P >>= 1;
   const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);   // >= 2K so two loads per thread cover a 4K-entry table
-  const size_t smem = sizeof(double) * 13 * (size_t)K;
+  const size_t smem = sizeof(double) * 13 * (size_t)K + sizeof(unsigned short) * (size_t)((K + P - 1) / P) * threads;
+  if (smem > 48 * 1024) {
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[s->legacy_py ? 1 : 0]) {
+      if (s->legacy_py) cudaFuncSetAttribute(viterbi_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      else cudaFuncSetAttribute(viterbi_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_set[s->legacy_py ? 1 : 0] = true;
+    }
+  }
   CK(cudaEventRecord(s->ev[4], s->stream));
   // the structured step costs O(K*Z) per SNP but runs in Z warps; measured crossover with the dense sliced scan is K ~ 120
   const bool structured = (s->vit_mode == 1 || (s->vit_mode < 0 && K >= 120)) && s->Z * 32 <= 256;

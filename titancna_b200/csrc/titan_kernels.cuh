@@ -1199,6 +1199,17 @@ __global__ void __launch_bounds__(1024) viterbi_forward_kernel(VitArgs A, int P)
   const bool lead = on && p == 0;
   const int per = (K + P - 1) / P;
   const int i0 = min(p * per, K), i1 = min(i0 + per, K);
+  const int nthr = blockDim.x;
+  const int cnt = on ? max(i1 - i0, 0) : 0;
+  unsigned short *offs = reinterpret_cast<unsigned short *>(sm + 13 * K);   // [per][blockDim]
+  {
+    int gi = i0 % U, zi = i0 / U;
+    for (int n = 0; n < cnt; ++n) {
+      const int cls = ((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0);
+      offs[n * nthr + tid] = (unsigned short)(cls * K + i0 + n);
+      if (++gi == U) { gi = 0; ++zi; }
+    }
+  }
   double lmu = 0, l1mu = 0, muC = 0, cN = 0, tv = 1;
   if (lead && !FROM_PY) {
     lmu = A.M.lmu[j]; l1mu = A.M.l1mu[j]; muC = A.M.muC[j]; cN = A.M.cN[gj]; tv = A.M.tv[gj];
@@ -1246,16 +1257,13 @@ __global__ void __launch_bounds__(1024) viterbi_forward_kernel(VitArgs A, int P)
     // phase B
     double best = -CUDART_INF;
     int arg = 0x7fffffff;
-    if (on && i0 < i1) {
-      int gi = i0 % U, zi = i0 / U;
-      best = v[(((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0)) * K + i0];
+    if (cnt > 0) {
+      // offs[n] = class(i0+n, j)*K + (i0+n): step-invariant, tabulated once before the loop
+      best = v[offs[tid]];
       arg = i0;
-      if (++gi == U) { gi = 0; ++zi; }
-      for (int i = i0 + 1; i < i1; ++i) {
-        const int cls = ((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0);
-        const double cand = v[cls * K + i];
-        if (best < cand) { best = cand; arg = i; }
-        if (++gi == U) { gi = 0; ++zi; }
+      for (int n = 1; n < cnt; ++n) {
+        const double cand = v[offs[n * nthr + tid]];
+        if (best < cand) { best = cand; arg = i0 + n; }
       }
     }
     for (int o = 1; o < P; o <<= 1) {
