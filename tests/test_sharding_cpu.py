@@ -27,6 +27,17 @@ def test_lpt_assignment_balances_the_sweep():
     assert load1[0] == costs.sum()
 
 
+def test_sweep_runs_every_solution_once_with_and_without_host_concurrency():
+    data, _ = synth.make_data(600, Z=2, maxCN=5, n_chr=3, seed=2)
+    seen = []
+    run_one = lambda d, p, **kw: (seen.append((p["ploidyParams"]["phi_0"], len(p["cellPrevParams"]["s_0"]))) or {"ok": True})
+    for conc in (1, 3):
+        seen.clear()
+        out, info = sweep.run_sweep(data, 0, 1, run_one=run_one, gather=False, concurrent=conc)
+        assert len(out) == 15 and sorted(seen) == sorted((float(p), z) for p in (2, 3, 4) for z in (1, 2, 3, 4, 5))
+        assert [(o["ploidy_0"], o["numClusters"]) for o in out] == [(p, z) for p in (2, 3, 4) for z in (1, 2, 3, 4, 5)]
+
+
 def test_chromosome_shards_cover_the_genome():
     data, _ = synth.make_data(5000, Z=2, maxCN=5, n_chr=23, seed=2)
     for world in (1, 2, 4, 8):

@@ -157,6 +157,7 @@ struct titan_solver {
   DevBuf<double> ltab;
   DevBuf<unsigned char> psi;
   bool vit_ready = false;
+  bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
 
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   titan_timing tm{};
@@ -403,6 +404,7 @@ extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup
     if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
     CK(cudaSetDevice(s->device));
     build_chunks(s);
+    s->state_valid = false;
   } catch (const CudaFail &f) {
     return f.code;
   }
@@ -604,12 +606,21 @@ struct Direction {
   }
 };
 
-static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o, bool want_post, double *loggamma_out) {
+// posterior_only: the parameters are those of the previous call, whose forward variables and verified
+// backward boundaries are still resident -- only the final backward pass is run again, now writing
+// the N-sized marginals (what runEMclonalCN returns as rhoG / rhoZ of its last E-step).
+static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o, bool want_post, double *loggamma_out,
+                      bool posterior_only = false) {
   const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
   const int64_t N = s->N;
   CK(cudaSetDevice(s->device));
-  int rc = upload_model(s, p, o ? o->muR : nullptr, o ? o->muC : nullptr);
-  if (rc != TITAN_OK) return rc;
+  int rc = TITAN_OK;
+  posterior_only = posterior_only && s->state_valid;
+  s->state_valid = false;
+  if (!posterior_only) {
+    rc = upload_model(s, p, o ? o->muR : nullptr, o ? o->muC : nullptr);
+    if (rc != TITAN_OK) return rc;
+  }
   const bool post = want_post || (o && (o->rhoG || o->rhoZ));
   if (post && !s->legacy_py) {
     if (s->rhoG.n < (size_t)N * U) s->rhoG.alloc((size_t)N * U);
@@ -647,7 +658,23 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   A.final_pass = 0;
   Direction F{s, A, false, false, s->stream}, B{s, A, true, post, overlap ? s->stream_b : s->stream};
   CK(cudaEventRecord(s->ev[0], s->stream));
-  if (overlap) {
+  if (posterior_only) {
+    B.st = s->stream;
+    B.A.rerun = s->rerun.p + kRoundSlots;
+    B.A.startv = s->startb.p;
+    B.A.endv = s->endb.p;
+    B.A.final_pass = 1;
+    B.A.round = 0;
+    CK(cudaEventRecord(s->ev[6], s->stream));
+    CK(cudaEventRecord(s->ev[7], s->stream));
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    CK(cudaEventRecord(s->ev[8], s->stream));
+    Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, B.A, post, s->stream));
+    CK(cudaEventRecord(s->ev[9], s->stream));
+    s->tm.kernel_launches++;
+    CK(cudaGetLastError());
+    B.runs = s->nChunks;
+  } else if (overlap) {
     CK(cudaEventRecord(s->ev_sync[0], s->stream));             // model constants are uploaded on the main stream
     CK(cudaStreamWaitEvent(s->stream_b, s->ev_sync[0], 0));
     B.A.beta_only = 1;
@@ -730,6 +757,7 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   }
   if (loggamma_out && s->legacy_py)
     CK(cudaMemcpy(loggamma_out, s->loggamma.p, sizeof(double) * (size_t)N * K, cudaMemcpyDeviceToHost));
+  s->state_valid = !s->legacy_py;
   return TITAN_OK;
 }
 
@@ -1072,12 +1100,13 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
     }
     out->iters = i + 1;
     // rhoG / rhoZ of the last executed E-step (R/hmmClonal.R:356-357): the per-iteration passes do not
-    // write the N-sized marginals, so that E-step is repeated once with the output switched on.
+    // write the N-sized marginals; its forward variables and verified boundaries are still resident,
+    // so only the final backward pass is repeated with the output switched on.
     if (o->want_posteriors && have_last && (out->rhoG || out->rhoZ)) {
       titan_estep_out eo{};
       eo.rhoG = out->rhoG;
       eo.rhoZ = out->rhoZ;
-      rc = estep_impl(s, &last_p, &eo, true, nullptr);
+      rc = estep_impl(s, &last_p, &eo, true, nullptr, /*posterior_only=*/true);
       if (rc != TITAN_OK) return rc;
       out->estep_ms += s->tm.last_estep_ms;
     }

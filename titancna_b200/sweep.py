@@ -165,7 +165,7 @@ def runEMclonalCN_sharded(data, params, rank, world, txnExpLen=1e15, txnZstrengt
 
 
 def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), maxCN=8, device=None, make_params=None,
-              run_one=None, gather=True, **em_kwargs):
+              run_one=None, gather=True, concurrent=1, **em_kwargs):
     """The snakemake sweep in one job: rank r runs the solutions LPT assigns to it and the final parameter sets
     are gathered (all_gather_object) -- no collective on the data path.  `run_one(data, params, **em_kwargs)` defaults
     to runEMclonalCN + viterbiClonalCN on this rank's GPU."""
@@ -183,10 +183,19 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
             path = viterbiClonalCN(d, cp)
             return {"n": cp["n"][-1], "phi": cp["phi"][-1], "s": cp["s"][:, -1], "loglik": cp["loglik"][-1],
                     "iters": cp["n"].size - 1, "path": path}
-    out = []
-    for ploidy, Z in mine:
-        res = run_one(data, make_params(ploidy, Z), **em_kwargs)
-        out.append({"ploidy_0": ploidy, "numClusters": Z, **res})
+    # `concurrent` > 1 runs that many of this rank's solutions at once (one host thread and one pair of CUDA
+    # streams each; ctypes releases the GIL): the verification rounds of one solution are latency-bound and
+    # leave most SMs idle, which a second solution's rounds fill.
+    def one(pz):
+        ploidy, Z = pz
+        return {"ploidy_0": ploidy, "numClusters": Z, **run_one(data, make_params(ploidy, Z), **em_kwargs)}
+
+    if concurrent > 1 and len(mine) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=int(concurrent)) as ex:
+            out = list(ex.map(one, mine))
+    else:
+        out = [one(pz) for pz in mine]
     if gather and world > 1:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
