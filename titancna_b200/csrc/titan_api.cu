@@ -143,6 +143,7 @@ struct titan_solver {
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
   DevBuf<int> chr_chunk0;          // [nChr+1]
   int overlap = 1;                 // run the forward and the backward boundary rounds concurrently on two streams
+  int round_batch = 4;             // verification rounds queued per host synchronisation
   cudaStream_t stream_b = nullptr; // second stream (backward boundary rounds)
   cudaEvent_t ev_sync[2] = {nullptr, nullptr};
   DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
@@ -255,6 +256,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
   if (const char *e = getenv("TITAN_OVERLAP")) s->overlap = atoi(e);
+  if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -578,8 +580,8 @@ struct Direction {
   void start(cudaEvent_t e0, cudaEvent_t e1) {
     ctr = s->rerun.p + (backward ? kRoundSlots : 0);
     ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
-    hard_cap = std::min(kRoundSlots - 1, s->maxChunksPerChr + 2);
-    CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 1), st));
+    hard_cap = std::min(kRoundSlots - 8, s->maxChunksPerChr + 2);
+    CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 8), st));
     A.rerun = ctr;
     A.startv = backward ? s->startb.p : s->startf.p;
     A.endv = backward ? s->endb.p : s->endf.p;
@@ -591,15 +593,24 @@ struct Direction {
     round = 0;
     done = s->maxChunksPerChr <= 1;      // plain sequential recursion: nothing to verify
   }
-  void next_round() {                    // launch one verification round and queue the read-back of its counter
-    ++round;
-    launch(round);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctr_h + round, ctr + round, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  // Queue up to `batch` verification rounds and the read-back of their counters.  A round whose
+  // predecessor re-ran nothing exits at once on the device, so queueing past the fixed point is cheap
+  // and the host synchronises once per batch instead of once per round.
+  int queued = 0;
+  void next_rounds(int batch) {
+    queued = std::max(1, std::min(batch, hard_cap - round));
+    for (int q = 1; q <= queued; ++q) {
+      launch(round + q);
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(ctr_h + round + 1, ctr + round + 1, sizeof(unsigned int) * (size_t)queued, cudaMemcpyDeviceToHost, st));
   }
-  int finish_round() {                   // after the stream has been synchronised
-    if (ctr_h[round] == 0) done = true;
-    else runs += ctr_h[round];
+  int finish_rounds() {                  // after the stream has been synchronised
+    for (int q = 1; q <= queued; ++q) {
+      ++round;
+      if (ctr_h[round] == 0) { done = true; break; }
+      runs += ctr_h[round];
+    }
     if (!done && round >= hard_cap)
       return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
     return TITAN_OK;
@@ -682,12 +693,12 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
     B.start(s->ev[8], s->ev[9]);
     while (!F.done || !B.done) {
       const bool f = !F.done, b = !B.done;
-      if (f) F.next_round();
-      if (b) B.next_round();
+      if (f) F.next_rounds(s->round_batch);
+      if (b) B.next_rounds(s->round_batch);
       if (f) CK(cudaStreamSynchronize(F.st));
       if (b) CK(cudaStreamSynchronize(B.st));
-      if (f && (rc = F.finish_round()) != TITAN_OK) return rc;
-      if (b && (rc = B.finish_round()) != TITAN_OK) return rc;
+      if (f && (rc = F.finish_rounds()) != TITAN_OK) return rc;
+      if (b && (rc = B.finish_rounds()) != TITAN_OK) return rc;
     }
     CK(cudaEventRecord(s->ev[1], s->stream));
     CK(cudaEventRecord(s->ev_sync[1], s->stream_b));
@@ -706,16 +717,16 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   } else {
     F.start(s->ev[6], s->ev[7]);
     while (!F.done) {
-      F.next_round();
+      F.next_rounds(s->round_batch);
       CK(cudaStreamSynchronize(F.st));
-      if ((rc = F.finish_round()) != TITAN_OK) return rc;
+      if ((rc = F.finish_rounds()) != TITAN_OK) return rc;
     }
     CK(cudaEventRecord(s->ev[1], s->stream));
     B.start(s->ev[8], s->ev[9]);
     while (!B.done) {
-      B.next_round();
+      B.next_rounds(s->round_batch);
       CK(cudaStreamSynchronize(B.st));
-      if ((rc = B.finish_round()) != TITAN_OK) return rc;
+      if ((rc = B.finish_rounds()) != TITAN_OK) return rc;
     }
   }
   CK(cudaEventRecord(s->ev[2], s->stream));

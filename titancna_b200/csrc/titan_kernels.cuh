@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= A.nChunks) return;
+  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
   const Chunk c = A.chunks[warp];
   const int U = A.U, K = U * Z;
   const bool active = lane < U;
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= A.nChunks) return;
+  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
   const Chunk c = A.chunks[warp];
   const int U = A.U, K = U * Z;
   const bool active = lane < U;
@@ -771,6 +773,7 @@ __global__ void __launch_bounds__(128) fwd_chunk_ws_kernel(FbArgs A) {
   extern __shared__ __align__(16) double ws_smem[];
   WsFlags *F = reinterpret_cast<WsFlags *>(ws_smem + NS * SD);
   const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
   const Chunk c = A.chunks[chunk];
   const int U = A.U, K = U * Z;
   const bool active = lane < U;
@@ -897,6 +900,7 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
   double *bring = ws_smem + NS * SD;
   WsFlags *F = reinterpret_cast<WsFlags *>(bring + NSB * BD);
   const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
   const Chunk c = A.chunks[chunk];
   const int U = A.U, K = U * Z;
   const bool active = lane < U;
