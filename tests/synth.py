@@ -28,7 +28,7 @@ def _mixture(rt, ct, n, s, phi, rn=0.5):
 
 
 def make_data(N, Z=3, maxCN=8, n_chr=23, seed=20261019, mean_seg=5000, n=0.3, phi=2.0, depth_mean=60,
-              logr_sd=0.15, exome=False, haplotype_bins=False):
+              logr_sd=0.15, exome=False, haplotype_bins=False, bin_size=100000):
     """-> (data dict with chr/posn/ref/tumDepth/logR, truth dict).  chr is an int array 1..n_chr."""
     rng = np.random.default_rng(seed)
     lens = np.array(HG19_LEN[:n_chr], dtype=np.float64)
@@ -74,7 +74,7 @@ def make_data(N, Z=3, maxCN=8, n_chr=23, seed=20261019, mean_seg=5000, n=0.3, ph
     ref = np.maximum(ref, depth - ref)                      # symmetric mode (R/utils.R:186-187)
     logR = rng.normal(muC[gu, gz], logr_sd)
     if haplotype_bins:                                      # 10X haplotype-block mode (R/haplotype.R:118-174)
-        key = chr_.astype(np.int64) * 100000 + posn // 100000
+        key = chr_.astype(np.int64) * 100000 + posn // bin_size
         _, inv = np.unique(key, return_inverse=True)
         ref = np.bincount(inv, weights=ref)[inv]
         depth = np.bincount(inv, weights=depth)[inv]

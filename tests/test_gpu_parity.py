@@ -308,3 +308,30 @@ def test_r_call_glue_is_a_drop_in_for_the_reference_so(golden):
     assert abs(got["loglik"] - want["loglik"]) <= 1e-11 * abs(want["loglik"])
     assert np.abs(np.exp(got["rho"]) - np.exp(want["rho"])).max() < 1e-9
     assert gpath.dtype == np.int32 and np.array_equal(gpath, wpath)
+
+
+@pytest.mark.parametrize("mode", ["exome", "haplotype"])
+def test_baseline_config5_value_distributions(mode):
+    """BASELINE configs[4]: exome-like positions (SNPs clustered in ~200 bp intervals with gaps up to 1e6 bp, so
+    the transition terms span their whole range) and 10X haplotype-block counts (block sums: depths in the
+    thousands).  E-step, EM parameters and Viterbi path against the oracle."""
+    N, Z = 5000, 3
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=3, seed=31, mean_seg=300, exome=(mode == "exome"),
+                              haplotype_bins=(mode == "haplotype"), bin_size=2_000_000)
+    assert mode != "haplotype" or data["tumDepth"].max() > 1000
+    kw = dict(txnExpLen=1e15, txnZstrength=1.0, maxiter=2, maxiterUpdate=1500)
+
+    def params(mod):
+        p = mod(8, Z, data=data)
+        p["genotypeParams"]["alphaKHyper"][:] = 10000
+        p["genotypeParams"]["betaKHyper"][:] = 25
+        return p
+
+    want = O.run_em_clonal_cn(data, params(O.load_default_parameters), engine="port", threads=8, **kw)
+    got = T.runEMclonalCN(data, params(T.loadDefaultParameters), verbose=False, **kw)
+    assert got["n"].shape == want["n"].shape
+    for k in ("n", "phi", "s", "var"):
+        assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < POST_ATOL, k
+    assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=LL_RTOL, atol=0)
+    assert np.abs(got["rhoG"] - want["rhoG"]).max() < POST_ATOL
+    assert np.array_equal(T.viterbiClonalCN(data, got), O.viterbi_clonal_cn(data, want, engine="port", threads=8))
