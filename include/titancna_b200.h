@@ -51,6 +51,8 @@ int titan_set_device(int device);
  *    positions[T]       base-pair positions (ascending)
  *    zStrength          txnZstrength * txnExpLen ;  txnLen = txnExpLen
  *    useOutlier         0/1 (fwd_backC_clonalCN.c:224-247 semantics)
+ *    Layouts outside the structured kernels (outlier state, repeated zygosity keys, K % numClust != 0,
+ *    > 32 unit states) are served by dense O(K^2) kernels with the same semantics.
  * ---------------------------------------------------------------------------------------- */
 /* rho_out[K x T] receives LOG posteriors (log 0 = -inf where the reference holds a finite
  * ~-750: compare after exp), loglik_out[1] the chromosome log-likelihood. */

@@ -244,8 +244,6 @@ def test_edge_cases_and_errors():
     # error behaviour mirrors the reference's error() text / refuses what it does not cover
     with pytest.raises(T.TitanError, match="obslik must be"):
         T.fwd_back_clonalCN(np.zeros(4), np.zeros((3, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15)
-    with pytest.raises(T.TitanError, match="useOutlier"):
-        T.fwd_back_clonalCN(np.zeros(5), np.zeros((5, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15, 1)
     with pytest.raises(T.TitanError, match="positive"):
         T.Solver(data, g, 2, 0.0, 1.0)
 
@@ -335,3 +333,49 @@ def test_baseline_config5_value_distributions(mode):
     assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=LL_RTOL, atol=0)
     assert np.abs(got["rhoG"] - want["rhoG"]).max() < POST_ATOL
     assert np.array_equal(T.viterbiClonalCN(data, got), O.viterbi_clonal_cn(data, want, engine="port", threads=8))
+
+
+def _legacy_case(N, U_zs, Z, outlier, K=None, seed=0):
+    rng = np.random.default_rng(seed)
+    zs = np.asarray(U_zs, float)
+    K = (zs.size * Z + (1 if outlier else 0)) if K is None else K
+    posn = np.cumsum(rng.integers(1, 5000, size=N)).astype(float)
+    truth = np.repeat(rng.integers(0, K, size=N // 40 + 1), 40)[:N]
+    py = rng.normal(-6.0, 1.5, size=(K, N))
+    py[truth, np.arange(N)] += 5.0                       # a sharp, piecewise-constant signal
+    lp = np.log(rng.dirichlet(np.full(K, 5.0)))
+    return lp, py, zs, posn
+
+
+@pytest.mark.parametrize("name,zs,Z,outlier,K,txn,zst", [
+    ("outlier state", [0, 1, 2, -1, 4, 5, 6, 7, 8, 9, 10, 11], 2, 1, None, 1e15, 1e15),
+    ("outlier, one cluster", [0, 1, 2, -1, 4, 5], 1, 1, None, 1e9, 1e18),
+    ("repeated zygosity keys", [0, 1, 1, -1, 2, 2, 3], 3, 0, None, 1e15, 5e20),
+    ("K not a multiple of numClust", [0, 1, 2, -1, 4, 5], 2, 0, 13, 1e6, 1e6),
+    ("40 unit states", list(range(3)) + [-1] + list(range(4, 40)), 2, 0, None, 1e15, 1e15),
+])
+def test_generic_compatibility_path_matches_reference_semantics(name, zs, Z, outlier, K, txn, zst):
+    """Layouts the structured kernels do not cover go through the dense kernels: outlier state with the
+    C-level semantics of src/fwd_backC_clonalCN.c:224-247, repeated zygosity keys, odd K."""
+    lp, py, zs, posn = _legacy_case(1200, zs, Z, outlier, K)
+    want_rho, want_ll = O.fwd_back(lp, py, zs, Z, posn, zst, txn, outlier, engine="port")
+    want_path = O.viterbi(lp, py, zs, Z, posn, zst, txn, outlier, engine="port")
+    got = T.fwd_back_clonalCN(lp, py, np.zeros(zs.size), zs, Z, posn, zst, txn, outlier)
+    assert abs(got["loglik"] - want_ll) <= 1e-11 * abs(want_ll), name
+    assert np.abs(np.exp(got["rho"]) - np.exp(want_rho)).max() < 1e-9, name
+    path = T.viterbi_clonalCN(lp, py, np.zeros(zs.size), zs, Z, posn, zst, txn, outlier)
+    assert np.array_equal(path, want_path), name
+
+
+def test_dense_kernel_cross_checks_structured_kernels(monkeypatch, golden):
+    """The dense kernel assumes no structure at all: same inputs through both implementations."""
+    g, py, lp = _fixture(golden)
+    posn = golden["data_posn"].astype(float)
+    a = T.fwd_back_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, 1e15, 1e15, 0)
+    pa = T.viterbi_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, 1e15, 1e15, 0)
+    monkeypatch.setenv("TITAN_FORCE_DENSE", "1")
+    b = T.fwd_back_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, 1e15, 1e15, 0)
+    pb = T.viterbi_clonalCN(lp, py, g["ct"], g["ZS"], 2, posn, 1e15, 1e15, 0)
+    assert abs(a["loglik"] - b["loglik"]) <= 1e-12 * abs(b["loglik"])
+    assert np.abs(np.exp(a["rho"]) - np.exp(b["rho"])).max() < 1e-9
+    assert np.array_equal(pa, pb) and np.array_equal(pa, golden["ref_path_1e15"].astype(np.int32))

@@ -886,6 +886,132 @@ extern "C" int titan_viterbi(titan_solver *s, const titan_params *p, int32_t *pa
 // ---------------------------------------------------------------------------------------------
 // legacy-compatible entries (one chromosome, materialised log emissions)
 // ---------------------------------------------------------------------------------------------
+// ---- generic compatibility path: any layout the reference's C accepts (outlier state, repeated zygosity
+// keys, K not a multiple of numClust, more than 32 unit states) through the dense kernels ----
+static bool needs_generic(int K, int numClust, const double *zs, int nZS, int useOutlier) {
+  if (useOutlier || numClust <= 0 || K % numClust != 0) return true;
+  if (const char *e = getenv("TITAN_FORCE_DENSE")) if (atoi(e)) return true;   // cross-check of the structured kernels
+  const int U = K / numClust;
+  if (U > 32 || numClust > kMaxZ || nZS < U) return true;
+  for (int a = 0; a < U; ++a)
+    for (int b = a + 1; b < U; ++b)
+      if (zs[a] == zs[b] && zs[a] != -1) return true;
+  return false;
+}
+
+struct GenericSetup {
+  int U = 1;
+  std::vector<unsigned char> cls;
+  std::vector<double> rhoG, rhoZ;
+};
+
+static int generic_setup(const char *who, int K, int T, const double *zs, int nZS, int numClust, const double *positions,
+                         double zStrength, double txnLen, int useOutlier, GenericSetup *g) {
+  if (K <= 0 || T <= 0) return fail(TITAN_ERR_ARG, "%s: The obslik must be %d-by-%d dimension.", who, K, T);
+  if (numClust <= 0) return fail(TITAN_ERR_ARG, "%s: numClust must be a positive scalar", who);
+  if (!(txnLen > 0) || !(zStrength > 0)) return fail(TITAN_ERR_ARG, "%s: txnLen / zStrength must be positive scalars", who);
+  g->U = K / numClust;                                  // src/fwd_backC_clonalCN.c:71 (integer division)
+  if (g->U < 1) return fail(TITAN_ERR_ARG, "%s: numClust=%d exceeds the %d states", who, numClust, K);
+  const int need = std::min(g->U, useOutlier ? std::max(K - 1, 1) : K);
+  if (nZS < need) return fail(TITAN_ERR_ARG, "%s: zygosityKey has %d entries, %d are indexed", who, nZS, need);
+  th::generic_class_matrix(K, g->U, zs, useOutlier != 0, g->cls);
+  g->rhoG.assign(T, 1.0);
+  g->rhoZ.assign(T, 1.0);
+  for (int t = 1; t < T; ++t) {
+    g->rhoG[t] = th::rho_keep(positions[t - 1], positions[t], txnLen);
+    g->rhoZ[t] = th::rho_keep(positions[t - 1], positions[t], zStrength);
+  }
+  int ndev = 0;
+  return titan_device_count(&ndev);
+}
+
+static int generic_fwd_back(const double *log_pi, int K, const double *py, int T, const double *zs, int nZS, int numClust,
+                            const double *positions, double zStrength, double txnLen, int useOutlier, double *rho_out,
+                            double *loglik_out) {
+  if (K > 1024) return fail(TITAN_ERR_UNSUPPORTED, "fwd_backC_clonalCN: K=%d exceeds the 1024 states of the dense kernel", K);
+  GenericSetup g;
+  int rc = generic_setup("fwd_backC_clonalCN", K, T, zs, nZS, numClust, positions, zStrength, txnLen, useOutlier, &g);
+  if (rc != TITAN_OK) return rc;
+  try {
+    DevBuf<double> dpy, dlp, dG, dZ, dal, dlg, dll;
+    DevBuf<unsigned char> dcls;
+    const size_t KT = (size_t)K * T;
+    dpy.alloc(KT); dlp.alloc(K); dG.alloc(T); dZ.alloc(T); dal.alloc(KT); dlg.alloc(KT); dll.alloc(1); dcls.alloc((size_t)K * K);
+    CK(cudaMemcpy(dpy.p, py, sizeof(double) * KT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dlp.p, log_pi, sizeof(double) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dG.p, g.rhoG.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dZ.p, g.rhoZ.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcls.p, g.cls.data(), (size_t)K * K, cudaMemcpyHostToDevice));
+    DenseArgs A{dpy.p, dlp.p, dG.p, dZ.p, dcls.p, K, T, dal.p, dlg.p, dll.p};
+    const int threads = ((K + 31) / 32) * 32;
+    dense_fwd_back_kernel<<<1, threads, sizeof(double) * (K + 32)>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(rho_out, dlg.p, sizeof(double) * KT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(loglik_out, dll.p, sizeof(double), cudaMemcpyDeviceToHost));
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+  return TITAN_OK;
+}
+
+static int generic_viterbi(const double *log_pi, int K, const double *py, int T, const double *zs, int nZS, int numClust,
+                           const double *positions, double zStrength, double txnLen, int useOutlier, int *path_out) {
+  if (K > 256) return fail(TITAN_ERR_UNSUPPORTED, "viterbiC_clonalCN: Viterbi back-pointers are 8-bit: K=%d > 256", K);
+  GenericSetup g;
+  int rc = generic_setup("viterbiC_clonalCN", K, T, zs, nZS, numClust, positions, zStrength, txnLen, useOutlier, &g);
+  if (rc != TITAN_OK) return rc;
+  try {
+    std::unordered_map<std::pair<uint64_t, uint64_t>, int, th::PairHash> ids;
+    std::vector<int> id(T, 0);
+    std::vector<std::pair<double, double>> distinct;
+    for (int t = 1; t < T; ++t) {
+      auto key = std::make_pair(th::bits_of(g.rhoG[t]), th::bits_of(g.rhoZ[t]));
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        it = ids.emplace(key, (int)distinct.size()).first;
+        distinct.emplace_back(g.rhoG[t], g.rhoZ[t]);
+      }
+      id[t] = it->second;
+    }
+    std::vector<double> tab(std::max<size_t>(1, distinct.size()) * 4 * (size_t)K);
+    for (size_t q = 0; q < distinct.size(); ++q)
+      th::viterbi_log_table_generic(K, g.cls.data(), distinct[q].first, distinct[q].second, tab.data() + q * 4 * (size_t)K);
+    DevBuf<double> dpy, dlp, dtab;
+    DevBuf<int> dcs, did, dpath;
+    DevBuf<unsigned char> dcls, dpsi, dhet;
+    const size_t KT = (size_t)K * T;
+    int cs[2] = {0, T};
+    std::vector<unsigned char> het0(std::max(g.U, 1), 0);
+    dpy.alloc(KT); dlp.alloc(K); dtab.alloc(tab.size()); dcs.alloc(2); did.alloc(T); dpath.alloc(T);
+    dcls.alloc((size_t)K * K); dpsi.alloc(KT); dhet.alloc(het0.size());
+    CK(cudaMemcpy(dpy.p, py, sizeof(double) * KT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dlp.p, log_pi, sizeof(double) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcs.p, cs, sizeof(cs), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(did.p, id.data(), sizeof(int) * T, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcls.p, g.cls.data(), (size_t)K * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dhet.p, het0.data(), het0.size(), cudaMemcpyHostToDevice));
+    VitArgs A{};
+    A.chr_start = dcs.p; A.txn_id = did.p; A.ltab = dtab.p; A.het = dhet.p; A.py = dpy.p; A.cls = dcls.p;
+    A.M.logpi = dlp.p;
+    A.U = g.U; A.Z = numClust; A.K = K; A.psi = dpsi.p; A.path = dpath.p;
+    int P = 4;
+    while (P > 1 && K * P > 1024) P >>= 1;
+    const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);
+    const size_t smem = sizeof(double) * 13 * (size_t)K + sizeof(unsigned short) * (size_t)((K + P - 1) / P) * threads;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(viterbi_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    viterbi_forward_kernel<true><<<1, threads, smem>>>(A, P);
+    CK(cudaGetLastError());
+    viterbi_backtrace_kernel<<<1, 128, 128 * (size_t)K>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(path_out, dpath.p, sizeof(int) * T, cudaMemcpyDeviceToHost));
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+  return TITAN_OK;
+}
+
 static int legacy_create(const char *who, const double *log_pi, int K, const double *py, int T, const double *zs, int nZS,
                          int numClust, const double *positions, double zStrength, double txnLen, int useOutlier,
                          titan_solver **out) {
@@ -912,6 +1038,10 @@ extern "C" int titan_fwd_back_clonalCN(const double *log_piGiZi, int K, const do
                                        double *loglik_out) {
   (void)copyNumKey; (void)nCT;   // unused by the reference's maths as well (fwd_backC_clonalCN.c:266)
   if (!rho_out || !loglik_out) return fail(TITAN_ERR_ARG, "fwd_backC_clonalCN: NULL output");
+  if (!log_piGiZi || !py || !zygosityKey || !positions) return fail(TITAN_ERR_ARG, "fwd_backC_clonalCN: NULL argument");
+  if (needs_generic(K, numClust, zygosityKey, nZS, useOutlier))
+    return generic_fwd_back(log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength, txnLen, useOutlier,
+                            rho_out, loglik_out);
   titan_solver *s = nullptr;
   int rc = legacy_create("fwd_backC_clonalCN", log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength,
                          txnLen, useOutlier, &s);
@@ -936,6 +1066,10 @@ extern "C" int titan_viterbi_clonalCN(const double *log_piGiZi, int K, const dou
                                       double zStrength, double txnLen, int useOutlier, int *path_out) {
   (void)copyNumKey; (void)nCT;
   if (!path_out) return fail(TITAN_ERR_ARG, "viterbiC_clonalCN: NULL output");
+  if (!log_piGiZi || !py || !zygosityKey || !positions) return fail(TITAN_ERR_ARG, "viterbiC_clonalCN: NULL argument");
+  if (needs_generic(K, numClust, zygosityKey, nZS, useOutlier))
+    return generic_viterbi(log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength, txnLen, useOutlier,
+                           path_out);
   titan_solver *s = nullptr;
   int rc = legacy_create("viterbiC_clonalCN", log_piGiZi, K, py, T, zygosityKey, nZS, numClust, positions, zStrength,
                          txnLen, useOutlier, &s);

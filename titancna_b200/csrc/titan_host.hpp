@@ -86,6 +86,37 @@ inline void viterbi_log_table(int K, int U, const unsigned char *het, double rho
   }
 }
 
+// Zygosity class / cluster number of joint state s exactly as the reference derives them
+// (src/fwd_backC_clonalCN.c:224-247), and the class of every transition i -> j:
+// 2*(zygosity_i == zygosity_j) + (cluster_i == cluster_j || zygosity_j == -1).
+inline void generic_class_matrix(int K, int U, const double *ZS, bool outlier, std::vector<unsigned char> &cls) {
+  std::vector<double> zs(K), clu(K);
+  for (int s = 0; s < K; ++s) {
+    if (outlier) {
+      if (s == 0) { zs[s] = -100.0; clu[s] = 0.0; }
+      else { clu[s] = std::ceil(((double)s) / U); zs[s] = ZS[(s - 1) % U]; }
+    } else {
+      clu[s] = std::ceil(((double)s + 1) / U);
+      zs[s] = ZS[s % U];
+    }
+  }
+  cls.assign((size_t)K * K, 0);
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j)
+      cls[(size_t)i * K + j] = (unsigned char)(((zs[i] == zs[j]) ? 2 : 0) | ((clu[i] == clu[j] || zs[j] == -1) ? 1 : 0));
+}
+
+// viterbi_log_table for an arbitrary class matrix (same arithmetic: sequential row sums, libm log)
+inline void viterbi_log_table_generic(int K, const unsigned char *cls, double rhoG, double rhoZ, double *out) {
+  const double gdiff = (1.0 - rhoG) / ((double)K - 1.0);
+  const double raw[4] = {gdiff * (1.0 - rhoZ), gdiff * rhoZ, rhoG * (1.0 - rhoZ), rhoG * rhoZ};
+  for (int i = 0; i < K; ++i) {
+    double sum = 0;
+    for (int j = 0; j < K; ++j) sum += raw[cls[(size_t)i * K + j]];
+    for (int c = 0; c < 4; ++c) out[i * 4 + c] = std::log(sum > 0 ? raw[c] / sum : raw[c]);
+  }
+}
+
 struct PairHash {
   size_t operator()(const std::pair<uint64_t, uint64_t> &p) const {
     return std::hash<uint64_t>()(p.first * 0x9E3779B97F4A7C15ull ^ (p.second + (p.first << 6) + (p.first >> 2)));

@@ -1149,6 +1149,112 @@ __global__ void txn_coeff_kernel(const double *__restrict__ rhoG, const double *
 }
 
 // ------------------------------------------------------------------------------------------
+// Dense forward-backward for the compatibility path: ANY state layout the reference's C accepts
+// (outlier state, repeated zygosity keys, K not a multiple of the cluster count), scaled linear space.
+// One CTA per call (one chromosome), one thread per state; the transition between two SNPs is the
+// reference's: raw = {oG, rhoG}[same zygosity] * {1-rhoZ, rhoZ}[same cluster or destination HET], rows
+// divided by their sums (src/fwd_backC_clonalCN.c:215-301) -- the class of every (i, j) pair comes from
+// a host-built K x K table, so no structure is assumed.  O(K^2) per SNP like the reference, but without
+// its 2 K^2 log() + 2 K^2 exp() per SNP.  Also serves as the cancellation-free cross-check of the
+// structured kernels (tests).
+// ------------------------------------------------------------------------------------------
+struct DenseArgs {
+  const double *py;            // [T][K] log emissions
+  const double *logpi;         // [K]
+  const double *rhoG, *rhoZ;   // [T] host-exact, entry t = between t-1 and t
+  const unsigned char *cls;    // [K][K] class of i -> j: 2*sameZygosity + (sameCluster || destHET)
+  int K, T;
+  double *alpha;               // [T][K] scratch
+  double *loggamma;            // [T][K] out
+  double *loglik;              // [1] out
+};
+
+__device__ __forceinline__ double block_sum(double v, double *red, int nwarps) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < nwarps; ++w) tot += red[w];
+  __syncthreads();
+  return tot;
+}
+
+__device__ __forceinline__ double block_max(double v, double *red, int nwarps) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = red[0];
+  for (int w = 1; w < nwarps; ++w) m = fmax(m, red[w]);
+  __syncthreads();
+  return m;
+}
+
+__global__ void __launch_bounds__(1024) dense_fwd_back_kernel(DenseArgs A) {
+  extern __shared__ double dsm[];
+  const int K = A.K, T = A.T, j = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+  double *w = dsm;                 // [K] alpha / rowsum (forward) or beta * B (backward)
+  double *red = dsm + K;           // [32]
+  const bool on = j < K;
+  const unsigned char *crow = A.cls + (size_t)(on ? j : 0) * K;      // classes of transitions j -> *
+  double ll = 0.0;
+  // ---- forward ----
+  double a;
+  {
+    const double p0 = on ? A.py[j] : -CUDART_INF;
+    const double lp = on ? A.logpi[j] : -CUDART_INF;
+    const double mx = block_max(p0 + lp, red, nw);
+    a = on ? exp(p0 + lp - mx) : 0.0;
+    const double tot = block_sum(a, red, nw);
+    a /= tot;
+    ll = mx + log(tot);
+    if (on) A.alpha[j] = a;
+  }
+  for (int t = 1; t < T; ++t) {
+    const double rG = A.rhoG[t], rZ = A.rhoZ[t];
+    const double oG = (1.0 - rG) / ((double)K - 1.0);
+    const double val[4] = {oG * (1.0 - rZ), oG * rZ, rG * (1.0 - rZ), rG * rZ};
+    double rs = 0.0;
+    if (on)
+      for (int i = 0; i < K; ++i) rs += val[crow[i]];
+    if (on) w[j] = rs > 0 ? a / rs : a;
+    const double pyj = on ? A.py[(size_t)t * K + j] : -CUDART_INF;
+    const double mx = block_max(pyj, red, nw);       // (also orders the w[] writes before the reads below)
+    double m = 0.0;
+    if (on)
+      for (int i = 0; i < K; ++i) m += w[i] * val[A.cls[(size_t)i * K + j]];
+    a = on ? m * exp(pyj - mx) : 0.0;
+    const double tot = block_sum(a, red, nw);
+    a /= tot;
+    ll += mx + log(tot);
+    if (on) A.alpha[(size_t)t * K + j] = a;
+  }
+  if (j == 0) A.loglik[0] = ll;
+  // ---- backward + posterior ----
+  double b = on ? 1.0 : 0.0;
+  if (on) A.loggamma[(size_t)(T - 1) * K + j] = log(a);
+  for (int t = T - 2; t >= 0; --t) {
+    const double rG = A.rhoG[t + 1], rZ = A.rhoZ[t + 1];
+    const double oG = (1.0 - rG) / ((double)K - 1.0);
+    const double val[4] = {oG * (1.0 - rZ), oG * rZ, rG * (1.0 - rZ), rG * rZ};
+    const double pyj = on ? A.py[(size_t)(t + 1) * K + j] : -CUDART_INF;
+    const double mx = block_max(pyj, red, nw);
+    if (on) w[j] = b * exp(pyj - mx);
+    __syncthreads();
+    double rs = 0.0, o = 0.0;
+    if (on)
+      for (int i = 0; i < K; ++i) { const double v = val[crow[i]]; rs += v; o += v * w[i]; }
+    b = on ? (rs > 0 ? o / rs : o) : 0.0;
+    const double tot = block_sum(b, red, nw);
+    b /= tot;
+    const double al = on ? A.alpha[(size_t)t * K + j] : 0.0;
+    const double g = al * b;
+    const double gt = block_sum(g, red, nw);
+    if (on) A.loggamma[(size_t)t * K + j] = log(g / gt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Viterbi.  One CTA per chromosome, one thread per destination state; delta lives in shared
 // memory, the per-step log-transition values come from a host-built table that reproduces the
 // reference's arithmetic bit for bit (sequential row sums, host libm log).  Every addition is a
@@ -1163,6 +1269,7 @@ struct VitArgs {
   ModelConsts M;
   const unsigned char *het;    // [U]
   const double *py;            // legacy: [K x N] log emissions, else nullptr
+  const unsigned char *cls;    // optional [K][K] transition classes (generic legacy path: outlier state, repeated zygosity keys)
   int U, Z, K;
   unsigned char *psi;          // [N][K] back-pointers (K <= 256)
   int *path;                   // [N] 1-based
@@ -1209,7 +1316,7 @@ __global__ void __launch_bounds__(1024) viterbi_forward_kernel(VitArgs A, int P)
   {
     int gi = i0 % U, zi = i0 / U;
     for (int n = 0; n < cnt; ++n) {
-      const int cls = ((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0);
+      const int cls = A.cls ? A.cls[(size_t)(i0 + n) * K + j] : (((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0));
       offs[n * nthr + tid] = (unsigned short)(cls * K + i0 + n);
       if (++gi == U) { gi = 0; ++zi; }
     }
