@@ -129,7 +129,7 @@ struct titan_solver {
 
   // configuration
   int chunk_len = 1024, warm = 192, max_rounds = 64;
-  int vit_mode = -1;               // 1: structured O(K*Z) Viterbi step, 0: dense sliced scan, -1: by K (TITAN_VIT_MODE)
+  int vit_mode = -1;               // 2: register-sliced dense scan, 1: structured O(K*Z) step, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
   int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
   double rtol = 1e-8, atol = 1e-290;   // 100x inside the 1e-6 posterior tolerance; errors do not amplify
 
@@ -154,9 +154,10 @@ struct titan_solver {
   int nSlices = 1, slice = 64;
 
   // Viterbi (lazy)
-  DevBuf<int> chr_start32, txn_id, path;
+  DevBuf<int> chr_start32, txn_id, path, tile_first;
+  int bt_rows = 0, nTiles = 0;
   DevBuf<double> ltab;
-  DevBuf<unsigned char> psi;
+  DevBuf<unsigned char> psi, bt_comp, bt_entry;
   bool vit_ready = false;
   bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
 
@@ -786,6 +787,24 @@ extern "C" int titan_estep(titan_solver *s, const titan_params *p, titan_estep_o
 // ---------------------------------------------------------------------------------------------
 // Viterbi
 // ---------------------------------------------------------------------------------------------
+// ---- tiled back-trace ----
+static std::vector<int> bt_tile_plan(const int *cs, int nChr, int K, int &rows) {
+  rows = K <= 128 ? 256 : 128;
+  std::vector<int> tf(nChr + 1, 0);
+  for (int c = 0; c < nChr; ++c) {
+    const int n = std::max(cs[c + 1] - cs[c] - 1, 0);      // psi rows cs+1 .. ce-1
+    tf[c + 1] = tf[c] + (n + rows - 1) / rows;
+  }
+  return tf;
+}
+
+static void launch_backtrace(const VitArgs &A, int nTiles, cudaStream_t st) {
+  const size_t smem = (size_t)A.bt_rows * A.K + 64 + A.bt_rows;
+  if (nTiles > 0) viterbi_bt_compose_kernel<<<nTiles, 256, smem, st>>>(A);
+  viterbi_bt_link_kernel<<<(A.nChr + 31) / 32, 32, 0, st>>>(A);
+  if (nTiles > 0) viterbi_bt_walk_kernel<<<nTiles, 256, smem, st>>>(A);
+}
+
 static int viterbi_prepare(titan_solver *s) {
   if (s->vit_ready) return TITAN_OK;
   const int64_t N = s->N;
@@ -814,10 +833,58 @@ static int viterbi_prepare(titan_solver *s) {
   CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
   s->ltab.alloc(tab.size());
   CK(cudaMemcpy(s->ltab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-  s->psi.alloc((size_t)N * K);
+  s->psi.alloc((size_t)N * K + 64);       // slack: the back-trace stages tiles with 16-byte loads
+  {
+    const std::vector<int> tf = bt_tile_plan(cs32.data(), s->nChr, K, s->bt_rows);
+    s->nTiles = tf.back();
+    s->tile_first.alloc(tf.size());
+    CK(cudaMemcpy(s->tile_first.p, tf.data(), sizeof(int) * tf.size(), cudaMemcpyHostToDevice));
+    s->bt_comp.alloc((size_t)std::max(1, s->nTiles) * K);
+    s->bt_entry.alloc((size_t)std::max(1, s->nTiles));
+  }
   s->path.alloc(N);
   s->vit_ready = true;
   return TITAN_OK;
+}
+
+// ---- Viterbi forward-kernel selection ----
+constexpr int kVitFastAutoMaxK = 104;
+static bool vit_fast_cfg(int K, int &P, int &PER) {
+  int want = 0;
+  if (const char *e = getenv("TITAN_VIT_P")) want = atoi(e);
+  if (K <= 40) { P = 8; PER = 5; }
+  else if (K <= 80) {
+    if (want == 8) { P = 8; PER = 10; } else { P = 4; PER = 20; }
+  }
+  else if (K <= 104) { P = 4; PER = 32; }
+  else if (K <= 128) { P = 2; PER = 64; }
+  else return false;
+  return true;
+}
+
+static void launch_vit_fast(const VitArgs &A, int nChr, int K, int P, int PER, cudaStream_t st) {
+  const int threads = ((K * P + 31) / 32) * 32;
+  const size_t smem = kVitFastSmem;
+  switch (PER) {
+    case 5: viterbi_fast_kernel<5, 8, 320><<<nChr, threads, smem, st>>>(A); break;
+    case 10: viterbi_fast_kernel<10, 8, 640><<<nChr, threads, smem, st>>>(A); break;
+    case 20: viterbi_fast_kernel<20, 4, 320><<<nChr, threads, smem, st>>>(A); break;
+    case 32: viterbi_fast_kernel<32, 4, 416><<<nChr, threads, smem, st>>>(A); break;
+    default: viterbi_fast_kernel<64, 2, 256><<<nChr, threads, smem, st>>>(A); break;
+  }
+}
+
+static void launch_vit_dense(const VitArgs &A, int nChr, int K, bool from_py, cudaStream_t st) {
+  int P = 4;                                   // threads per destination state (power of two)
+  while (P > 1 && K * P > 1024) P >>= 1;
+  const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);   // >= 2K so two loads per thread cover a 4K-entry table
+  const size_t smem = sizeof(double) * 13 * (size_t)K + sizeof(unsigned short) * (size_t)((K + P - 1) / P) * threads;
+  if (smem > 48 * 1024) {
+    if (from_py) cudaFuncSetAttribute(viterbi_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    else cudaFuncSetAttribute(viterbi_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  }
+  if (from_py) viterbi_forward_kernel<true><<<nChr, threads, smem, st>>>(A, P);
+  else viterbi_forward_kernel<false><<<nChr, threads, smem, st>>>(A, P);
 }
 
 static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_out) {
@@ -837,33 +904,40 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   A.U = s->U; A.Z = s->Z; A.K = s->K;
   A.psi = s->psi.p;
   A.path = s->path.p;
+  A.nChr = s->nChr; A.bt_rows = s->bt_rows;
+  A.tile_first = s->tile_first.p; A.comp = s->bt_comp.p; A.entry = s->bt_entry.p;
   const int K = s->K;
-  int P = 4;                                   // threads per destination state (power of two)
-  if (const char *e = getenv("TITAN_VIT_P")) P = std::max(1, std::min(32, atoi(e)));
-  while (P > 1 && K * P > 1024) P >>= 1;
-  const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);   // >= 2K so two loads per thread cover a 4K-entry table
-  const size_t smem = sizeof(double) * 13 * (size_t)K + sizeof(unsigned short) * (size_t)((K + P - 1) / P) * threads;
-  if (smem > 48 * 1024) {
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[s->legacy_py ? 1 : 0]) {
-      if (s->legacy_py) cudaFuncSetAttribute(viterbi_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      else cudaFuncSetAttribute(viterbi_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr_set[s->legacy_py ? 1 : 0] = true;
-    }
-  }
   CK(cudaEventRecord(s->ev[4], s->stream));
-  // the structured step costs O(K*Z) per SNP but runs in Z warps; measured crossover with the dense sliced scan is K ~ 120
-  const bool structured = (s->vit_mode == 1 || (s->vit_mode < 0 && K >= 120)) && s->Z * 32 <= 256;
-  if (structured) {
+  int fP = 0, fPER = 0;
+  const bool fast_ok = vit_fast_cfg(K, fP, fPER);
+  const bool struct_ok = s->Z * 32 <= 256;
+  // 2: register-sliced dense scan (one barrier per SNP), 1: structured O(K*Z) step in Z warps, 0: shared-memory dense scan
+  int mode = s->vit_mode;
+  if (mode < 0) mode = (fast_ok && K <= kVitFastAutoMaxK) ? 2 : ((struct_ok && K >= 120) ? 1 : 0);
+  if (mode == 2 && !fast_ok) mode = struct_ok ? 1 : 0;
+  if (mode == 1 && !struct_ok) mode = 0;
+  if (mode == 2) {
+    if (!s->legacy_py) {   // exact log emissions, materialised in the (idle) alpha buffer
+      const long long total = (long long)s->N * K;
+      const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+      viterbi_emission_kernel<<<blocks, 256, 0, s->stream>>>(s->snp.p, A.M, s->U, K, total, s->alpha.p);
+      CK(cudaGetLastError());
+      s->tm.kernel_launches += 1;
+      s->state_valid = false;
+      A.py = s->alpha.p;
+    }
+    launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
+  } else if (mode == 1) {
     const size_t smem2 = sizeof(double) * (4 * (size_t)K + 16 * (size_t)s->Z);
     if (s->legacy_py) viterbi_struct_kernel<true><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
     else viterbi_struct_kernel<false><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
-  } else if (s->legacy_py) viterbi_forward_kernel<true><<<s->nChr, threads, smem, s->stream>>>(A, P);
-  else viterbi_forward_kernel<false><<<s->nChr, threads, smem, s->stream>>>(A, P);
+  } else {
+    launch_vit_dense(A, s->nChr, K, s->legacy_py, s->stream);
+  }
   CK(cudaGetLastError());
-  viterbi_backtrace_kernel<<<s->nChr, 128, 128 * (size_t)K, s->stream>>>(A);
+  launch_backtrace(A, s->nTiles, s->stream);
   CK(cudaGetLastError());
-  s->tm.kernel_launches += 2;
+  s->tm.kernel_launches += 2 + (s->nTiles > 0 ? 2 : 0);
   CK(cudaEventRecord(s->ev[5], s->stream));
   CK(cudaMemcpyAsync(path_out, s->path.p, sizeof(int) * s->N, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -983,7 +1057,13 @@ static int generic_viterbi(const double *log_pi, int K, const double *py, int T,
     int cs[2] = {0, T};
     std::vector<unsigned char> het0(std::max(g.U, 1), 0);
     dpy.alloc(KT); dlp.alloc(K); dtab.alloc(tab.size()); dcs.alloc(2); did.alloc(T); dpath.alloc(T);
-    dcls.alloc((size_t)K * K); dpsi.alloc(KT); dhet.alloc(het0.size());
+    dcls.alloc((size_t)K * K); dpsi.alloc(KT + 64); dhet.alloc(het0.size());
+    int bt_rows = 0;
+    const std::vector<int> tf = bt_tile_plan(cs, 1, K, bt_rows);
+    DevBuf<int> dtf;
+    DevBuf<unsigned char> dcomp, dentry;
+    dtf.alloc(tf.size()); dcomp.alloc((size_t)std::max(1, tf.back()) * K); dentry.alloc(std::max(1, tf.back()));
+    CK(cudaMemcpy(dtf.p, tf.data(), sizeof(int) * tf.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dpy.p, py, sizeof(double) * KT, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dlp.p, log_pi, sizeof(double) * K, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dtab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
@@ -995,15 +1075,12 @@ static int generic_viterbi(const double *log_pi, int K, const double *py, int T,
     A.chr_start = dcs.p; A.txn_id = did.p; A.ltab = dtab.p; A.het = dhet.p; A.py = dpy.p; A.cls = dcls.p;
     A.M.logpi = dlp.p;
     A.U = g.U; A.Z = numClust; A.K = K; A.psi = dpsi.p; A.path = dpath.p;
-    int P = 4;
-    while (P > 1 && K * P > 1024) P >>= 1;
-    const int threads = std::max(((K * P + 31) / 32) * 32, ((2 * K + 31) / 32) * 32);
-    const size_t smem = sizeof(double) * 13 * (size_t)K + sizeof(unsigned short) * (size_t)((K + P - 1) / P) * threads;
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(viterbi_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    viterbi_forward_kernel<true><<<1, threads, smem>>>(A, P);
+    int fP = 0, fPER = 0;
+    if (vit_fast_cfg(K, fP, fPER)) launch_vit_fast(A, 1, K, fP, fPER, 0);
+    else launch_vit_dense(A, 1, K, true, 0);
     CK(cudaGetLastError());
-    viterbi_backtrace_kernel<<<1, 128, 128 * (size_t)K>>>(A);
+    A.nChr = 1; A.bt_rows = bt_rows; A.tile_first = dtf.p; A.comp = dcomp.p; A.entry = dentry.p;
+    launch_backtrace(A, tf.back(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(path_out, dpath.p, sizeof(int) * T, cudaMemcpyDeviceToHost));
   } catch (const CudaFail &f) {

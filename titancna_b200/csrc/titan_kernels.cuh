@@ -1273,6 +1273,11 @@ struct VitArgs {
   int U, Z, K;
   unsigned char *psi;          // [N][K] back-pointers (K <= 256)
   int *path;                   // [N] 1-based
+  // tiled back-trace
+  int nChr, bt_rows;           // rows of psi per tile
+  const int *tile_first;       // [nChr+1] first tile of every chromosome
+  unsigned char *comp;         // [nTiles][K] state entering a tile -> state leaving it
+  unsigned char *entry;        // [nTiles] state at the top row of a tile
 };
 
 // exact log emission in the reference's association order; no contraction
@@ -1404,6 +1409,182 @@ __global__ void __launch_bounds__(1024) viterbi_forward_kernel(VitArgs A, int P)
 }
 
 // ------------------------------------------------------------------------------------------
+// Exact log emissions of every (SNP, state), materialised once per decode by a fully parallel
+// kernel so that the sequential Viterbi kernel below carries no emission arithmetic at all.
+// reference: R/hmmClonal.R:449-459, :617-634 (association order of SURVEY.md A.3)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) viterbi_emission_kernel(const SnpRec *__restrict__ snp, ModelConsts M, int U, int K,
+                                                               long long total, double *__restrict__ py) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+    const long long t = q / K;
+    const int j = (int)(q - t * K), g = j % U;
+    const SnpRec r = snp[t];
+    py[q] = emission_exact(r, M.lmu[j], M.l1mu[j], M.muC[j], M.cN[g], M.tv[g]);
+  }
+}
+
+// first-index arg-max over compile-time positions [LO, HI) of a register array: the right half wins
+// only on a strictly larger value, which is the reference's left-to-right scan with strict '<'
+template <int LO, int HI>
+struct ArgmaxTree {
+  template <int PER>
+  static __device__ __forceinline__ void run(const double (&c)[PER], double &bv, int &bi) {
+    constexpr int MID = (LO + HI) / 2;
+    double lv, rv;
+    int li, ri;
+    ArgmaxTree<LO, MID>::run(c, lv, li);
+    ArgmaxTree<MID, HI>::run(c, rv, ri);
+    const bool r = lv < rv;
+    bv = r ? rv : lv;
+    bi = r ? ri : li;
+  }
+};
+template <int LO>
+struct ArgmaxTree<LO, LO + 1> {
+  template <int PER>
+  static __device__ __forceinline__ void run(const double (&c)[PER], double &bv, int &bi) { bv = c[LO]; bi = LO; }
+};
+
+// Latency-lean Viterbi step (same arithmetic, same ordering as viterbi_forward_kernel):
+//   * the shared-memory addresses of a thread's PER candidate class values live in REGISTERS, so
+//     the slice scan is PER independent loads (register + immediate addressing, the two value
+//     buffers sit a compile-time stride apart) followed by a compare tree of depth log2(PER),
+//     instead of a chain of PER dependent (offset load -> value load -> compare) links;
+//   * the lead thread of destination j turns its fresh delta_t[j] straight into the four class
+//     values of SOURCE j for step t+1 (double-buffered, [K][4] so they are two 16-byte stores):
+//     a step has ONE barrier and delta never makes a round trip through shared memory;
+//   * log emissions come from the materialised py matrix and the transition rows of state j from the
+//     per-gap tables, both fetched D steps ahead into registers by the lead thread that uses them.
+constexpr int kVitMaxK = 128;                       // largest K served by viterbi_fast_kernel
+constexpr int kVitVS = 4 * kVitMaxK + 8;            // doubles per class-value buffer (+ the -inf slot), 16-byte multiple
+constexpr size_t kVitFastSmem = sizeof(double) * (2 * kVitVS + kVitMaxK);
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+template <int PER, int P, int MAXT>
+__global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int D = 4;                 // prefetch distance (steps); even, so the buffer parity of a step is static
+  constexpr unsigned VSB = kVitVS * sizeof(double);
+  const int K = A.K, U = A.U, K4 = 4 * A.K;
+  double *vbuf = sm;                   // [2][kVitVS]: class values [K][4] + a -inf slot at 4K
+  double *dfin = sm + 2 * kVitVS;      // [K] last delta
+  const int chr = blockIdx.x;
+  const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
+  if (cs >= ce) return;
+  const int tid = threadIdx.x;
+  const int j = tid / P, p = tid % P;
+  const bool on = j < K;
+  const int gj = on ? j % U : 0, zj = on ? j / U : 0;
+  const bool hetj = on && A.het[gj];
+  const bool lead = on && p == 0;
+  const int per = (K + P - 1) / P;
+  const int i0 = min(p * per, K), i1 = min(i0 + per, K);
+  const int cnt = on ? max(i1 - i0, 0) : 0;
+  const unsigned vbase = (unsigned)__cvta_generic_to_shared(vbuf);
+  unsigned adr[PER];                   // shared-memory byte address (buffer 0) of candidate n
+  {
+    int gi = i0 % U, zi = i0 / U;
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      int o = K4;                      // the -inf slot
+      if (n < cnt) {
+        const int cls = A.cls ? A.cls[(size_t)(i0 + n) * K + j] : (((gi == gj) ? 2 : 0) | ((zi == zj || hetj) ? 1 : 0));
+        o = (i0 + n) * 4 + cls;
+        if (++gi == U) { gi = 0; ++zi; }
+      }
+      adr[n] = vbase + 8u * (unsigned)o;
+    }
+  }
+  if (tid < 2) vbuf[tid * kVitVS + K4] = -CUDART_INF;
+  // ---- prefetch ring (lead threads): slot u serves steps tt with (tt - cs - 1) % D == u ----
+  //   e_q[u] = py[tt][j];  la_q/lb_q[u] = class log-transitions of row j for the move tt -> tt+1;
+  //   id_q[u] = table id needed when the slot is refilled for step tt+D
+  double e_q[D];
+  double2 la_q[D], lb_q[D];
+  int id_q[D];
+  const int last = ce - 1;
+  const double *pyj = A.py + j;
+  const double *ltj = A.ltab + (size_t)j * 4;
+#pragma unroll
+  for (int u = 0; u < D; ++u) {
+    e_q[u] = 0.0; la_q[u] = make_double2(0, 0); lb_q[u] = make_double2(0, 0); id_q[u] = 0;
+    if (lead) {
+      const int tt = min(cs + 1 + u, last);
+      e_q[u] = pyj[(size_t)tt * K];
+      const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)A.txn_id[min(tt + 1, last)] * K4);
+      la_q[u] = row[0]; lb_q[u] = row[1];
+      id_q[u] = A.txn_id[min(tt + 1 + D, last)];
+    }
+  }
+  // ---- t = cs ----
+  if (lead) {
+    const double d0 = __dadd_rn(A.M.logpi[j], pyj[(size_t)cs * K]);
+    A.psi[(size_t)cs * K + j] = 0;
+    dfin[j] = d0;
+    if (cs + 1 < ce) {
+      const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)A.txn_id[cs + 1] * K4);
+      const double2 a = row[0], b = row[1];
+      double2 *dst = reinterpret_cast<double2 *>(vbuf + 4 * j);
+      dst[0] = make_double2(__dadd_rn(d0, a.x), __dadd_rn(d0, a.y));
+      dst[1] = make_double2(__dadd_rn(d0, b.x), __dadd_rn(d0, b.y));
+    }
+  }
+  __syncthreads();
+  for (int t = cs + 1; t < ce; t += D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      const int tt = t + u;
+      if (tt >= ce) break;
+      constexpr unsigned zero = 0;
+      const unsigned rd = (u & 1) ? VSB : zero;       // step t+u reads buffer (u & 1), writes the other one
+      double c[PER];
+#pragma unroll
+      for (int n = 0; n < PER; ++n) c[n] = lds_f64(adr[n] + rd);
+      double best;
+      int pos;
+      ArgmaxTree<0, PER>::run(c, best, pos);
+      int arg = i0 + pos;
+#pragma unroll
+      for (int o = 1; o < P; o <<= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        const bool take = ob > best || (ob == best && oa < arg);
+        best = take ? ob : best;
+        arg = take ? oa : arg;
+      }
+      if (lead) {
+        const double d = __dadd_rn(best, e_q[u]);
+        double2 *dst = reinterpret_cast<double2 *>(vbuf + ((u & 1) ? 0 : kVitVS) + 4 * j);
+        dst[0] = make_double2(__dadd_rn(d, la_q[u].x), __dadd_rn(d, la_q[u].y));
+        dst[1] = make_double2(__dadd_rn(d, lb_q[u].x), __dadd_rn(d, lb_q[u].y));
+        A.psi[(size_t)tt * K + j] = (unsigned char)arg;
+        if (tt == last) dfin[j] = d;
+        // refill the slot for step tt + D
+        const int tp = min(tt + D, last);
+        e_q[u] = pyj[(size_t)tp * K];
+        const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)id_q[u] * K4);
+        la_q[u] = row[0]; lb_q[u] = row[1];
+        id_q[u] = A.txn_id[min(tp + 1 + D, last)];
+      }
+      __syncthreads();
+    }
+  }
+  // first-index arg-max of the last delta (viterbiC_clonalCN.c:118) and its publication
+  if (tid == 0) {
+    int arg = 0;
+    for (int i = 1; i < K; ++i)
+      if (dfin[arg] < dfin[i]) arg = i;
+    A.path[ce - 1] = arg;            // 0-based for now; the backtrace adds 1
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Structured Viterbi step: O(K*Z) work per SNP instead of O(K^2), still bit-exact.
 //
 // One warp per clonal cluster z, lane = genotype g (as in the forward-backward kernels).  Source
@@ -1530,38 +1711,80 @@ __global__ void __launch_bounds__(256) viterbi_struct_kernel(VitArgs A) {
   }
 }
 
-// back-trace: one CTA per chromosome stages psi rows through shared memory in coalesced tiles,
-// thread 0 chases the pointers inside the tile (a dependent chain of shared-memory loads
-// instead of a dependent chain of HBM loads).
-__global__ void viterbi_backtrace_kernel(VitArgs A) {
-  extern __shared__ unsigned char tile[];
-  __shared__ int s_state;
-  const int TILE = 128;
+// ------------------------------------------------------------------------------------------
+// Back-trace (src/viterbiC_clonalCN.c:119-126: path[t-1] = psi[t][path[t]]), parallel in position.
+// Row t of psi is a map state -> state, and maps compose associatively, so the pointer chase over a
+// chromosome splits into tiles of R rows (tile k of a chromosome covers rows hi = ce-1-k*R down to
+// lo = max(hi-R+1, cs+1)):
+//   compose  one CTA per tile: thread s follows start state s through the tile -> comp[tile][s]
+//   link     one thread per chromosome chains the tile maps from the arg-max end state -> entry[tile]
+//   walk     one CTA per tile: re-walk from the now known entry state, coalesced store of the path
+// Integer work only; identical to the sequential chase by construction.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bt_locate(const VitArgs &A, int tile, int &chr, int &lo, int &hi) {
+  chr = 0;
+  while (chr + 1 < A.nChr && A.tile_first[chr + 1] <= tile) ++chr;
+  const int k = tile - A.tile_first[chr];
+  const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
+  hi = ce - 1 - k * A.bt_rows;
+  lo = max(hi - A.bt_rows + 1, cs + 1);
+}
+
+// stage psi rows lo..hi (contiguous bytes) into shared memory with 16-byte loads; returns the tile's first byte
+__device__ __forceinline__ const unsigned char *bt_stage(const VitArgs &A, int lo, int hi, unsigned char *smem) {
+  const size_t base = (size_t)lo * A.K, n = (size_t)(hi - lo + 1) * A.K;
+  const size_t a0 = base & ~(size_t)15;
+  const int shift = (int)(base - a0);
+  const int chunks = (int)((shift + n + 15) >> 4);        // psi is allocated with 64 bytes of slack behind it
+  const uint4 *src = reinterpret_cast<const uint4 *>(A.psi + a0);
+  uint4 *dst = reinterpret_cast<uint4 *>(smem);
+  for (int q = threadIdx.x; q < chunks; q += blockDim.x) dst[q] = src[q];
+  __syncthreads();
+  return smem + shift;
+}
+
+__global__ void __launch_bounds__(256) viterbi_bt_compose_kernel(VitArgs A) {
+  extern __shared__ __align__(16) unsigned char bt_sm[];
+  int chr, lo, hi;
+  bt_locate(A, blockIdx.x, chr, lo, hi);
+  const unsigned char *tile = bt_stage(A, lo, hi, bt_sm);
   const int K = A.K;
-  const int chr = blockIdx.x;
+  for (int s = threadIdx.x; s < K; s += blockDim.x) {
+    int st = s;
+    for (int t = hi; t >= lo; --t) st = tile[(size_t)(t - lo) * K + st];
+    A.comp[(size_t)blockIdx.x * K + s] = (unsigned char)st;
+  }
+}
+
+__global__ void viterbi_bt_link_kernel(VitArgs A) {
+  const int chr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chr >= A.nChr) return;
   const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
   if (cs >= ce) return;
+  int st = A.path[ce - 1];             // 0-based arg-max of the last delta (forward kernel)
+  A.path[ce - 1] = st + 1;
+  for (int k = A.tile_first[chr]; k < A.tile_first[chr + 1]; ++k) {
+    A.entry[k] = (unsigned char)st;
+    st = A.comp[(size_t)k * A.K + st];
+  }
+}
+
+__global__ void __launch_bounds__(256) viterbi_bt_walk_kernel(VitArgs A) {
+  extern __shared__ __align__(16) unsigned char bt_sm[];
+  int chr, lo, hi;
+  bt_locate(A, blockIdx.x, chr, lo, hi);
+  const unsigned char *tile = bt_stage(A, lo, hi, bt_sm);
+  const int K = A.K, rows = hi - lo + 1;
+  unsigned char *sp = bt_sm + (((size_t)A.bt_rows * K + 31) & ~(size_t)15) + 16;   // [rows] states of path[lo-1 .. hi-1]
   if (threadIdx.x == 0) {
-    s_state = A.path[ce - 1];
-    A.path[ce - 1] = s_state + 1;
+    int st = A.entry[blockIdx.x];
+    for (int t = hi; t >= lo; --t) {
+      st = tile[(size_t)(t - lo) * K + st];
+      sp[t - lo] = (unsigned char)st;
+    }
   }
   __syncthreads();
-  // walk t = ce-1 .. cs+1: path[t-1] = psi[t][path[t]]
-  for (int hi = ce - 1; hi > cs; hi -= TILE) {
-    const int lo = max(hi - TILE + 1, cs + 1);          // rows lo..hi
-    const size_t base = (size_t)lo * K, n = (size_t)(hi - lo + 1) * K;
-    for (size_t q = threadIdx.x; q < n; q += blockDim.x) tile[q] = A.psi[base + q];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int state = s_state;
-      for (int t = hi; t >= lo; --t) {
-        state = tile[(size_t)(t - lo) * K + state];
-        A.path[t - 1] = state + 1;
-      }
-      s_state = state;
-    }
-    __syncthreads();
-  }
+  for (int q = threadIdx.x; q < rows; q += blockDim.x) A.path[lo - 1 + q] = (int)sp[q] + 1;
 }
 
 }  // namespace titan
