@@ -848,7 +848,7 @@ static int viterbi_prepare(titan_solver *s) {
 }
 
 // ---- Viterbi forward-kernel selection ----
-constexpr int kVitFastAutoMaxK = 104;
+constexpr int kVitClusterAutoMaxZ = 4;
 static bool vit_fast_cfg(int K, int &P, int &PER) {
   int want = 0;
   if (const char *e = getenv("TITAN_VIT_P")) want = atoi(e);
@@ -862,15 +862,51 @@ static bool vit_fast_cfg(int K, int &P, int &PER) {
   return true;
 }
 
+template <int PER, int P, int MAXT>
+static void launch_vit_fast_t(const VitArgs &A, int nChr, int threads, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(viterbi_fast_kernel<PER, P, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  viterbi_fast_kernel<PER, P, MAXT><<<nChr, threads, smem, st>>>(A);
+}
+
 static void launch_vit_fast(const VitArgs &A, int nChr, int K, int P, int PER, cudaStream_t st) {
   const int threads = ((K * P + 31) / 32) * 32;
-  const size_t smem = kVitFastSmem;
+  const size_t smem = sizeof(double) * (2 * kVitVS + kVitMaxK) + VitRing::bytes(K);
   switch (PER) {
-    case 5: viterbi_fast_kernel<5, 8, 320><<<nChr, threads, smem, st>>>(A); break;
-    case 10: viterbi_fast_kernel<10, 8, 640><<<nChr, threads, smem, st>>>(A); break;
-    case 20: viterbi_fast_kernel<20, 4, 320><<<nChr, threads, smem, st>>>(A); break;
-    case 32: viterbi_fast_kernel<32, 4, 416><<<nChr, threads, smem, st>>>(A); break;
-    default: viterbi_fast_kernel<64, 2, 256><<<nChr, threads, smem, st>>>(A); break;
+    case 5: launch_vit_fast_t<5, 8, 320>(A, nChr, threads, smem, st); break;
+    case 10: launch_vit_fast_t<10, 8, 640>(A, nChr, threads, smem, st); break;
+    case 20: launch_vit_fast_t<20, 4, 320>(A, nChr, threads, smem, st); break;
+    case 32: launch_vit_fast_t<32, 4, 416>(A, nChr, threads, smem, st); break;
+    default: launch_vit_fast_t<64, 2, 256>(A, nChr, threads, smem, st); break;
+  }
+}
+
+template <int Z>
+static void launch_vit_cluster_z(const VitArgs &A, int nChr, cudaStream_t st) {
+  constexpr int H = 2, W = Z * H;
+  const size_t smem = sizeof(double) * W * 33 * 4 + 16 * (size_t)(2 * 2 * W * 32) + sizeof(double) * (size_t)(A.K + 2) +
+                      VitRing::bytes(A.K);
+  if (A.U <= 26) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_cluster_kernel<Z, H, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    viterbi_cluster_kernel<Z, H, 13><<<nChr, 32 * W, smem, st>>>(A);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_cluster_kernel<Z, H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    viterbi_cluster_kernel<Z, H, 16><<<nChr, 32 * W, smem, st>>>(A);
+  }
+}
+
+static bool vit_cluster_ok(const VitArgs &A) { return !A.cls && A.U <= 32 && A.Z >= 1 && A.Z <= 8 && A.py != nullptr; }
+
+static void launch_vit_cluster(const VitArgs &A, int nChr, cudaStream_t st) {
+  switch (A.Z) {
+    case 1: launch_vit_cluster_z<1>(A, nChr, st); break;
+    case 2: launch_vit_cluster_z<2>(A, nChr, st); break;
+    case 3: launch_vit_cluster_z<3>(A, nChr, st); break;
+    case 4: launch_vit_cluster_z<4>(A, nChr, st); break;
+    case 5: launch_vit_cluster_z<5>(A, nChr, st); break;
+    case 6: launch_vit_cluster_z<6>(A, nChr, st); break;
+    case 7: launch_vit_cluster_z<7>(A, nChr, st); break;
+    default: launch_vit_cluster_z<8>(A, nChr, st); break;
   }
 }
 
@@ -911,12 +947,19 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   int fP = 0, fPER = 0;
   const bool fast_ok = vit_fast_cfg(K, fP, fPER);
   const bool struct_ok = s->Z * 32 <= 256;
-  // 2: register-sliced dense scan (one barrier per SNP), 1: structured O(K*Z) step in Z warps, 0: shared-memory dense scan
+  // 3: cluster-sliced scan, 2: register-sliced dense scan (both one barrier per SNP, emissions materialised first),
+  // 1: structured O(K*Z) step in Z warps, 0: shared-memory dense scan
+  const bool cluster_ok = s->U <= 32 && s->Z <= 8;
   int mode = s->vit_mode;
-  if (mode < 0) mode = (fast_ok && K <= kVitFastAutoMaxK) ? 2 : ((struct_ok && K >= 120) ? 1 : 0);
+  if (mode < 0) {   // measured on B200 (1 M SNPs, 23 chromosomes): cluster-sliced wins for Z <= 4 and wherever the dense scan has no instance
+    if (cluster_ok && (s->Z <= kVitClusterAutoMaxZ || !fast_ok)) mode = 3;
+    else if (fast_ok) mode = 2;
+    else mode = (struct_ok && K >= 120) ? 1 : 0;
+  }
+  if (mode == 3 && !cluster_ok) mode = 2;
   if (mode == 2 && !fast_ok) mode = struct_ok ? 1 : 0;
   if (mode == 1 && !struct_ok) mode = 0;
-  if (mode == 2) {
+  if (mode >= 2) {
     if (!s->legacy_py) {   // exact log emissions, materialised in the (idle) alpha buffer
       const long long total = (long long)s->N * K;
       const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
@@ -926,7 +969,8 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
       s->state_valid = false;
       A.py = s->alpha.p;
     }
-    launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
+    if (mode == 3) launch_vit_cluster(A, s->nChr, s->stream);
+    else launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
   } else if (mode == 1) {
     const size_t smem2 = sizeof(double) * (4 * (size_t)K + 16 * (size_t)s->Z);
     if (s->legacy_py) viterbi_struct_kernel<true><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);

@@ -1458,22 +1458,72 @@ struct ArgmaxTree<LO, LO + 1> {
 //     per-gap tables, both fetched D steps ahead into registers by the lead thread that uses them.
 constexpr int kVitMaxK = 128;                       // largest K served by viterbi_fast_kernel
 constexpr int kVitVS = 4 * kVitMaxK + 8;            // doubles per class-value buffer (+ the -inf slot), 16-byte multiple
-constexpr size_t kVitFastSmem = sizeof(double) * (2 * kVitVS + kVitMaxK);
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void lds_v2f64(unsigned addr, double &x, double &y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-step inputs of the sequential Viterbi kernels -- the log emission of state j at step s, the four
+// class log-transitions of row j for the move s -> s+1, and the id of the table needed DV steps later --
+// stream through a 4-slot shared-memory ring filled by cp.async: no register is the target of a global
+// load inside the step loop, so no scoreboard wait on an in-flight load ever lands on the critical path
+// (with register prefetch the loop back-edge waited for the youngest load: 25 % of the step time).
+constexpr int DV = 6;                    // prefetch distance in steps; ring slot of step s is (s - cs - 1) & 7
+constexpr int RV = 8;                    // ring slots
+struct VitRing {
+  double *L;    // [RV][K][4]
+  double *e;    // [RV][K]
+  int *id;      // [RV][K]   txn_id[s + DV + 1], consumed when group s + DV is issued
+  __device__ __forceinline__ void carve(double *base, int K) {
+    L = base; e = base + 4 * RV * (size_t)K; id = reinterpret_cast<int *>(base + 5 * RV * (size_t)K);
+  }
+  static __host__ __device__ constexpr size_t bytes(int K) { return (size_t)K * RV * (4 * 8 + 8 + 4); }
+  // one commit group: everything state j needs at step s
+  __device__ __forceinline__ void issue(const VitArgs &A, int slot, int s, int last, int j, int row_id) const {
+    const int K = A.K;
+    const int sc = min(s, last);
+    cp_async<8>(e + slot * K + j, A.py + (size_t)sc * K + j);
+    const double *row = A.ltab + (size_t)row_id * 4 * K + (size_t)j * 4;
+    cp_async<16>(L + ((size_t)slot * K + j) * 4, row);
+    cp_async<16>(L + ((size_t)slot * K + j) * 4 + 2, row + 2);
+    cp_async<4>(id + slot * K + j, A.txn_id + min(s + DV + 1, last));
+    cp_async_commit();
+  }
+  // groups of the first DV steps (s = cs+1 .. cs+DV), table ids read directly
+  __device__ __forceinline__ void prologue(const VitArgs &A, int cs, int last, int j) const {
+#pragma unroll
+    for (int u = 0; u < DV; ++u) {
+      const int s = cs + 1 + u;
+      issue(A, u, s, last, j, A.txn_id[min(s + 1, last)]);
+    }
+    cp_async_wait<DV - 1>();
+  }
+};
+
 
 template <int PER, int P, int MAXT>
 __global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int D = 4;                 // prefetch distance (steps); even, so the buffer parity of a step is static
+  constexpr int D = 4;                 // unroll of the step loop = ring slots; even, so the buffer parity of a step is static
   constexpr unsigned VSB = kVitVS * sizeof(double);
   const int K = A.K, U = A.U, K4 = 4 * A.K;
   double *vbuf = sm;                   // [2][kVitVS]: class values [K][4] + a -inf slot at 4K
   double *dfin = sm + 2 * kVitVS;      // [K] last delta
+  VitRing ring;
+  ring.carve(sm + 2 * kVitVS + kVitMaxK, A.K);
   const int chr = blockIdx.x;
   const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
   if (cs >= ce) return;
@@ -1502,26 +1552,10 @@ __global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
     }
   }
   if (tid < 2) vbuf[tid * kVitVS + K4] = -CUDART_INF;
-  // ---- prefetch ring (lead threads): slot u serves steps tt with (tt - cs - 1) % D == u ----
-  //   e_q[u] = py[tt][j];  la_q/lb_q[u] = class log-transitions of row j for the move tt -> tt+1;
-  //   id_q[u] = table id needed when the slot is refilled for step tt+D
-  double e_q[D];
-  double2 la_q[D], lb_q[D];
-  int id_q[D];
   const int last = ce - 1;
   const double *pyj = A.py + j;
   const double *ltj = A.ltab + (size_t)j * 4;
-#pragma unroll
-  for (int u = 0; u < D; ++u) {
-    e_q[u] = 0.0; la_q[u] = make_double2(0, 0); lb_q[u] = make_double2(0, 0); id_q[u] = 0;
-    if (lead) {
-      const int tt = min(cs + 1 + u, last);
-      e_q[u] = pyj[(size_t)tt * K];
-      const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)A.txn_id[min(tt + 1, last)] * K4);
-      la_q[u] = row[0]; lb_q[u] = row[1];
-      id_q[u] = A.txn_id[min(tt + 1 + D, last)];
-    }
-  }
+  if (lead) ring.prologue(A, cs, last, j);
   // ---- t = cs ----
   if (lead) {
     const double d0 = __dadd_rn(A.M.logpi[j], pyj[(size_t)cs * K]);
@@ -1543,6 +1577,17 @@ __global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
       if (tt >= ce) break;
       constexpr unsigned zero = 0;
       const unsigned rd = (u & 1) ? VSB : zero;       // step t+u reads buffer (u & 1), writes the other one
+      // this step's ring slot (filled by this very thread): off the critical path, consumed after the scan
+      double e_u = 0.0;
+      double2 la_u = make_double2(0, 0), lb_u = make_double2(0, 0);
+      int id_u = 0;
+      const int slot = (tt - cs - 1) & (RV - 1);
+      if (lead) {
+        e_u = ring.e[slot * K + j];
+        const double2 *rl = reinterpret_cast<const double2 *>(ring.L + ((size_t)slot * K + j) * 4);
+        la_u = rl[0]; lb_u = rl[1];
+        id_u = ring.id[slot * K + j];
+      }
       double c[PER];
 #pragma unroll
       for (int n = 0; n < PER; ++n) c[n] = lds_f64(adr[n] + rd);
@@ -1559,18 +1604,14 @@ __global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
         arg = take ? oa : arg;
       }
       if (lead) {
-        const double d = __dadd_rn(best, e_q[u]);
+        const double d = __dadd_rn(best, e_u);
         double2 *dst = reinterpret_cast<double2 *>(vbuf + ((u & 1) ? 0 : kVitVS) + 4 * j);
-        dst[0] = make_double2(__dadd_rn(d, la_q[u].x), __dadd_rn(d, la_q[u].y));
-        dst[1] = make_double2(__dadd_rn(d, lb_q[u].x), __dadd_rn(d, lb_q[u].y));
+        dst[0] = make_double2(__dadd_rn(d, la_u.x), __dadd_rn(d, la_u.y));
+        dst[1] = make_double2(__dadd_rn(d, lb_u.x), __dadd_rn(d, lb_u.y));
         A.psi[(size_t)tt * K + j] = (unsigned char)arg;
         if (tt == last) dfin[j] = d;
-        // refill the slot for step tt + D
-        const int tp = min(tt + D, last);
-        e_q[u] = pyj[(size_t)tp * K];
-        const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)id_q[u] * K4);
-        la_q[u] = row[0]; lb_q[u] = row[1];
-        id_q[u] = A.txn_id[min(tp + 1 + D, last)];
+        ring.issue(A, (slot + DV) & (RV - 1), tt + DV, last, j, id_u);
+        cp_async_wait<DV - 1>();      // the group of step tt+1 has landed (own copies: visible to this thread)
       }
       __syncthreads();
     }
@@ -1581,6 +1622,172 @@ __global__ void __launch_bounds__(MAXT) viterbi_fast_kernel(VitArgs A) {
     for (int i = 1; i < K; ++i)
       if (dfin[arg] < dfin[i]) arg = i;
     A.path[ce - 1] = arg;            // 0-based for now; the backtrace adds 1
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cluster-sliced Viterbi step: O(K*U) compares per SNP instead of O(K^2), bit-exact, ONE barrier.
+//
+// Warp (z', h) scans slice h of the sources of clonal cluster z' (lane = genotype g of the
+// DESTINATION).  For a destination of genotype g every source (g', z') offers one of two values,
+// depending only on whether the destination sits in cluster z' (or is diploid HET) -- class 1/3 -- or
+// not -- class 0/2 -- so the warp produces, per lane, two first-index arg-maxima over its slice:
+//   X = max over the slice of (g' == g ? v2 : v0)      for destinations (g, z != z')
+//   Y = max over the slice of (g' == g ? v3 : v1)      for destination  (g, z') and HET destinations
+// The class values [source][4] sit in a warp-private shared-memory table (all H warps of a cluster
+// keep identical copies, so only __syncwarp orders their update); lane g loads one 16-byte pair per
+// source through a register-resident address that points 16 bytes further for its own genotype.
+// Slices are contiguous and ascending in source index, so both the slice scan and the gather over
+// the Z*H slice results are compare trees in which the right operand wins only when strictly larger:
+// the reference's left-to-right scan with strict '<' (src/viterbiC_clonalCN.c:210-229).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) VCand { double v; int i; int pad; };
+
+template <int LO, int HI>
+struct PairTree {     // first-index arg-max over candidates [LO, HI) held as (value, index) register arrays
+  template <int N>
+  static __device__ __forceinline__ void run(const double (&v)[N], const int (&ix)[N], double &bv, int &bi) {
+    constexpr int MID = (LO + HI) / 2;
+    double lv, rv;
+    int li, ri;
+    PairTree<LO, MID>::run(v, ix, lv, li);
+    PairTree<MID, HI>::run(v, ix, rv, ri);
+    const bool r = lv < rv;
+    bv = r ? rv : lv;
+    bi = r ? ri : li;
+  }
+};
+template <int LO>
+struct PairTree<LO, LO + 1> {
+  template <int N>
+  static __device__ __forceinline__ void run(const double (&v)[N], const int (&ix)[N], double &bv, int &bi) { bv = v[LO]; bi = ix[LO]; }
+};
+
+template <int Z, int H, int UP>
+__global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) {
+  extern __shared__ __align__(16) unsigned char vc_sm[];
+  constexpr int W = Z * H;                  // warps
+  constexpr int D = 4;                      // unroll of the step loop = ring slots; even: the exchange parity of a step is static
+  constexpr int TABD = 33 * 4;              // doubles per class-value table: [32 sources][4 classes] + a -inf row
+  double *tab_all = reinterpret_cast<double *>(vc_sm);                       // [W][TABD]
+  VCand *xch = reinterpret_cast<VCand *>(tab_all + W * TABD);                // [2 parity][2 X/Y][W][32]
+  double *dfin = reinterpret_cast<double *>(xch + 2 * 2 * W * 32);           // [K]
+  VitRing ring;
+  ring.carve(dfin + ((A.K + 1) & ~1), A.K);
+  const int K = A.K, U = A.U, K4 = 4 * A.K;
+  const int chr = blockIdx.x;
+  const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
+  if (cs >= ce) return;
+  const int warp = threadIdx.x >> 5, g = threadIdx.x & 31;
+  const int zs = warp / H, h = warp % H;
+  const bool on = g < U;
+  const int j = on ? g + zs * U : 0;        // the state this lane owns: source (g, zs) of its table, destination (g, zs)
+  const bool het = on && A.het[g];
+  const bool writer = on && h == 0;
+  double *tab = tab_all + warp * TABD;
+  const int per = (U + H - 1) / H;
+  const int g0 = h * per;
+  unsigned adr[UP];
+  {
+    const unsigned tbase = (unsigned)__cvta_generic_to_shared(tab);
+#pragma unroll
+    for (int n = 0; n < UP; ++n) {
+      const int gs = g0 + n;
+      const bool valid = n < per && gs < U;
+      adr[n] = tbase + (valid ? 32u * (unsigned)gs + (gs == g ? 16u : 0u) : 32u * 32u);
+    }
+  }
+  if (g < 4) tab[32 * 4 + g] = -CUDART_INF;
+  // gather addresses: slice result (z', h') that applies to destination cluster zs
+  unsigned gadr[W];
+  {
+    const unsigned xbase = (unsigned)__cvta_generic_to_shared(xch);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int sel = ((w / H) == zs || het) ? 1 : 0;
+      gadr[w] = xbase + 16u * (unsigned)((sel * W + w) * 32 + g);
+    }
+  }
+  constexpr unsigned XPAR = 16u * 2 * W * 32;     // bytes between the two exchange parities
+  VCand *xmine = xch + warp * 32 + g;             // parity 0, X; Y sits W*32 entries further
+  const int last = ce - 1;
+  const double *pyj = A.py + j;
+  const double *ltj = A.ltab + (size_t)j * 4;
+  if (writer) ring.prologue(A, cs, last, j);      // the H warps of a cluster share the ring entries of their states
+  // ---- t = cs ----
+  {
+    double d0 = -CUDART_INF;
+    double2 a = make_double2(0, 0), b = make_double2(0, 0);
+    if (on) {
+      d0 = __dadd_rn(A.M.logpi[j], pyj[(size_t)cs * K]);
+      if (cs + 1 < ce) {
+        const double2 *row = reinterpret_cast<const double2 *>(ltj + (size_t)A.txn_id[cs + 1] * K4);
+        a = row[0]; b = row[1];
+      }
+    }
+    if (writer) { A.psi[(size_t)cs * K + j] = 0; dfin[j] = d0; }
+    double2 *dst = reinterpret_cast<double2 *>(tab + 4 * g);
+    dst[0] = make_double2(__dadd_rn(d0, a.x), __dadd_rn(d0, a.y));
+    dst[1] = make_double2(__dadd_rn(d0, b.x), __dadd_rn(d0, b.y));
+  }
+  __syncthreads();
+  for (int t = cs + 1; t < ce; t += D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      const int tt = t + u;
+      if (tt >= ce) break;
+      // ---- slice scan ----
+      double c0[UP], c1[UP];
+#pragma unroll
+      for (int n = 0; n < UP; ++n) lds_v2f64(adr[n], c0[n], c1[n]);
+      double xv, yv;
+      int xp, yp;
+      ArgmaxTree<0, UP>::run(c0, xv, xp);
+      ArgmaxTree<0, UP>::run(c1, yv, yp);
+      const int ibase = zs * U + g0;
+      VCand *xo = xmine + ((u & 1) ? 2 * W * 32 : 0);
+      VCand cx, cy;
+      cx.v = xv; cx.i = ibase + xp; cx.pad = 0;
+      cy.v = yv; cy.i = ibase + yp; cy.pad = 0;
+      xo[0] = cx;
+      xo[W * 32] = cy;
+      __syncthreads();
+      // ---- gather over the Z*H slices, in source order ----
+      double gv[W];
+      int gi[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        double ip;
+        lds_v2f64(gadr[w] + ((u & 1) ? XPAR : 0u), gv[w], ip);
+        gi[w] = __double2loint(ip);
+      }
+      // this step's ring slot: landed before the barrier above (writer's wait_group in the previous step)
+      const int slot = (tt - cs - 1) & (RV - 1);
+      const double e_u = ring.e[slot * K + j];
+      const double2 *rl = reinterpret_cast<const double2 *>(ring.L + ((size_t)slot * K + j) * 4);
+      const double2 la_u = rl[0], lb_u = rl[1];
+      double best;
+      int arg;
+      PairTree<0, W>::run(gv, gi, best, arg);
+      const double d = __dadd_rn(best, e_u);
+      double2 *dst = reinterpret_cast<double2 *>(tab + 4 * g);
+      dst[0] = make_double2(__dadd_rn(d, la_u.x), __dadd_rn(d, la_u.y));
+      dst[1] = make_double2(__dadd_rn(d, lb_u.x), __dadd_rn(d, lb_u.y));
+      if (writer) {
+        A.psi[(size_t)tt * K + j] = (unsigned char)arg;
+        if (tt == last) dfin[j] = d;
+        ring.issue(A, (slot + DV) & (RV - 1), tt + DV, last, j, ring.id[slot * K + j]);
+        cp_async_wait<DV - 1>();      // the group of step tt+1 has landed; the next barrier publishes it
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // first-index arg-max of the last delta (viterbiC_clonalCN.c:118)
+    int arg = 0;
+    for (int i = 1; i < K; ++i)
+      if (dfin[arg] < dfin[i]) arg = i;
+    A.path[ce - 1] = arg;            // 0-based for now; the back-trace adds 1
   }
 }
 
