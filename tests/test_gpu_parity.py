@@ -111,12 +111,16 @@ def test_fused_estep_matches_oracle(N, Z, maxCN, n_chr, txn, zfac, chunk, warm):
     assert tm["n_chunks"] >= n_chr
 
 
+@pytest.mark.parametrize("vit_mode", ["-1", "0", "2", "3"])
 @pytest.mark.parametrize("N,Z,maxCN,n_chr,txn,zfac", [
     (6000, 3, 8, 3, 1e15, 1.0), (5000, 1, 8, 2, 1e15, 5e5), (4000, 5, 8, 2, 1e9, 1e9), (3000, 2, 5, 4, 1e5, 1.0),
     (2000, 8, 4, 2, 1e15, 1.0)])
-def test_fused_viterbi_bit_exact(N, Z, maxCN, n_chr, txn, zfac):
-    """Systematic near-ties included: with hetBaselineSkew = 0 the diploid-HET states of different
-    clusters have identical emissions."""
+def test_fused_viterbi_bit_exact(N, Z, maxCN, n_chr, txn, zfac, vit_mode, monkeypatch):
+    """Every forward kernel (auto choice, shared-memory dense scan, register-sliced dense scan,
+    cluster-sliced scan) against the reference C.  Systematic near-ties included: with
+    hetBaselineSkew = 0 the diploid-HET states of different clusters have identical emissions
+    (SURVEY.md 7.2-2)."""
+    monkeypatch.setenv("TITAN_VIT_MODE", vit_mode)
     data, truth = synth.make_data(N, Z=Z, maxCN=maxCN, n_chr=n_chr, seed=5 + Z, mean_seg=250)
     for skew in (None, 0.0):
         p = T.loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z, hetBaselineSkew=skew)
@@ -249,7 +253,8 @@ def test_edge_cases_and_errors():
 
 
 @pytest.mark.parametrize("env", [{"TITAN_WS_MODE": "0"}, {"TITAN_WS_MODE": "2"}, {"TITAN_OVERLAP": "0"},
-                                 {"TITAN_OVERLAP": "0", "TITAN_WS_MODE": "0"}, {"TITAN_VIT_MODE": "1"}])
+                                 {"TITAN_OVERLAP": "0", "TITAN_WS_MODE": "0"}, {"TITAN_VIT_MODE": "2"},
+                                 {"TITAN_VIT_MODE": "3"}])
 def test_kernel_variants_agree(env, monkeypatch):
     """Every execution strategy (warp-per-chunk only, warp-specialised only, forward/backward rounds
     overlapped on two streams or run back to back) is the same function of the inputs: compare each
@@ -275,7 +280,7 @@ def test_kernel_variants_agree(env, monkeypatch):
     ref_sol = T.Solver(data, g, Z, 1e15, 1.0)
     p0 = ref_sol.viterbi(*args)
     ref_sol.close()
-    assert np.array_equal(p0, p1)                     # dense and structured Viterbi steps: identical paths
+    assert np.array_equal(p0, p1)                     # every Viterbi forward kernel: identical paths
     assert tm["last_fwd_rounds"] >= 2
     assert np.allclose(par["loglik_chr"], seq["loglik_chr"], rtol=1e-11, atol=0)
     assert np.abs(par["rhoG"] - seq["rhoG"]).max() < 1e-7

@@ -129,7 +129,7 @@ struct titan_solver {
 
   // configuration
   int chunk_len = 1024, warm = 192, max_rounds = 64;
-  int vit_mode = -1;               // 2: register-sliced dense scan, 1: structured O(K*Z) step, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
+  int vit_mode = -1;               // 3: cluster-sliced scan, 2: register-sliced dense scan, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
   int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
   double rtol = 1e-8, atol = 1e-290;   // 100x inside the 1e-6 posterior tolerance; errors do not amplify
 
@@ -946,19 +946,16 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   CK(cudaEventRecord(s->ev[4], s->stream));
   int fP = 0, fPER = 0;
   const bool fast_ok = vit_fast_cfg(K, fP, fPER);
-  const bool struct_ok = s->Z * 32 <= 256;
   // 3: cluster-sliced scan, 2: register-sliced dense scan (both one barrier per SNP, emissions materialised first),
-  // 1: structured O(K*Z) step in Z warps, 0: shared-memory dense scan
+  // 0: shared-memory dense scan (any K <= 256, any class matrix)
   const bool cluster_ok = s->U <= 32 && s->Z <= 8;
   int mode = s->vit_mode;
   if (mode < 0) {   // measured on B200 (1 M SNPs, 23 chromosomes): cluster-sliced wins for Z <= 4 and wherever the dense scan has no instance
     if (cluster_ok && (s->Z <= kVitClusterAutoMaxZ || !fast_ok)) mode = 3;
-    else if (fast_ok) mode = 2;
-    else mode = (struct_ok && K >= 120) ? 1 : 0;
+    else mode = fast_ok ? 2 : 0;
   }
   if (mode == 3 && !cluster_ok) mode = 2;
-  if (mode == 2 && !fast_ok) mode = struct_ok ? 1 : 0;
-  if (mode == 1 && !struct_ok) mode = 0;
+  if (mode == 2 && !fast_ok) mode = 0;
   if (mode >= 2) {
     if (!s->legacy_py) {   // exact log emissions, materialised in the (idle) alpha buffer
       const long long total = (long long)s->N * K;
@@ -971,10 +968,6 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
     }
     if (mode == 3) launch_vit_cluster(A, s->nChr, s->stream);
     else launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
-  } else if (mode == 1) {
-    const size_t smem2 = sizeof(double) * (4 * (size_t)K + 16 * (size_t)s->Z);
-    if (s->legacy_py) viterbi_struct_kernel<true><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
-    else viterbi_struct_kernel<false><<<s->nChr, 32 * s->Z, smem2, s->stream>>>(A);
   } else {
     launch_vit_dense(A, s->nChr, K, s->legacy_py, s->stream);
   }

@@ -1792,133 +1792,6 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
 }
 
 // ------------------------------------------------------------------------------------------
-// Structured Viterbi step: O(K*Z) work per SNP instead of O(K^2), still bit-exact.
-//
-// One warp per clonal cluster z, lane = genotype g (as in the forward-backward kernels).  Source
-// i = (g', z') reaches destination j = (g, z) through one of four classes, and the class value
-// v_c[i] = delta[i] (+) logA_c(i) is the same double for every destination of that class, so the
-// arg-max over the K sources decomposes into group maxima:
-//   same genotype, cluster z'      : v3[g, z'] if z' == z or j is HET, else v2[g, z']
-//   other genotypes, cluster z'    : max over g' != g of v1[g', z'] if z' == z or j is HET, else of v0[g', z']
-// "max over lanes except my own" comes from a top-2 warp reduction.  Every comparison orders by
-// (value descending, source index ascending), which reproduces the reference's left-to-right scan
-// with strict '<' (src/viterbiC_clonalCN.c:210-229) including exact ties.
-// Exchange between the Z warps goes through double-buffered shared memory: one barrier per SNP.
-// ------------------------------------------------------------------------------------------
-struct Cand { double v; int i; };
-__device__ __forceinline__ bool cand_better(const Cand &a, const Cand &b) { return a.v > b.v || (a.v == b.v && a.i < b.i); }
-
-__device__ __forceinline__ void top2_reduce(Cand &m1, Cand &m2) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Cand p1, p2;
-    p1.v = __shfl_xor_sync(0xffffffffu, m1.v, o); p1.i = __shfl_xor_sync(0xffffffffu, m1.i, o);
-    p2.v = __shfl_xor_sync(0xffffffffu, m2.v, o); p2.i = __shfl_xor_sync(0xffffffffu, m2.i, o);
-    if (cand_better(p1, m1)) {
-      const Cand n2 = cand_better(m1, p2) ? m1 : p2;
-      m1 = p1; m2 = n2;
-    } else {
-      m2 = cand_better(p1, m2) ? p1 : m2;
-    }
-  }
-}
-
-template <bool FROM_PY>
-__global__ void __launch_bounds__(256) viterbi_struct_kernel(VitArgs A) {
-  extern __shared__ double sm[];
-  const int K = A.K, U = A.U, Z = A.Z, K4 = 4 * A.K;
-  // exchange buffers, double-buffered by step parity
-  double *xv2 = sm;                     // [2][K]  v2 of every state
-  double *xv3 = sm + 2 * K;             // [2][K]  v3 of every state
-  double *xt = sm + 4 * K;              // [2][Z][2 classes][4]: top-2 (v1,v2 values; indices as doubles) of v1 and v0 per cluster
-  __shared__ double last_delta[256];
-  const int chr = blockIdx.x;
-  const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
-  const int z = threadIdx.x >> 5, g = threadIdx.x & 31;
-  const bool on = g < U;
-  const int j = on ? g + z * U : 0;
-  const bool hetj = on && A.het[g];
-  if (cs >= ce) return;
-  double lmu = 0, l1mu = 0, muC = 0, cN = 0, tv = 1;
-  if (on && !FROM_PY) {
-    lmu = A.M.lmu[j]; l1mu = A.M.l1mu[j]; muC = A.M.muC[j]; cN = A.M.cN[g]; tv = A.M.tv[g];
-  }
-  const double ninf = -CUDART_INF;
-  double delta = ninf;
-  if (on) {
-    const double e0 = FROM_PY ? A.py[(size_t)cs * K + j] : emission_exact(A.snp[cs], lmu, l1mu, muC, cN, tv);
-    delta = __dadd_rn(A.M.logpi[j], e0);
-    A.psi[(size_t)cs * K + j] = 0;
-  }
-  // prefetch (one step ahead): the four class log-transitions of my own state, the table id, the emission
-  int id_n = (cs + 2 < ce) ? A.txn_id[cs + 2] : 0;
-  double2 la = make_double2(0, 0), lb = make_double2(0, 0);
-  double e = 0.0;
-  if (cs + 1 < ce && on) {
-    const double2 *row = reinterpret_cast<const double2 *>(A.ltab + (size_t)A.txn_id[cs + 1] * K4 + (size_t)j * 4);
-    la = row[0]; lb = row[1];
-    e = FROM_PY ? A.py[(size_t)(cs + 1) * K + j] : emission_exact(A.snp[cs + 1], lmu, l1mu, muC, cN, tv);
-  }
-  for (int t = cs + 1; t < ce; ++t) {
-    const int buf = (t - cs) & 1;
-    const int tn = min(t + 1, ce - 1), tnn = min(t + 2, ce - 1);
-    // ---- prefetch for step t+1 ----
-    double2 la_n = make_double2(0, 0), lb_n = make_double2(0, 0);
-    SnpRec rec_n;
-    double py_n = 0.0;
-    if (on) {
-      const double2 *row = reinterpret_cast<const double2 *>(A.ltab + (size_t)id_n * K4 + (size_t)j * 4);
-      la_n = row[0]; lb_n = row[1];
-      if (FROM_PY) py_n = A.py[(size_t)tn * K + j];
-      else rec_n = A.snp[tn];
-    }
-    const int id_nn = A.txn_id[tnn];
-    // ---- class values of my own state as a SOURCE ----
-    const double v0 = on ? __dadd_rn(delta, la.x) : ninf;   // other genotype, other cluster (dest not HET)
-    const double v1 = on ? __dadd_rn(delta, la.y) : ninf;   // other genotype, same cluster or dest HET
-    const double v2 = on ? __dadd_rn(delta, lb.x) : ninf;   // same genotype, other cluster (dest not HET)
-    const double v3 = on ? __dadd_rn(delta, lb.y) : ninf;   // same genotype, same cluster or dest HET
-    Cand a1{v1, on ? j : 0x7fffffff}, a2{ninf, 0x7fffffff}, b1{v0, on ? j : 0x7fffffff}, b2{ninf, 0x7fffffff};
-    top2_reduce(a1, a2);
-    top2_reduce(b1, b2);
-    if (on) { xv2[buf * K + j] = v2; xv3[buf * K + j] = v3; }
-    if (g == 0) {
-      double *d = xt + ((buf * Z + z) * 2) * 4;
-      d[0] = a1.v; d[1] = (double)a1.i; d[2] = a2.v; d[3] = (double)a2.i;
-      d[4] = b1.v; d[5] = (double)b1.i; d[6] = b2.v; d[7] = (double)b2.i;
-    }
-    __syncthreads();
-    // ---- arg-max over the sources of destination j ----
-    Cand best{ninf, 0x7fffffff};
-    if (on) {
-      for (int zz = 0; zz < Z; ++zz) {
-        const bool strong = (zz == z) || hetj;           // same cluster, or destination is diploid HET
-        const int isrc = g + zz * U;                     // same genotype in cluster zz
-        Cand c{strong ? xv3[buf * K + isrc] : xv2[buf * K + isrc], isrc};
-        if (cand_better(c, best)) best = c;
-        const double *d = xt + ((buf * Z + zz) * 2 + (strong ? 0 : 1)) * 4;
-        Cand o1{d[0], (int)d[1]}, o2{d[2], (int)d[3]};
-        const Cand o = (o1.i == isrc) ? o2 : o1;         // best other-genotype source of cluster zz
-        if (cand_better(o, best)) best = o;
-      }
-      delta = __dadd_rn(best.v, e);
-      A.psi[(size_t)t * K + j] = (unsigned char)best.i;
-      e = FROM_PY ? py_n : emission_exact(rec_n, lmu, l1mu, muC, cN, tv);
-    }
-    la = la_n; lb = lb_n; id_n = id_nn;
-  }
-  // first-index arg-max of the last delta (viterbiC_clonalCN.c:118)
-  if (on) last_delta[j] = delta;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int arg = 0;
-    for (int i = 1; i < K; ++i)
-      if (last_delta[arg] < last_delta[i]) arg = i;
-    A.path[ce - 1] = arg;            // 0-based for now; the backtrace adds 1
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Back-trace (src/viterbiC_clonalCN.c:119-126: path[t-1] = psi[t][path[t]]), parallel in position.
 // Row t of psi is a map state -> state, and maps compose associatively, so the pointer chase over a
 // chromosome splits into tiles of R rows (tile k of a chromosome covers rows hi = ce-1-k*R down to
