@@ -159,12 +159,15 @@ struct titan_solver {
   DevBuf<double> ltab;
   DevBuf<unsigned char> psi, bt_comp, bt_entry;
   bool vit_ready = false;
+  std::thread vit_builder;          // builds the Viterbi log-transition tables on the host while the EM runs
+  std::vector<double> vit_tab;      // [nDistinct][K][4]
   bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
 
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   titan_timing tm{};
 
   ~titan_solver() {
+    if (vit_builder.joinable()) vit_builder.join();
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
     for (auto &e : ev_sync)
@@ -173,6 +176,8 @@ struct titan_solver {
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
+
+static void build_viterbi_tables(titan_solver *s);
 
 static void build_chunks(titan_solver *s) {
   s->chunks_h.clear();
@@ -375,6 +380,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     s->rerun.alloc(2 * kRoundSlots);
     s->rerun_h.alloc(2 * kRoundSlots);
     build_chunks(s);
+    if (!s->legacy_py && K <= 256) s->vit_builder = std::thread([s]() { build_viterbi_tables(s); });
   } catch (const CudaFail &f) {
     return f.code;
   } catch (const std::bad_alloc &) {
@@ -805,6 +811,23 @@ static void launch_backtrace(const VitArgs &A, int nTiles, cudaStream_t st) {
   if (nTiles > 0) viterbi_bt_walk_kernel<<<nTiles, 256, smem, st>>>(A);
 }
 
+// exact log-transition tables, one per distinct (rhoG, rhoZ) pair (host libm, sequential row sums);
+// independent per pair, so they are spread over the host threads.  Parameter-independent: started in
+// the background at solver creation and joined by the first decode.
+static void build_viterbi_tables(titan_solver *s) {
+  const int K = s->K;
+  const size_t np = std::max<size_t>(1, s->pairG.size());
+  s->vit_tab.assign(np * 4 * (size_t)K, 0.0);
+  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->pairG.size() + 255) / 256)));
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < nt; ++w)
+    pool.emplace_back([s, w, nt, K]() {
+      for (size_t q = w; q < s->pairG.size(); q += nt)
+        th::viterbi_log_table(K, s->U, s->het.data(), s->pairG[q], s->pairZ[q], s->vit_tab.data() + q * 4 * (size_t)K);
+    });
+  for (auto &t : pool) t.join();
+}
+
 static int viterbi_prepare(titan_solver *s) {
   if (s->vit_ready) return TITAN_OK;
   const int64_t N = s->N;
@@ -814,25 +837,15 @@ static int viterbi_prepare(titan_solver *s) {
   for (int c = 0; c <= s->nChr; ++c) cs32[c] = (int)s->chr_start[c];
   s->chr_start32.alloc(s->nChr + 1);
   CK(cudaMemcpy(s->chr_start32.p, cs32.data(), sizeof(int) * (s->nChr + 1), cudaMemcpyHostToDevice));
-  // exact log-transition tables, one per distinct (rhoG, rhoZ) pair (host libm, sequential row sums);
-  // independent per pair, so they are spread over the host threads
-  const size_t np = std::max<size_t>(1, s->pairG.size());
-  std::vector<double> tab(np * 4 * (size_t)K);
-  {
-    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->pairG.size() + 255) / 256)));
-    std::vector<std::thread> pool;
-    for (unsigned w = 0; w < nt; ++w)
-      pool.emplace_back([&, w]() {
-        for (size_t q = w; q < s->pairG.size(); q += nt)
-          th::viterbi_log_table(K, s->U, s->het.data(), s->pairG[q], s->pairZ[q], tab.data() + q * 4 * (size_t)K);
-      });
-    for (auto &t : pool) t.join();
-  }
+  if (s->vit_builder.joinable()) s->vit_builder.join();
+  if (s->vit_tab.empty()) build_viterbi_tables(s);
+  const std::vector<double> &tab = s->vit_tab;
   const std::vector<int> &id = s->pair_id;
   s->txn_id.alloc(N);
   CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
   s->ltab.alloc(tab.size());
   CK(cudaMemcpy(s->ltab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+  std::vector<double>().swap(s->vit_tab);
   s->psi.alloc((size_t)N * K + 64);       // slack: the back-trace stages tiles with 16-byte loads
   {
     const std::vector<int> tf = bt_tile_plan(cs32.data(), s->nChr, K, s->bt_rows);
