@@ -230,7 +230,21 @@ struct SolverInit {
   int nZS;
 };
 
+// TITAN_TRACE=1: wall-clock phases of solver creation on stderr
+struct PhaseTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTrace() : on(getenv("TITAN_TRACE") && atoi(getenv("TITAN_TRACE"))), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[titan trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 static int solver_create_impl(const SolverInit &in, titan_solver **out) {
+  PhaseTrace trace;
   if (!out) return fail(TITAN_ERR_ARG, "titan_solver_create: out is NULL");
   *out = nullptr;
   if (in.N <= 0 || in.nChr <= 0 || !in.chr_start || !in.posn)
@@ -270,6 +284,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     for (auto &e : s->ev) CK(cudaEventCreate(&e));
     CK(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
     for (auto &e : s->ev_sync) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    trace.mark("streams + events");
     s->N = in.N; s->nChr = in.nChr; s->U = in.U; s->Z = in.Z; s->K = in.U * in.Z;
     s->chr_start.assign(in.chr_start, in.chr_start + in.nChr + 1);
     s->het.resize(in.U);
@@ -336,17 +351,24 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
           s->rhoZ_h[t] = s->pairZ[id];
         }
     }
+    trace.mark("distinct gaps (host exp)");
     {
       DevBuf<double> dG, dZ;
       dG.alloc(N); dZ.alloc(N);
+      trace.mark("  rho alloc");
       CK(cudaMemcpy(dG.p, s->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(dZ.p, s->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+      trace.mark("  rho memcpy");
       s->txn.alloc(N);
+      trace.mark("  txn alloc");
       txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h, s->txn.p);
       CK(cudaGetLastError());
+      trace.mark("  txn launch");
       CK(cudaStreamSynchronize(s->stream));
+      trace.mark("  txn sync");
       s->tm.kernel_launches++;
     }
+    trace.mark("  rho free");
     if (s->legacy_py) {
       s->py.alloc((size_t)N * K);
       CK(cudaMemcpy(s->py.p, in.py, sizeof(double) * N * K, cudaMemcpyHostToDevice));
@@ -368,7 +390,9 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
       s->snp.alloc(N);
       CK(cudaMemcpy(s->snp.p, rec.data(), sizeof(SnpRec) * N, cudaMemcpyHostToDevice));
     }
+    trace.mark("SnpRec (host lgamma) + upload");
     s->alpha.alloc((size_t)N * K);
+    trace.mark("alpha alloc");
     s->het_d.alloc(s->U);
     CK(cudaMemcpy(s->het_d.p, s->het.data(), s->U, cudaMemcpyHostToDevice));
     s->model.alloc(5 * (size_t)K + 3 * (size_t)s->U);
@@ -380,6 +404,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     s->rerun.alloc(2 * kRoundSlots);
     s->rerun_h.alloc(2 * kRoundSlots);
     build_chunks(s);
+    trace.mark("small buffers + chunks");
     if (!s->legacy_py && K <= 256) s->vit_builder = std::thread([s]() { build_viterbi_tables(s); });
   } catch (const CudaFail &f) {
     return f.code;
