@@ -31,8 +31,12 @@ def make_params(ploidy, Z):
 def run_one(d, p, **kw):
     T.lib().titan_set_device(local)
     t0 = time.perf_counter()
-    cp = T.runEMclonalCN(d, p, verbose=False, **kw)
-    path = T.viterbiClonalCN(d, cp)
+    sol = T.Solver(d, p["genotypeParams"], len(p["cellPrevParams"]["s_0"]), kw.get("txnExpLen", 1e15), kw.get("txnZstrength", 5e5))
+    try:
+        cp = T.runEMclonalCN(d, p, verbose=False, solver=sol, **kw)
+        path = T.viterbiClonalCN(d, cp, solver=sol)
+    finally:
+        sol.close()
     return {"n": float(cp["n"][-1]), "phi": float(cp["phi"][-1]), "loglik": float(cp["loglik"][-1]), "iters": int(cp["n"].size - 1),
             "segments": int(1 + np.count_nonzero(np.diff(path))), "seconds": time.perf_counter() - t0}
 

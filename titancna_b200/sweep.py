@@ -179,8 +179,15 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
             return p
     if run_one is None:
         def run_one(d, p, **kw):
-            cp = runEMclonalCN(d, p, verbose=False, **kw)
-            path = viterbiClonalCN(d, cp)
+            # one device-resident solver per solution: the SNP columns are uploaded once and the Viterbi
+            # transition tables are built in the background while the EM runs
+            sol = Solver(d, p["genotypeParams"], len(p["cellPrevParams"]["s_0"]), kw.get("txnExpLen", 1e15),
+                         kw.get("txnZstrength", 5e5), device=device)
+            try:
+                cp = runEMclonalCN(d, p, verbose=False, solver=sol, **kw)
+                path = viterbiClonalCN(d, cp, solver=sol)
+            finally:
+                sol.close()
             return {"n": cp["n"][-1], "phi": cp["phi"][-1], "s": cp["s"][:, -1], "loglik": cp["loglik"][-1],
                     "iters": cp["n"].size - 1, "path": path}
     # `concurrent` > 1 runs that many of this rank's solutions at once (one host thread and one pair of CUDA
