@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY.  Follows R/utils.R:772-785 (decoupleMegaVar), :788-862 (decodeLOH, symmetric
 table), :865-913 (outputTitanResults core columns, correctResults=FALSE), :1065-1135
-(outputTitanSegments) and :1342-1401 (getMajorMinorCN) statement by statement, including the
-reference's quirks (cluster relabelling through sortS$ix; crossed Minor/Major assignment).
+(outputTitanSegments), :1342-1401 (getMajorMinorCN) and :1420-1498 (removeEmptyClusters, without its
+recomputeLogLik tail: the tests re-enter the oracle's own EM for that) statement by statement, including
+the reference's quirks (cluster relabelling through sortS$ix; crossed Minor/Major assignment; `s` re-sorted
+but piZ/rhoZ/mu subset in stored order; in-place relabelling loop).
 Parity unpinned: the reference holds no golden table for these functions.
 """
 import math
@@ -106,3 +108,76 @@ def output_segments(rows, sample):
                      "Clonal_Cluster": seg[0]["ClonalCluster"], "Cellular_Prevalence": seg[0]["CellularPrevalence"]})
         start = end + 1
     return segs
+
+
+def remove_empty_clusters(cp, rows, proportion_threshold=0.001, proportion_threshold_clonal=0.05):
+    """R/utils.R:1420-1498 on a list of row dicts.  Returns (new cp dict of plain lists / arrays, new rows)."""
+    rows = [dict(r) for r in rows]
+    s = [list(map(float, r)) for r in np.asarray(cp["s"], float).reshape(np.asarray(cp["s"]).shape[0], -1)]
+    Z = len(s)
+    n = [float(v) for v in np.atleast_1d(cp["n"])]
+    clust = {}
+    for cl in range(1, Z + 1):
+        cnt = 0
+        for r in rows:
+            if r["ClonalCluster"] == cl:
+                cnt += 1
+        frac = cnt / len(rows)
+        clust[cl] = None if (frac < proportion_threshold or (frac < proportion_threshold_clonal and cl == 1)) else cl
+    k = len(s[0]) - 1
+    s = [s[z] for z in sorted(range(Z), key=lambda z: (s[z][k], z))]
+    out = {"piZ": None, "rhoZ": None, "muC": None, "muR": None}
+    sP = {key: list(np.atleast_1d(v)) for key, v in (cp.get("cellPrevParams") or {}).items()}
+    kept = [cl for cl in range(1, Z + 1) if clust[cl] is not None]
+    if kept:
+        purity = (1 - s[kept[0] - 1][k]) * (1 - n[k])
+        n[k] = 1 - purity
+        s = [s[cl - 1] for cl in kept]
+        first = s[0][k]
+        for row in s:
+            row[k] = 1 - (1 - row[k]) / (1 - first)
+        idx = [cl - 1 for cl in kept]
+        for key in ("piZ", "rhoZ"):
+            if cp.get(key) is not None:
+                out[key] = np.asarray(cp[key])[idx]
+        for key in ("muC", "muR"):
+            if cp.get(key) is not None:
+                out[key] = np.asarray(cp[key])[:, idx]
+        sP = {key: [v[j] if j < len(v) else float("nan") for j in idx] for key, v in sP.items()}
+        for new, cl in enumerate(kept, start=1):
+            clust[cl] = new
+        for cl in range(1, Z + 1):
+            target = None
+            if clust[cl] is None:
+                right = [c for c in range(1, Z + 1) if clust[c] is not None and str(c) > str(cl)]
+                left = [c for c in range(1, Z + 1) if clust[c] is not None and str(c) < str(cl)]
+                if right:
+                    target = clust[right[0]]
+                elif left:
+                    target = clust[left[-1]]
+            else:
+                target = clust[cl]
+            if target is None:
+                continue
+            hit = [r for r in rows if r["ClonalCluster"] == cl]
+            for r in hit:
+                r["CellularPrevalence"] = 1 - s[target - 1][k]
+            for r in hit:
+                r["ClonalCluster"] = float(target)
+    else:
+        n[k] = 1 - s[0][k]
+        s = [s[0]]
+        s[0][k] = 0.0
+        sP = {key: [v[0] if len(v) else float("nan")] for key, v in sP.items()}
+        for key in out:
+            out[key] = cp.get(key)
+        for r in rows:
+            if r["TITANcall"] != "HET":
+                r["CellularPrevalence"] = 1
+                r["ClonalCluster"] = 1.0
+    new_cp = dict(cp)
+    new_cp.update({"s": np.array(s), "n": np.array(n), "cellPrevParams": {key: np.array(v) for key, v in sP.items()}})
+    for key, v in out.items():
+        if v is not None:
+            new_cp[key] = v
+    return new_cp, rows

@@ -191,7 +191,7 @@ def test_em_production_settings_synthetic():
     assert np.array_equal(gpath, wpath)
     # segment calls bit-exact (north_star): decode + segmenter on both paths
     from oracle import results_oracle as RO
-    segs = T.outputTitanSegments(T.outputTitanResults(data, got, gpath), "synthetic", got)
+    segs = T.outputTitanSegments(T.outputTitanResults(data, got, gpath, correctResults=False)["results"], "synthetic", got)
     wsegs = RO.output_segments(RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, want, wpath), "synthetic")
     assert segs["Length.snp."].size == len(wsegs)
     for k in ("Start_Position.bp.", "End_Position.bp.", "Length.snp.", "TITAN_state", "Copy_Number", "MinorCN", "MajorCN"):
@@ -384,3 +384,45 @@ def test_dense_kernel_cross_checks_structured_kernels(monkeypatch, golden):
     assert abs(a["loglik"] - b["loglik"]) <= 1e-12 * abs(b["loglik"])
     assert np.abs(np.exp(a["rho"]) - np.exp(b["rho"])).max() < 1e-9
     assert np.array_equal(pa, pb) and np.array_equal(pa, golden["ref_path_1e15"].astype(np.int32))
+
+
+def test_correct_results_reenters_the_estep_like_the_reference():
+    """outputTitanResults(correctResults=TRUE, recomputeLogLik=TRUE) -- the reference's default, SURVEY.md 3.4:
+    removeEmptyClusters prunes a cluster, rescales n / s, and runs runEMclonalCN(maxiter=1, fixed normal, no s /
+    ploidy update) with the NEW cluster count (R/utils.R:1500-1522).  The same corrected parameters go through the
+    oracle's EM; log-likelihood, means and posteriors must agree to the north_star tolerances."""
+    from oracle import results_oracle as RO
+    N, Z = 5000, 3
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=3, seed=21, mean_seg=300)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=Z, data=data)
+    cp = T.runEMclonalCN(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=3, verbose=False)
+    path = T.viterbiClonalCN(data, cp)
+    cp["txn_exp_len"], cp["txn_z_strength"] = 1e15, 1.0          # the fields R/utils.R:1514-1515 reads
+    share = [np.count_nonzero((path - 1) // 25 == z) / N for z in range(Z)]
+    thr = float(np.sort(share)[1]) * 0.999 + 1e-9                # prune exactly the least populated cluster(s)
+    out = T.outputTitanResults(data, cp, path, proportionThreshold=thr, proportionThresholdClonal=0.0, verbose=False)
+    got = out["convergeParams"]
+    rows = RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, cp, path)
+    want_cp, want_rows = RO.remove_empty_clusters(cp, rows, thr, 0.0)
+    newZ = want_cp["s"].shape[0]
+    assert 1 <= newZ < Z and got["s"].shape[0] == newZ
+    it = want_cp["n"].size - 1
+    po = {"genotypeParams": dict(cp["genotypeParams"]), "ploidyParams": dict(cp["ploidyParams"]),
+          "normalParams": dict(cp["normalParams"]), "cellPrevParams": dict(want_cp["cellPrevParams"])}
+    po["genotypeParams"].update(var_0=cp["var"][:, it], piG_0=cp["piG"][:, it])
+    po["normalParams"]["n_0"] = float(want_cp["n"][it])
+    po["ploidyParams"]["phi_0"] = float(cp["phi"][it])
+    po["cellPrevParams"].update(s_0=want_cp["s"][:, it], piZ_0=np.asarray(want_cp["piZ"])[:newZ, it])
+    want = O.run_em_clonal_cn(data, po, txnExpLen=1e15, txnZstrength=1.0, maxiter=1, normalEstimateMethod="fixed",
+                              estimateS=False, estimatePloidy=False, engine="port", threads=8)
+    assert abs(got["loglik"][it] - want["loglik"][-1]) <= LL_RTOL * abs(want["loglik"][-1])
+    assert np.array_equal(got["loglik"][:it], cp["loglik"][:it])
+    for k in ("muC", "muR"):
+        assert np.abs(got[k][:, :, it] - want[k][:, :, 1]).max() < POST_ATOL, k
+    assert got["rhoZ"].shape == (newZ, N) and got["rhoG"].shape == (25, N)
+    assert np.abs(got["rhoG"] - want["rhoG"]).max() < POST_ATOL
+    assert np.abs(got["rhoZ"] - want["rhoZ"]).max() < POST_ATOL
+    for k in ("ClonalCluster", "CellularPrevalence"):
+        a, b = np.asarray(out["corrResults"][k], float), np.array([r[k] for r in want_rows], float)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), k
+    assert np.nanmax(out["corrResults"]["ClonalCluster"]) <= newZ

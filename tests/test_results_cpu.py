@@ -20,7 +20,7 @@ def test_results_and_segments_match_loop_restatement(Z, s):
     U, N = 25, data["posn"].size
     path = np.repeat(rng.integers(1, U * Z + 1, size=N // 7 + 1), 7)[:N].astype(np.int32)
     cp = _fake_cp(Z, U, s)
-    res = R.outputTitanResults(data, cp, path)
+    res = R.outputTitanResults(data, cp, path, correctResults=False)["results"]
     rows = RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, cp, path)
     for k in ("CopyNumber", "TITANstate", "ClonalCluster", "CellularPrevalence", "AllelicRatio", "LogRatio"):
         a = np.asarray(res[k], float)
@@ -48,7 +48,7 @@ def test_segments_of_the_reference_fixture_path(golden):
     data = {"chr": golden["data_chr"], "posn": golden["data_posn"].astype(float), "ref": golden["data_ref"].astype(float),
             "tumDepth": golden["data_tumDepth"].astype(float), "logR": golden["data_logR"]}
     cp = {"s": golden["cp_s"], "var": golden["cp_var"], "useOutlierState": False, "symmetric": True}
-    res = R.outputTitanResults(data, cp, path)
+    res = R.outputTitanResults(data, cp, path, correctResults=False)["results"]
     segs = R.outputTitanSegments(res, "chr2", cp)
     joint_runs = 1 + np.count_nonzero(np.diff(path))
     geno_runs = 1 + np.count_nonzero(np.diff((path - 1) % 12))
@@ -68,5 +68,66 @@ def test_decode_tables_and_quirks():
         assert dec["G"][g] == call and dec["CN"][g] == cn
         assert R.getMajorMinorCN(g) == {"majorCN": RO._MM[g][0], "minorCN": RO._MM[g][1]}
         assert sum(RO._MM[g]) == cn
-    with pytest.raises(NotImplementedError):
-        R.outputTitanResults({}, {"useOutlierState": False, "symmetric": True}, [], correctResults=True)
+
+
+def _cluster_cp(Z, U, s_last, n_last=0.3, N=10):
+    rng = np.random.default_rng(7)
+    return {"s": np.column_stack([np.linspace(0.1, 0.5, Z), np.asarray(s_last, float)]), "var": np.zeros((U, 2)),
+            "n": np.array([0.5, n_last]), "phi": np.array([2.0, 2.1]), "piZ": rng.random((Z, 2)), "rhoZ": rng.random((Z, N)),
+            "muC": rng.random((U, Z, 2)), "muR": rng.random((U, Z, 2)), "loglik": np.array([-np.inf, -5.0]),
+            "cellPrevParams": {"s_0": np.linspace(0.1, 0.5, Z), "alphaSHyper": np.full(Z, 2.0), "betaSHyper": np.full(Z, 2.0),
+                               "kappaZHyper": np.full(Z, 2.0), "piZ_0": np.full(Z, 1 / Z)},
+            "useOutlierState": False, "symmetric": True}
+
+
+@pytest.mark.parametrize("name,Z,s_last,weights,thr", [
+    ("all kept", 3, [0.4, 0.01, 0.2], [0.3, 0.3, 0.4], 0.05),
+    ("clonal cluster below its own threshold", 3, [0.05, 0.3, 0.6], [0.03, 0.5, 0.47], 0.001),
+    ("middle cluster empty: reassigned to the right", 3, [0.3, 0.1, 0.2], [0.5, 0.01, 0.49], 0.05),
+    ("last cluster empty: reassigned to the left", 4, [0.1, 0.2, 0.3, 0.4], [0.4, 0.3, 0.29, 0.01], 0.05),
+    ("first two empty", 4, [0.4, 0.3, 0.2, 0.1], [0.01, 0.02, 0.5, 0.47], 0.05),
+    ("unsorted prevalences", 5, [0.5, 0.1, 0.3, 0.2, 0.05], [0.3, 0.02, 0.3, 0.03, 0.35], 0.05),
+    ("nothing populated", 3, [0.2, 0.1, 0.3], [0.02, 0.02, 0.02], 0.05),
+    ("single cluster", 1, [0.02], [0.9], 0.05)])
+def test_remove_empty_clusters_matches_loop_restatement(name, Z, s_last, weights, thr):
+    """R/utils.R:1420-1498 (the part of correctResults=TRUE before the E-step re-entry)."""
+    rng = np.random.default_rng(len(name))
+    N, U = 3000, 25
+    data, _ = synth.make_data(N, Z=max(Z, 1), maxCN=8, n_chr=3, seed=3, mean_seg=50)
+    w = np.asarray(weights, float)
+    lab = rng.choice(np.arange(Z + 1), size=N, p=np.append(w, 1 - w.sum()))      # label Z -> diploid HET (no cluster)
+    geno = np.where(lab == Z, 4, rng.choice([1, 2, 3, 5, 6, 9, 14, 25], size=N))  # unit state 4 = HET
+    path = (geno + np.minimum(lab, Z - 1) * U).astype(np.int32)
+    cp = _cluster_cp(Z, U, s_last, N=N)
+    out = R.outputTitanResults(data, cp, path, correctResults=True, proportionThreshold=thr, recomputeLogLik=False)
+    rows = RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, cp, path)
+    want_cp, want_rows = RO.remove_empty_clusters(cp, rows, thr, 0.05)
+    got_cp, got = out["convergeParams"], out["corrResults"]
+    for k in ("ClonalCluster", "CellularPrevalence"):
+        a, b = np.asarray(got[k], float), np.array([r[k] for r in want_rows], float)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (name, k)
+        assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), (name, k)
+    for k in ("s", "n", "piZ", "rhoZ", "muC", "muR"):
+        assert np.array_equal(np.asarray(got_cp[k]), np.asarray(want_cp[k])), (name, k)
+    for k in cp["cellPrevParams"]:
+        assert np.array_equal(got_cp["cellPrevParams"][k], want_cp["cellPrevParams"][k]), (name, k)
+    # the inputs are untouched (R passes by value) and the uncorrected table is returned next to the corrected one
+    assert np.array_equal(np.asarray(cp["s"])[:, 1], np.asarray(s_last, float))
+    base = R.outputTitanResults(data, cp, path, correctResults=False)
+    assert base["corrResults"] is None and base["convergeParams"] is cp
+    a, b = np.asarray(out["results"]["ClonalCluster"]), np.asarray(base["results"]["ClonalCluster"])
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    if name == "all kept":
+        assert got_cp["s"].shape[0] == Z and got_cp["n"][1] == 1 - (1 - 0.01) * (1 - 0.3)
+    if name == "nothing populated":
+        assert got_cp["s"].shape == (1, 2) and got_cp["s"][0, 1] == 0.0 and got_cp["n"][1] == 1 - 0.1
+
+
+def test_recompute_loglik_without_transition_fields_is_an_error_not_undefined_behaviour():
+    """R/utils.R:1514-1515 reads convergeParams$txn_exp_len / $txn_z_strength, which nothing sets: the reference
+    passes NULL to its C code (SURVEY.md App. B #7).  The mirror refuses instead."""
+    data, _ = synth.make_data(500, Z=2, maxCN=8, n_chr=2, seed=3, mean_seg=50)
+    cp = _cluster_cp(2, 25, [0.1, 0.3], N=500)
+    path = np.full(500, 1, dtype=np.int32)
+    with pytest.raises(ValueError, match="txn_exp_len"):
+        R.outputTitanResults(data, cp, path)            # reference defaults: correctResults=TRUE, recomputeLogLik=TRUE

@@ -6,7 +6,9 @@ chromosome with their medians.  O(N) host table work in the reference (R) and he
 tables are dicts of equal-length numpy columns.  Quirks of the reference are preserved on purpose:
 the cluster relabelling `sortS$ix[Zclust]` (:891-894) and the crossed MinorCN/MajorCN assignment
 (:1107-1108 with the inverted field names of getMajorMinorCN :1342-1401).
-Not covered: correctResults=TRUE (removeEmptyClusters, R/utils.R:1420-1524), subclone profiles, file output.
+correctResults=TRUE (removeEmptyClusters, R/utils.R:1420-1524) is covered, including the hidden re-entry into the
+E-step (recomputeLogLik=TRUE -> runEMclonalCN(maxiter=1, fixed normal, no s / ploidy update)).
+Not covered: subclone profiles, posterior-probability columns, file output.
 """
 from __future__ import annotations
 
@@ -49,10 +51,14 @@ def getMajorMinorCN(state, symmetric=True):
     return {"majorCN": int(_MAJOR_FIELD[state]), "minorCN": int(_MINOR_FIELD[state])}
 
 
-def outputTitanResults(data, convergeParams, optimalPath, correctResults=False, **_ignored):
-    """R/utils.R:865-976 with correctResults=FALSE: the per-SNP result table."""
-    if correctResults:
-        raise NotImplementedError("correctResults=TRUE (removeEmptyClusters) is not covered")
+def outputTitanResults(data, convergeParams, optimalPath, filename=None, is_haplotypeData=False, posteriorProbs=False,
+                       subcloneProfiles=False, correctResults=True, proportionThreshold=0.05,
+                       proportionThresholdClonal=0.05, recomputeLogLik=True, rerunViterbi=False, verbose=True):
+    """R/utils.R:865-976.  Returns dict(results = per-SNP table, corrResults = the table after removeEmptyClusters
+    (None with correctResults=False), convergeParams = the -- possibly corrected -- parameter list), as the
+    reference's list(results, corrResults, convergeParams).  Tables are dicts of equal-length numpy columns."""
+    if filename is not None or posteriorProbs or subcloneProfiles or is_haplotypeData:
+        raise NotImplementedError("file output, posterior columns, subclone profiles and haplotype columns are not covered")
     cp = convergeParams
     if cp.get("useOutlierState") is None:
         raise ValueError("convergeParams does not contain element: useOutlierState.")
@@ -74,10 +80,123 @@ def outputTitanResults(data, convergeParams, optimalPath, correctResults=False, 
     Sout[ok] = s[Zclust[ok].astype(np.int64) - 1]
     ref0 = np.asarray(data.get("refOriginal", data["ref"]), float)
     depth = np.asarray(data["tumDepth"], float)
-    return {"Chr": np.asarray(data["chr"]), "Position": np.asarray(data["posn"]), "RefCount": ref0, "Depth": depth,
-            "AllelicRatio": ref0 / depth, "LogRatio": np.log2(np.exp(np.asarray(data["logR"], float))),
-            "CopyNumber": CN, "TITANstate": G, "TITANcall": calls, "ClonalCluster": Zclust,
-            "CellularPrevalence": 1 - Sout}
+    outmat = {"Chr": np.asarray(data["chr"]), "Position": np.asarray(data["posn"]), "RefCount": ref0, "Depth": depth,
+              "AllelicRatio": ref0 / depth, "LogRatio": np.log2(np.exp(np.asarray(data["logR"], float))),
+              "CopyNumber": CN, "TITANstate": G, "TITANcall": calls, "ClonalCluster": Zclust,
+              "CellularPrevalence": 1 - Sout}
+    corrmat = None
+    if correctResults:
+        corr = removeEmptyClusters(data, cp, outmat, proportionThreshold=proportionThreshold,
+                                   proportionThresholdClonal=proportionThresholdClonal,
+                                   recomputeLogLik=recomputeLogLik, verbose=verbose)
+        corrmat, cp = corr["results"], corr["convergeParams"]
+    return {"results": outmat, "corrResults": corrmat, "convergeParams": cp}
+
+
+def removeEmptyClusters(data, convergeParams, results, proportionThreshold=0.001, proportionThresholdClonal=0.05,
+                        recomputeLogLik=True, verbose=True, solver=None):
+    """R/utils.R:1420-1524.  Drops clonal clusters that hold too small a share of the SNPs, re-expresses normal
+    contamination and cellular prevalences relative to the first kept cluster, relabels the result table and --
+    recomputeLogLik -- re-enters the E-step once with the corrected parameters.  Inputs are not modified.
+    Reference quirks kept: `s` is re-sorted by its last column while piZ / rhoZ / muR / muC are subset in their
+    stored order (:1434-1448); the relabelling loop edits the table in place, cluster by cluster (:1454-1470);
+    with no populated cluster the first row of the sorted `s` is kept whatever the table holds (:1474-1477)."""
+    cp = dict(convergeParams)
+    res = {k: np.array(v, copy=True) for k, v in results.items()}
+    s = np.array(np.asarray(cp["s"], float).reshape(np.asarray(cp["s"]).shape[0], -1), copy=True)
+    Z = s.shape[0]
+    n = np.array(np.atleast_1d(cp["n"]), dtype=float, copy=True)
+    cc = res["ClonalCluster"] = np.asarray(res["ClonalCluster"], float)
+    prev = res["CellularPrevalence"] = np.asarray(res["CellularPrevalence"], float)
+    nrow = cc.size
+    clust = list(range(1, Z + 1))                          # NA -> None
+    for cl in range(1, Z + 1):
+        frac = np.count_nonzero(cc == cl) / nrow
+        if frac < proportionThreshold or (frac < proportionThresholdClonal and cl == 1):
+            clust[cl - 1] = None
+    k = s.shape[1] - 1
+    s = s[np.argsort(s[:, k], kind="stable")]              # order(..., decreasing = FALSE)
+    sP = {key: np.array(np.atleast_1d(v), copy=True) for key, v in (cp.get("cellPrevParams") or {}).items()}
+
+    def sub(v, idx):                                       # `[`(v, idx): NA beyond the end
+        v = np.asarray(v)
+        out = np.full(len(idx), np.nan) if v.dtype.kind == "f" else np.zeros(len(idx), dtype=v.dtype)
+        for q, j in enumerate(idx):
+            if j < v.size:
+                out[q] = v[j]
+        return out
+
+    if any(c is not None for c in clust):
+        keep = [j for j, c in enumerate(clust) if c is not None]
+        purity = (1 - s[keep[0], k]) * (1 - n[k])
+        n[k] = 1 - purity
+        s = s[keep]
+        s[:, k] = 1 - (1 - s[:, k]) / (1 - s[0, k])
+        for key, axis in (("piZ", 0), ("rhoZ", 0), ("muC", 1), ("muR", 1)):
+            if cp.get(key) is not None:
+                cp[key] = np.take(np.asarray(cp[key]), keep, axis=axis)
+        sP = {key: sub(v, keep) for key, v in sP.items()}
+        lab = 0
+        for j in range(Z):
+            if clust[j] is not None:
+                lab += 1
+                clust[j] = lab
+        names = [str(j + 1) for j in range(Z)]
+        for cl in range(1, Z + 1):                         # in place, in this order
+            rows = cc == cl
+            if clust[cl - 1] is None:
+                right = [j for j in range(Z) if clust[j] is not None and names[j] > str(cl)]   # character comparison (:1458)
+                left = [j for j in range(Z) if clust[j] is not None and names[j] < str(cl)]
+                if right:
+                    prev[rows] = 1 - s[clust[right[0]] - 1, k]
+                    cc[rows] = clust[right[0]]
+                elif left:
+                    prev[rows] = 1 - s[clust[left[-1]] - 1, k]
+                    cc[rows] = clust[left[-1]]
+            else:
+                prev[rows] = 1 - s[clust[cl - 1] - 1, k]
+                cc[rows] = clust[cl - 1]
+    else:
+        n[k] = 1 - s[0, k]
+        s = s[:1]
+        s[:, k] = 0.0
+        sP = {key: sub(v, [0]) for key, v in sP.items()}
+        not_het = np.asarray(res["TITANcall"]) != "HET"
+        prev[not_het] = 1
+        cc[not_het] = 1
+    cp["s"], cp["n"], cp["cellPrevParams"] = s, n, sP
+
+    if recomputeLogLik:
+        if cp.get("txn_exp_len") is None or cp.get("txn_z_strength") is None:
+            raise ValueError("removeEmptyClusters(recomputeLogLik=TRUE) reads convergeParams$txn_exp_len and $txn_z_strength "
+                             "(R/utils.R:1514-1515), which runEMclonalCN does not set: the reference passes NULL and its C "
+                             "code then reads a zero-length vector (undefined behaviour).  Set both fields, or call with "
+                             "recomputeLogLik=FALSE as scripts/R_scripts/titanCNA.R:266 does.")
+        from .hmm import runEMclonalCN
+        it = n.size - 1
+        newZ = s.shape[0]
+        new = {"genotypeParams": dict(cp["genotypeParams"]), "ploidyParams": dict(cp["ploidyParams"]),
+               "normalParams": dict(cp["normalParams"]), "cellPrevParams": dict(sP)}
+        new["genotypeParams"]["var_0"] = np.asarray(cp["var"], float)[:, it]
+        if cp.get("varR") is not None:
+            new["genotypeParams"]["varR_0"] = np.asarray(cp["varR"], float)[:, it]
+        new["genotypeParams"]["piG_0"] = np.asarray(cp["piG"], float)[:, it]
+        new["normalParams"]["n_0"] = float(n[it])
+        new["ploidyParams"]["phi_0"] = float(np.atleast_1d(cp["phi"])[it])
+        new["cellPrevParams"]["s_0"] = s[:, it].copy()
+        new["cellPrevParams"]["piZ_0"] = np.asarray(cp["piZ"], float)[:newZ, it]
+        p = runEMclonalCN(data, new, maxiter=1, txnExpLen=float(cp["txn_exp_len"]), txnZstrength=float(cp["txn_z_strength"]),
+                          useOutlierState=False, normalEstimateMethod="fixed", estimateS=False, estimatePloidy=False,
+                          verbose=verbose, solver=solver if getattr(solver, "Z", None) == newZ else None)
+        ll = np.array(np.atleast_1d(cp["loglik"]), dtype=float, copy=True)
+        ll[it] = p["loglik"][-1]
+        cp["loglik"] = ll
+        for key in ("muC", "muR"):
+            m = np.array(cp[key], dtype=float, copy=True)
+            m[:, :, it] = p[key][:, :, 1] if p[key].shape[1] == m.shape[1] else p[key][:, :1, 1]   # R recycles U values over the clusters
+            cp[key] = m
+        cp["rhoZ"], cp["rhoG"] = p["rhoZ"], p["rhoG"]
+    return {"convergeParams": cp, "results": res}
 
 
 def outputTitanSegments(results, id, convergeParams=None):
