@@ -23,7 +23,7 @@ args = (0.45, sP["s_0"], 2.04, g["var_0"], g["piG_0"], sP["piZ_0"], g)
 for _ in range(a.steps):
     out = sol.estep(*args)
 tm = sol.timing()
-print("estep ms", tm["last_estep_ms"], "fwd r0", tm["last_fwd_r0_ms"], "bwd r0", tm["last_bwd_r0_ms"], "rounds", tm["last_fwd_rounds"], tm["last_bwd_rounds"], "ll", out["loglik"])
+print("estep ms", round(tm["last_estep_ms"], 3), "fwd all", round(tm["last_fwd_ms"], 3), "bwd all", round(tm["last_bwd_ms"], 3), "fwd r0", tm["last_fwd_r0_ms"], "bwd r0", tm["last_bwd_r0_ms"], "rounds", tm["last_fwd_rounds"], tm["last_bwd_rounds"], "ll", out["loglik"])
 if a.viterbi:
     path = sol.viterbi(*args)
     print("viterbi ms", sol.timing()["last_viterbi_ms"], "segments", 1 + np.count_nonzero(np.diff(path)))
