@@ -203,6 +203,11 @@ typedef struct titan_timing {
 } titan_timing;
 int titan_solver_timing(const titan_solver *s, titan_timing *t);
 
+/* Device buffers of destroyed solvers stay cached in the CUDA memory pool of the current device (a sweep
+ * creates one solver per solution; cudaMalloc/cudaFree of such blocks cost more than an E-step).  This
+ * returns the cached memory to the driver.  No counterpart in the reference (R frees through its GC). */
+int titan_release_cached_memory(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,7 @@ EXPORTS = [
     "titan_fwd_back_clonalCN", "titan_viterbi_clonalCN", "titan_get_position_overlap",
     "titan_solver_create", "titan_solver_destroy", "titan_solver_configure", "titan_solver_set_stream",
     "titan_estep", "titan_viterbi", "titan_em_run", "titan_mstep", "titan_solver_timing",
+    "titan_release_cached_memory",
 ]
 
 _lib = None

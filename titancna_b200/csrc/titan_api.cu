@@ -5,6 +5,7 @@
 #include "../../include/titancna_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -75,6 +76,23 @@ extern "C" int titan_set_device(int device) {
 // ---------------------------------------------------------------------------------------------
 // solver
 // ---------------------------------------------------------------------------------------------
+// Device buffers come from the stream-ordered allocator with a pool that never shrinks on its own: a sweep
+// creates and destroys a solver (hundreds of MB) per solution, and cudaMalloc / cudaFree of such blocks
+// sporadically cost 50-500 ms each (unmap / remap), several times the E-step.  Ordering contract: every API
+// entry leaves its streams synchronised and ~titan_solver synchronises before its members are released, so
+// a block is never returned to the pool while work on it is in flight.
+static void pool_prepare() {
+  static thread_local int prepared_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == prepared_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  prepared_dev = dev;
+}
+
 template <class T>
 struct DevBuf {
   T *p = nullptr;
@@ -82,11 +100,13 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    CK(cudaMalloc(&p, count * sizeof(T)));
+    pool_prepare();
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), cudaStreamPerThread));
+    CK(cudaStreamSynchronize(cudaStreamPerThread));     // usable from any stream from here on
     n = count;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, cudaStreamPerThread);
     p = nullptr;
     n = 0;
   }
@@ -168,6 +188,8 @@ struct titan_solver {
 
   ~titan_solver() {
     if (vit_builder.joinable()) vit_builder.join();
+    if (stream) cudaStreamSynchronize(stream);          // members (device buffers) go back to the pool after this body
+    if (stream_b) cudaStreamSynchronize(stream_b);
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
     for (auto &e : ev_sync)
@@ -294,6 +316,44 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     const int64_t N = in.N;
     const int K = s->K;
 
+    // per-SNP records (lgamma bracket from a host table): built on worker threads while this thread hashes the gaps
+    std::vector<SnpRec> rec;
+    std::atomic<int64_t> bad_snp{-1};
+    struct Joiner {
+      std::thread t;
+      void join() { if (t.joinable()) t.join(); }
+      ~Joiner() { join(); }
+    } rec_builder;
+    if (!s->legacy_py && in.ref && in.depth && in.logR) {
+      rec.resize((size_t)N);
+      rec_builder.t = std::thread([&rec, &bad_snp, &in, N]() {
+        double dmax = 0;
+        for (int64_t t = 0; t < N; ++t) dmax = std::max(dmax, in.depth[t]);
+        th::LgammaTable tab;
+        if (dmax >= 0 && dmax < 1e7) tab.ensure((int64_t)dmax);       // shared read-only table; larger depths use lgamma directly
+        const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (unsigned w = 0; w < nt; ++w)
+          pool.emplace_back([&, w]() {
+            th::LgammaTable own;                                        // only touched for depths beyond the shared table
+            const int64_t t0 = N * w / nt, t1 = N * (w + 1) / nt;
+            for (int64_t t = t0; t < t1; ++t) {
+              const double x = in.ref[t], d = in.depth[t];
+              if (!(x == x) || !(d == d) || !(in.logR[t] == in.logR[t])) {
+                int64_t expect = -1;
+                bad_snp.compare_exchange_strong(expect, t);
+                return;
+              }
+              rec[t].x = x;
+              rec[t].nx = d - x;
+              rec[t].lr = in.logR[t];
+              rec[t].lb = (d >= 0 && d < (double)tab.v.size()) ? th::binom_log_norm(x, d, tab) : th::binom_log_norm(x, d, own);
+            }
+          });
+        for (auto &th_ : pool) th_.join();
+      });
+    }
+
     // host-exact transition terms (parameter independent).  exp() is evaluated once per DISTINCT gap
     // length (an open-addressing table keyed on the gap's bit pattern), then gaps that round to the
     // same (rhoG, rhoZ) pair are merged: the Viterbi tables are built per distinct pair.
@@ -375,18 +435,10 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
       s->snp.alloc(1);
     } else {
       if (!in.ref || !in.depth || !in.logR) return fail(TITAN_ERR_ARG, "ref, tumDepth and logR columns are required");
-      std::vector<SnpRec> rec((size_t)N);
-      th::LgammaTable tab;
-      for (int64_t t = 0; t < N; ++t) {
-        double x = in.ref[t], d = in.depth[t];
-        if (!(x == x) || !(d == d) || !(in.logR[t] == in.logR[t]))
-          return fail(TITAN_ERR_ARG, "NA/NaN in the data columns at SNP %lld (filterData removes these, R/utils.R:273-310)",
-                      (long long)t);
-        rec[t].x = x;
-        rec[t].nx = d - x;
-        rec[t].lr = in.logR[t];
-        rec[t].lb = th::binom_log_norm(x, d, tab);
-      }
+      rec_builder.join();
+      if (bad_snp >= 0)
+        return fail(TITAN_ERR_ARG, "NA/NaN in the data columns at SNP %lld (filterData removes these, R/utils.R:273-310)",
+                    (long long)bad_snp);
       s->snp.alloc(N);
       CK(cudaMemcpy(s->snp.p, rec.data(), sizeof(SnpRec) * N, cudaMemcpyHostToDevice));
     }
@@ -456,6 +508,20 @@ extern "C" int titan_solver_set_stream(titan_solver *s, void *cuda_stream) {
     if (e != cudaSuccess) return fail(TITAN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     s->own_stream = true;
   }
+  return TITAN_OK;
+}
+
+extern "C" int titan_release_cached_memory(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaMemPool_t pool;
+  e = cudaDeviceGetDefaultMemPool(&pool, dev);
+  if (e == cudaSuccess) {
+    cudaDeviceSynchronize();
+    e = cudaMemPoolTrimTo(pool, 0);
+  }
+  if (e != cudaSuccess) return fail(TITAN_ERR_CUDA, "cudaMemPoolTrimTo: %s", cudaGetErrorString(e));
   return TITAN_OK;
 }
 
