@@ -426,3 +426,19 @@ def test_correct_results_reenters_the_estep_like_the_reference():
         a, b = np.asarray(out["corrResults"][k], float), np.array([r[k] for r in want_rows], float)
         assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), k
     assert np.nanmax(out["corrResults"]["ClonalCluster"]) <= newZ
+
+
+def test_sweep_with_selection_on_one_gpu():
+    """TitanCNA.snakefile:8-52 + selectSolution.R in one process: every (ploidy, numClusters) solution through
+    runEMclonalCN + viterbiClonalCN + result table + S_Dbw, then the reference's selection rule."""
+    data, _ = synth.make_data(6000, Z=2, maxCN=8, n_chr=4, seed=31, mean_seg=300)
+    out, info = T.run_sweep(data, 0, 1, ploidies=(2, 3), clusters=(1, 2), maxiter=3, txnExpLen=1e15, txnZstrength=1.0)
+    assert len(out) == 4 and sorted((o["ploidy_0"], o["numClusters"]) for o in out) == [(2, 1), (2, 2), (3, 1), (3, 2)]
+    for o in out:
+        assert np.isfinite(o["loglik"]) and np.isfinite(o["sdbw"]) and o["sdbw"] > 0
+        assert int(np.sum(o["segs"]["Length.snp."])) == 6000
+    best = T.selectSolution(out)
+    assert (best["ploidy_0"], best["numClusters"]) in {(o["ploidy_0"], o["numClusters"]) for o in out}
+    from oracle import selection_oracle as SO
+    want = SO.select_solution(out)
+    assert (best["ploidy_0"], best["numClusters"]) == (want["ploidy_0"], want["numClusters"])

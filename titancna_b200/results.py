@@ -199,6 +199,22 @@ def removeEmptyClusters(data, convergeParams, results, proportionThreshold=0.001
     return {"convergeParams": cp, "results": res}
 
 
+def _segment_medians(v, seg_id, nseg):
+    """round(median(v[segment], na.rm = TRUE), 6) for every segment at once (one sort instead of one per segment)."""
+    v = np.asarray(v, float)
+    ok = ~np.isnan(v)
+    order = np.lexsort((v[ok], seg_id[ok]))
+    sv, sid = v[ok][order], seg_id[ok][order]
+    cnt = np.bincount(sid, minlength=nseg)
+    first = np.cumsum(cnt) - cnt
+    out = np.full(nseg, np.nan)
+    has = cnt > 0
+    lo = first[has] + (cnt[has] - 1) // 2
+    hi = first[has] + cnt[has] // 2
+    out[has] = (sv[lo] + sv[hi]) / 2
+    return np.round(out, 6)
+
+
 def outputTitanSegments(results, id, convergeParams=None):
     """R/utils.R:1065-1135: run-length segments of TITANstate per chromosome."""
     state = np.asarray(results["TITANstate"])
@@ -210,8 +226,8 @@ def outputTitanSegments(results, id, convergeParams=None):
     end = np.append(start[1:], n) - 1
     ar = np.maximum(results["AllelicRatio"], 1 - np.asarray(results["AllelicRatio"]))
     lr = np.asarray(results["LogRatio"])
-    med_ar = np.array([np.round(np.nanmedian(ar[a:b + 1]), 6) for a, b in zip(start, end)])
-    med_lr = np.array([np.round(np.nanmedian(lr[a:b + 1]), 6) for a, b in zip(start, end)])
+    seg_id = np.cumsum(brk) - 1
+    med_ar, med_lr = _segment_medians(ar, seg_id, start.size), _segment_medians(lr, seg_id, start.size)
     st = state[start].astype(np.int64)
     return {"Sample": np.full(start.size, id), "Chromosome": chr_[start].astype(str),
             "Start_Position.bp.": np.asarray(results["Position"])[start], "End_Position.bp.": np.asarray(results["Position"])[end],

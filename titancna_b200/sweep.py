@@ -20,6 +20,8 @@ from . import _lib
 from ._lib import c_double_p, check, lib
 from .hmm import Solver, _check_params, _hyper, chromosome_offsets, runEMclonalCN, viterbiClonalCN
 from .params import loadDefaultParameters
+from .results import outputTitanResults, outputTitanSegments
+from .selection import outputModelParameters, selectSolution
 
 
 def lpt_assign(costs, n_bins):
@@ -165,10 +167,11 @@ def runEMclonalCN_sharded(data, params, rank, world, txnExpLen=1e15, txnZstrengt
 
 
 def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), maxCN=8, device=None, make_params=None,
-              run_one=None, gather=True, concurrent=1, **em_kwargs):
+              run_one=None, gather=True, concurrent=1, keep_path=False, **em_kwargs):
     """The snakemake sweep in one job: rank r runs the solutions LPT assigns to it and the final parameter sets
     are gathered (all_gather_object) -- no collective on the data path.  `run_one(data, params, **em_kwargs)` defaults
-    to runEMclonalCN + viterbiClonalCN on this rank's GPU."""
+    to runEMclonalCN + viterbiClonalCN on this rank's GPU followed by the result table, segments and S_Dbw index;
+    `selectSolution(out)` then applies the reference's selection rule to the gathered records."""
     grid, costs = solution_grid(ploidies, clusters)
     where, load = lpt_assign(costs, world)
     mine = [grid[i] for i in range(len(grid)) if where[i] == rank]
@@ -188,8 +191,18 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
                 path = viterbiClonalCN(d, cp, solver=sol)
             finally:
                 sol.close()
-            return {"n": cp["n"][-1], "phi": cp["phi"][-1], "s": cp["s"][:, -1], "loglik": cp["loglik"][-1],
-                    "iters": cp["n"].size - 1, "path": path}
+            # what scripts/R_scripts/titanCNA.R:263-285 derives per solution: corrected result table, segments and
+            # the S_Dbw validity index that selectSolution.R ranks the cluster counts by
+            res = outputTitanResults(d, cp, path, proportionThreshold=0.05, proportionThresholdClonal=0.05,
+                                     recomputeLogLik=False, verbose=False)
+            segs = outputTitanSegments(res["corrResults"], "sweep", res["convergeParams"])
+            mp = outputModelParameters(res["convergeParams"], res["corrResults"])
+            out = {"n": cp["n"][-1], "phi": cp["phi"][-1], "s": cp["s"][:, -1], "loglik": cp["loglik"][-1],
+                   "iters": cp["n"].size - 1, "sdbw": mp["S_Dbw"], "dens_bw": mp["dens_bw"], "scat": mp["scat"],
+                   "segs": {"TITAN_call": segs["TITAN_call"], "Length.snp.": segs["Length.snp."]}}
+            if keep_path:
+                out["path"] = path
+            return out
     # `concurrent` > 1 runs that many of this rank's solutions at once (one host thread and one pair of CUDA
     # streams each; ctypes releases the GIL): the verification rounds of one solution are latency-bound and
     # leave most SMs idle, which a second solution's rounds fill.
