@@ -56,6 +56,24 @@ def main():
     dst = os.path.join(ROOT, "tests", "golden", "emresults_chr2.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst), "bytes")
+    staging()
+
+
+def staging():
+    """tests/golden/allelecounts_chr2.npz: the numeric columns of inst/extdata/test_alleleCounts_chr2.txt, the file the
+    fixture's `data` object was built from (vignettes/TitanCNA.Rnw:93-120) -- pins loadAlleleCounts / filterData."""
+    cols = {"chr": [], "position": [], "refCount": [], "NrefCount": []}
+    with open(os.path.join(REF, "inst", "extdata", "test_alleleCounts_chr2.txt")) as fh:
+        next(fh)
+        for line in fh:
+            f = line.rstrip("\n").split("\t")
+            if len(f) < 6 or not f[0]:
+                continue
+            cols["chr"].append(int(f[0])); cols["position"].append(int(f[1]))
+            cols["refCount"].append(int(f[3])); cols["NrefCount"].append(int(f[5]))
+    dst = os.path.join(ROOT, "tests", "golden", "allelecounts_chr2.npz")
+    np.savez_compressed(dst, **{k: np.asarray(v, dtype=np.int32) for k, v in cols.items()})
+    print("wrote", dst, os.path.getsize(dst), "bytes")
 
 
 if __name__ == "__main__":
