@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Follows R/utils.R:772-785 (decoupleMegaVar), :788-862 (decodeLOH, symmetric
 table), :865-913 (outputTitanResults core columns, correctResults=FALSE), :1065-1135
-(outputTitanSegments), :1342-1401 (getMajorMinorCN) and :1420-1498 (removeEmptyClusters, without its
+(outputTitanSegments), :1175-1340 (correctIntegerCN, logRbasedCN, allelicRatioBasedCN), :1342-1401
+(getMajorMinorCN) and :1420-1498 (removeEmptyClusters, without its
 recomputeLogLik tail: the tests re-enter the oracle's own EM for that) statement by statement, including
 the reference's quirks (cluster relabelling through sortS$ix; crossed Minor/Major assignment; `s` re-sorted
 but piZ/rhoZ/mu subset in stored order; in-place relabelling loop).
@@ -181,3 +182,105 @@ def remove_empty_clusters(cp, rows, proportion_threshold=0.001, proportion_thres
         if v is not None:
             new_cp[key] = v
     return new_cp, rows
+
+
+def _isna(v):
+    return v is None or v != v
+
+
+def logr_based_cn(x, purity, ploidy, cell_prev, cn=2):
+    if _isna(x):
+        return float("nan")
+    cp = 1.0 if _isna(cell_prev) else cell_prev
+    ct = (2.0 ** x) * (cn * (1 - purity) + purity * ploidy * (cn / 2)) - cn * (1 - purity) - cn * purity * (1 - cp)
+    ct = ct / (purity * cp)
+    return max(ct, 1 / 2 ** 6)
+
+
+def allelic_ratio_based_cn(x, ct, purity, cell_prev, rn=0.5, cn=2):
+    if _isna(x) or _isna(ct):
+        return float("nan")
+    cp = 1.0 if _isna(cell_prev) else cell_prev
+    total = (1 - purity) * cn + purity * (1 - cp) * cn + purity * cp * ct
+    rt = (x * total - ((1 - purity) * rn * cn + purity * (1 - cp) * rn * cn)) / (purity * cp * ct)
+    return max(min(rt, 1.0), 0.0)
+
+
+def _rint(v):
+    return float(round(v)) if not _isna(v) else float("nan")      # Python round(): half to even, like R
+
+
+def correct_integer_cn(cn_rows, seg_rows, purity, ploidy, max_auto=None, max_x=None, correct_homd=True,
+                       min_purity=0.2, gender="male", chrs=None):
+    """R/utils.R:1175-1312 on lists of row dicts (per-SNP table rows, segment rows)."""
+    chrs = [str(c) for c in (list(range(1, 23)) + ["X"] if chrs is None else chrs)]
+    cn_rows, seg_rows = [dict(r) for r in cn_rows], [dict(r) for r in seg_rows]
+    autos = [c for c in chrs if "X" not in c and "Y" not in c]
+    xs = [c for c in chrs if "X" in c]
+    if max_auto is None:
+        max_auto = max(r["Copy_Number"] for r in seg_rows if str(r["Chromosome"]) in autos and not _isna(r["Copy_Number"]))
+    if max_x is None and gender == "female" and xs:
+        max_x = max(r["Copy_Number"] for r in seg_rows if str(r["Chromosome"]) in xs and not _isna(r["Copy_Number"]))
+    names = ["HOMD", "HETD", "NEUT", "GAIN", "AMP", "HLAMP"] + ["HLAMP"] * 1000
+    names_x = ["HETD", "NEUT", "GAIN", "AMP", "HLAMP"] + ["HLAMP"] * 1000
+    for rows, ckey, lkey, rkey, pkey, nkey in ((seg_rows, "Chromosome", "Median_logR", "Median_Ratio", "Cellular_Prevalence", "Copy_Number"),
+                                               (cn_rows, "Chr", "LogRatio", "AllelicRatio", "CellularPrevalence", "CopyNumber")):
+        for r in rows:
+            c = str(r[ckey])
+            r["logR_Copy_Number"] = r["Corrected_logR"] = r["Corrected_Ratio"] = float("nan")
+            if c in chrs:
+                r["logR_Copy_Number"] = logr_based_cn(r[lkey], purity, ploidy, r[pkey], 2)
+                r["Corrected_logR"] = math.log2(r["logR_Copy_Number"] / ploidy)
+                r["Corrected_Ratio"] = allelic_ratio_based_cn(r[rkey], r["logR_Copy_Number"], purity, r[pkey])
+            if gender == "male" and c in xs:
+                r["logR_Copy_Number"] = logr_based_cn(r[lkey], purity, ploidy, r[pkey], 1)
+                r["Corrected_logR"] = math.log2(r["logR_Copy_Number"] / (ploidy / 2))
+                r["Corrected_Ratio"] = float("nan")
+            r["Corrected_Copy_Number"] = float(r[nkey]) if not _isna(r[nkey]) else float("nan")
+    for r in seg_rows:
+        r["Corrected_MajorCN"], r["Corrected_MinorCN"] = float(r["MajorCN"]), float(r["MinorCN"])
+    if purity >= min_purity:
+        touched = set()
+        for rows, ckey, nkey, is_seg in ((seg_rows, "Chromosome", "Copy_Number", True), (cn_rows, "Chr", "CopyNumber", False)):
+            for idx, r in enumerate(rows):
+                c = str(r[ckey])
+                hit = False
+                if c in chrs and not _isna(r[nkey]) and r[nkey] >= max_auto:
+                    hit = True
+                if correct_homd and c in chrs and not _isna(r[nkey]) and r[nkey] == 0:
+                    hit = True
+                if not is_seg and c in chrs and _isna(r[nkey]):
+                    hit = True
+                if gender == "male" and c in xs:
+                    hit = True
+                if hit:
+                    r["Corrected_Copy_Number"] = _rint(r["logR_Copy_Number"])
+                    if is_seg:
+                        touched.add(idx)
+        for idx, r in enumerate(seg_rows):
+            rl, cc = _rint(r["logR_Copy_Number"]), r["Corrected_Copy_Number"]
+            if _isna(rl) or _isna(cc):
+                continue
+            if ((rl < ploidy and cc > ploidy) or (rl > ploidy and cc < ploidy)) and abs(rl - cc) > 2:
+                r["Corrected_Copy_Number"] = rl
+                touched.add(idx)
+                for q in cn_rows:
+                    if str(q["Chr"]) == str(r["Chromosome"]) and r["Start_Position.bp."] <= q["Position"] <= r["End_Position.bp."]:
+                        q["Corrected_Copy_Number"] = rl
+        for idx in touched:
+            r = seg_rows[idx]
+            if _isna(r["Corrected_Ratio"]) or _isna(r["Corrected_Copy_Number"]):
+                r["Corrected_MajorCN"] = r["Corrected_MinorCN"] = float("nan")
+            else:
+                r["Corrected_MajorCN"] = _rint(r["Corrected_Ratio"] * r["Corrected_Copy_Number"])
+                r["Corrected_MinorCN"] = _rint((1 - r["Corrected_Ratio"]) * r["Corrected_Copy_Number"])
+    for rows, ckey, nkey in ((seg_rows, "Chromosome", "Copy_Number"), (cn_rows, "Chr", "CopyNumber")):
+        for r in rows:
+            cc = r["Corrected_Copy_Number"]
+            r["Corrected_Call"] = None if _isna(cc) else names[int(cc)]
+            if gender == "male" and xs:
+                if str(r[ckey]) in xs and not _isna(cc):
+                    r["Corrected_Call"] = names_x[int(cc)]
+            elif max_x is not None and str(r[ckey]) in xs and not _isna(r[nkey]) and r[nkey] >= max_x:
+                r["Corrected_Call"] = "HLAMP"
+    return cn_rows, seg_rows

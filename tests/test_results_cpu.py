@@ -131,3 +131,42 @@ def test_recompute_loglik_without_transition_fields_is_an_error_not_undefined_be
     path = np.full(500, 1, dtype=np.int32)
     with pytest.raises(ValueError, match="txn_exp_len"):
         R.outputTitanResults(data, cp, path)            # reference defaults: correctResults=TRUE, recomputeLogLik=TRUE
+
+
+@pytest.mark.parametrize("gender,purity,max_auto", [("male", 0.7, None), ("female", 0.7, None), ("male", 0.1, None),
+                                                     ("female", 0.45, 6), ("male", 0.9, 5)])
+def test_correct_integer_cn_matches_loop_restatement(gender, purity, max_auto):
+    """R/utils.R:1175-1340 (scripts/R_scripts/titanCNA.R:278-281): copy numbers re-derived from the corrected log
+    ratio for high-level amplifications, homozygous deletions, chrX of males and calls that contradict the ratio."""
+    rng = np.random.default_rng(11)
+    N, Z, U = 3000, 2, 25
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=17, mean_seg=40)
+    data = dict(data)
+    data["chr"] = np.where(np.asarray(data["chr"]) == 23, "X", np.asarray(data["chr"]).astype(str))
+    data["logR"] = data["logR"] + rng.normal(0, 0.5, size=N)            # push some calls against their log ratio
+    path = np.repeat(rng.integers(1, U * Z + 1, size=N // 6 + 1), 6)[:N].astype(np.int32)
+    cp = _cluster_cp(Z, U, [0.05, 0.4], N=N)
+    tab = R.outputTitanResults(data, cp, path, correctResults=False)["results"]
+    segs = R.outputTitanSegments(tab, "s", cp)
+    rows = RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, cp, path)
+    seg_rows = RO.output_segments(rows, "s")
+    got = R.correctIntegerCN(tab, segs, purity, 2.3, maxCNtoCorrect_autosomes=max_auto, gender=gender)
+    w_cn, w_segs = RO.correct_integer_cn(rows, seg_rows, purity, 2.3, max_auto=max_auto, gender=gender)
+    for table, want, keys in ((got["cn"], w_cn, ("logR_Copy_Number", "Corrected_logR", "Corrected_Ratio", "Corrected_Copy_Number")),
+                              (got["segs"], w_segs, ("logR_Copy_Number", "Corrected_logR", "Corrected_Ratio", "Corrected_Copy_Number",
+                                                     "Corrected_MajorCN", "Corrected_MinorCN"))):
+        for k in keys:
+            a, b = np.asarray(table[k], float), np.array([r[k] for r in want], float)
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (k, gender)
+            assert np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-12, atol=1e-12), (k, gender)
+        assert list(table["Corrected_Call"]) == [r["Corrected_Call"] for r in want]
+    changed = np.count_nonzero(got["segs"]["Corrected_Copy_Number"] != np.asarray(segs["Copy_Number"], float))
+    assert (changed > 0) == (purity >= 0.2)
+    assert "Corrected_Copy_Number" not in tab and "Corrected_Copy_Number" not in segs          # inputs untouched
+    if gender == "male" and purity >= 0.2:
+        x = np.asarray(got["cn"]["Chr"]).astype(str) == "X"
+        assert x.any() and np.all(np.isnan(got["cn"]["Corrected_Ratio"][x]))
+        assert set(got["cn"]["Corrected_Call"][x]) <= {"HETD", "NEUT", "GAIN", "AMP", "HLAMP"}
+    # the S_Dbw index prefers the corrected copy number when the table has it (R/utils.R:631-637)
+    from titancna_b200 import selection as S
+    assert S.computeSDbwIndex(got["cn"], data_type="LogRatio")["S_DbwIndex"] > 0

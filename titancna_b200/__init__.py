@@ -8,7 +8,7 @@ from .params import loadDefaultParameters, setupClonalParameters, estimateDirich
 from .hmm import (Solver, runEMclonalCN, viterbiClonalCN, fwd_back_clonalCN, viterbi_clonalCN,  # noqa: F401
                   chromosome_offsets)
 from .sweep import runEMclonalCN_sharded, run_sweep, lpt_assign, shard_chromosomes, solution_grid  # noqa: F401
-from .results import outputTitanResults, outputTitanSegments, removeEmptyClusters, decoupleMegaVar, decodeLOH, getMajorMinorCN  # noqa: F401
+from .results import outputTitanResults, outputTitanSegments, removeEmptyClusters, correctIntegerCN, decoupleMegaVar, decodeLOH, getMajorMinorCN  # noqa: F401
 from .selection import computeSDbwIndex, outputModelParameters, selectSolution  # noqa: F401
 from .staging import loadAlleleCounts, filterData, removeCentromere, getPositionOverlap, setGenomeStyle  # noqa: F401
 from ._lib import TitanError, device_count, lib, LIB_PATH  # noqa: F401

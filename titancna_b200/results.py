@@ -8,6 +8,8 @@ the cluster relabelling `sortS$ix[Zclust]` (:891-894) and the crossed MinorCN/Ma
 (:1107-1108 with the inverted field names of getMajorMinorCN :1342-1401).
 correctResults=TRUE (removeEmptyClusters, R/utils.R:1420-1524) is covered, including the hidden re-entry into the
 E-step (recomputeLogLik=TRUE -> runEMclonalCN(maxiter=1, fixed normal, no s / ploidy update)).
+correctIntegerCN (:1175-1340), the step between the segments and the parameter file in the production driver
+(scripts/R_scripts/titanCNA.R:278-281), is covered as well.
 Not covered: subclone profiles, posterior-probability columns, file output.
 """
 from __future__ import annotations
@@ -236,3 +238,112 @@ def outputTitanSegments(results, id, convergeParams=None):
             "MinorCN": _MAJOR_FIELD[st], "MajorCN": _MINOR_FIELD[st],      # crossed on purpose (:1107-1108)
             "Clonal_Cluster": np.asarray(results["ClonalCluster"])[start],
             "Cellular_Prevalence": np.asarray(results["CellularPrevalence"])[start]}
+
+
+_CN_NAMES = ["HOMD", "HETD", "NEUT", "GAIN", "AMP", "HLAMP"]
+_CN_NAMES_X = ["HETD", "NEUT", "GAIN", "AMP", "HLAMP"]
+
+
+def logRbasedCN(x, purity, ploidyT, cellPrev=None, cn=2):
+    """R/utils.R:1314-1327: total copies implied by a log2 ratio at the given purity / ploidy / cellular prevalence."""
+    x = np.asarray(x, float)
+    cp = np.ones_like(x) if cellPrev is None else np.where(np.isnan(np.asarray(cellPrev, float)), 1.0, np.asarray(cellPrev, float))
+    ct = (np.power(2.0, x) * (cn * (1 - purity) + purity * ploidyT * (cn / 2)) - cn * (1 - purity) - cn * purity * (1 - cp))
+    ct = ct / (purity * cp)
+    return np.where(np.isnan(ct), np.nan, np.maximum(ct, 1 / 2 ** 6))
+
+
+def allelicRatioBasedCN(x, ct, purity, cellPrev=None, rn=0.5, cn=2):
+    """R/utils.R:1329-1340: tumour allelic fraction implied by an observed ratio."""
+    x, ct = np.asarray(x, float), np.asarray(ct, float)
+    cp = np.ones_like(x) if cellPrev is None else np.where(np.isnan(np.asarray(cellPrev, float)), 1.0, np.asarray(cellPrev, float))
+    total = (1 - purity) * cn + purity * (1 - cp) * cn + purity * cp * ct
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rt = (x * total - ((1 - purity) * rn * cn + purity * (1 - cp) * rn * cn)) / (purity * cp * ct)
+    return np.where(np.isnan(rt), np.nan, np.clip(rt, 0.0, 1.0))
+
+
+def correctIntegerCN(cn, segs, purity, ploidy, maxCNtoCorrect_autosomes=None, maxCNtoCorrect_X=None, correctHOMD=True,
+                     minPurityToCorrect=0.2, gender="male", chrs=None):
+    """R/utils.R:1175-1312: copy numbers re-derived from the purity / ploidy corrected log ratio where the HMM's
+    state space cannot represent them (>= the largest modelled copy number, homozygous deletions, chrX of males,
+    calls that contradict the log ratio).  Returns dict(cn = per-SNP table, segs = segment table) with the
+    Corrected_* columns added; the inputs are not modified.  (scripts/R_scripts/titanCNA.R:278-281.)"""
+    chrs = [str(c) for c in (list(range(1, 23)) + ["X"] if chrs is None else chrs)]
+    cn = {k: np.array(v, copy=True) for k, v in cn.items()}
+    segs = {k: np.array(v, copy=True) for k, v in segs.items()}
+    seg_ratio = "Median_HaplotypeRatio" if "Median_HaplotypeRatio" in segs else "Median_Ratio"
+    cn_ratio = "HaplotypeRatio" if "HaplotypeRatio" in cn else "AllelicRatio"
+    autosomes = [c for c in chrs if "X" not in c and "Y" not in c]
+    chr_x = [c for c in chrs if "X" in c]
+    s_chr, c_chr = np.asarray(segs["Chromosome"]).astype(str), np.asarray(cn["Chr"]).astype(str)
+    s_in, c_in = np.isin(s_chr, chrs), np.isin(c_chr, chrs)
+    s_x, c_x = np.isin(s_chr, chr_x), np.isin(c_chr, chr_x)
+    s_cn = np.asarray(segs["Copy_Number"], float)
+    c_cn = np.asarray(cn["CopyNumber"], float)
+    if maxCNtoCorrect_autosomes is None:
+        maxCNtoCorrect_autosomes = np.nanmax(s_cn[np.isin(s_chr, autosomes)])
+    if maxCNtoCorrect_X is None and gender == "female" and chr_x:
+        maxCNtoCorrect_X = np.nanmax(s_cn[s_x])
+
+    def corrected(lr, ratio, prev, inside, on_x):
+        lr_cn = np.where(inside, logRbasedCN(lr, purity, ploidy, prev, cn=2), np.nan)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            c_lr = np.log2(lr_cn / ploidy)
+        c_ratio = np.where(inside, allelicRatioBasedCN(ratio, lr_cn, purity, prev, rn=0.5, cn=2), np.nan)
+        if gender == "male" and chr_x:
+            lr_cn = np.where(on_x, logRbasedCN(lr, purity, ploidy, prev, cn=1), lr_cn)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                c_lr = np.where(on_x, np.log2(lr_cn / (ploidy / 2)), c_lr)
+            c_ratio = np.where(on_x, np.nan, c_ratio)
+        return lr_cn, c_lr, c_ratio
+
+    segs["logR_Copy_Number"], segs["Corrected_logR"], segs["Corrected_Ratio"] = corrected(
+        segs["Median_logR"], segs[seg_ratio], segs["Cellular_Prevalence"], s_in, s_x)
+    cn["logR_Copy_Number"], cn["Corrected_logR"], cn["Corrected_Ratio"] = corrected(
+        cn["LogRatio"], cn[cn_ratio], cn["CellularPrevalence"], c_in, c_x)
+    s_corr, c_corr = s_cn.copy(), c_cn.copy()
+    s_major, s_minor = np.asarray(segs["MajorCN"], float).copy(), np.asarray(segs["MinorCN"], float).copy()
+    with np.errstate(invalid="ignore"):
+        s_round, c_round = np.round(segs["logR_Copy_Number"]), np.round(cn["logR_Copy_Number"])
+        if purity >= minPurityToCorrect:
+            touched = s_in & (s_cn >= maxCNtoCorrect_autosomes)
+            c_touch = c_in & (c_cn >= maxCNtoCorrect_autosomes)
+            if correctHOMD:
+                touched |= s_in & (s_cn == 0)
+                c_touch |= c_in & (c_cn == 0)
+            c_touch |= c_in & np.isnan(c_cn)
+            if gender == "male" and chr_x:
+                touched |= s_x
+                c_touch |= c_x
+            s_corr[touched] = s_round[touched]
+            c_corr[c_touch] = c_round[c_touch]
+            opp = (((s_round < ploidy) & (s_corr > ploidy)) | ((s_round > ploidy) & (s_corr < ploidy))) & (np.abs(s_round - s_corr) > 2)
+            s_corr[opp] = s_round[opp]
+            c_pos = np.asarray(cn["Position"], float)
+            for j in np.flatnonzero(opp):                       # bins inside a re-called segment follow it (last hit wins)
+                inside = (c_chr == s_chr[j]) & (c_pos >= segs["Start_Position.bp."][j]) & (c_pos <= segs["End_Position.bp."][j])
+                c_corr[inside] = s_corr[j]
+            touched |= opp
+            s_major[touched] = np.round(segs["Corrected_Ratio"][touched] * s_corr[touched])
+            s_minor[touched] = np.round((1 - segs["Corrected_Ratio"][touched]) * s_corr[touched])
+
+    def calls(corr, on_x, titan_cn):
+        names = np.array(_CN_NAMES + ["HLAMP"] * 1000, dtype=object)
+        names_x = np.array(_CN_NAMES_X + ["HLAMP"] * 1000, dtype=object)
+        out = np.full(corr.size, None, dtype=object)
+        ok = ~np.isnan(corr)
+        out[ok] = names[corr[ok].astype(np.int64)]
+        if gender == "male" and chr_x:
+            sel = on_x & ok
+            out[sel] = names_x[corr[sel].astype(np.int64)]
+        elif maxCNtoCorrect_X is not None:
+            with np.errstate(invalid="ignore"):
+                out[on_x & (titan_cn >= maxCNtoCorrect_X)] = "HLAMP"
+        return out
+
+    segs["Corrected_Copy_Number"], segs["Corrected_MajorCN"], segs["Corrected_MinorCN"] = s_corr, s_major, s_minor
+    segs["Corrected_Call"] = calls(s_corr, s_x, s_cn)
+    cn["Corrected_Copy_Number"] = c_corr
+    cn["Corrected_Call"] = calls(c_corr, c_x, c_cn)
+    return {"cn": cn, "segs": segs}

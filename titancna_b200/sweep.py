@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import c_double_p, check, lib
 from .hmm import Solver, _check_params, _hyper, chromosome_offsets, runEMclonalCN, viterbiClonalCN
 from .params import loadDefaultParameters
-from .results import outputTitanResults, outputTitanSegments
+from .results import correctIntegerCN, outputTitanResults, outputTitanSegments
 from .selection import outputModelParameters, selectSolution
 
 
@@ -195,8 +195,13 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
             # the S_Dbw validity index that selectSolution.R ranks the cluster counts by
             res = outputTitanResults(d, cp, path, proportionThreshold=0.05, proportionThresholdClonal=0.05,
                                      recomputeLogLik=False, verbose=False)
-            segs = outputTitanSegments(res["corrResults"], "sweep", res["convergeParams"])
-            mp = outputModelParameters(res["convergeParams"], res["corrResults"])
+            cpc = res["convergeParams"]
+            segs = outputTitanSegments(res["corrResults"], "sweep", cpc)
+            chrs = list(dict.fromkeys(np.asarray(d["chr"]).astype(str).tolist()))
+            corr = correctIntegerCN(res["corrResults"], segs, 1 - float(cpc["n"][-1]), float(cpc["phi"][-1]),
+                                    maxCNtoCorrect_autosomes=maxCN, minPurityToCorrect=0.2, gender="male", chrs=chrs)
+            segs = corr["segs"]
+            mp = outputModelParameters(cpc, corr["cn"])
             out = {"n": cp["n"][-1], "phi": cp["phi"][-1], "s": cp["s"][:, -1], "loglik": cp["loglik"][-1],
                    "iters": cp["n"].size - 1, "sdbw": mp["S_Dbw"], "dens_bw": mp["dens_bw"], "scat": mp["scat"],
                    "segs": {"TITAN_call": segs["TITAN_call"], "Length.snp.": segs["Length.snp."]}}
