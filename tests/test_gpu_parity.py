@@ -442,3 +442,31 @@ def test_sweep_with_selection_on_one_gpu():
     from oracle import selection_oracle as SO
     want = SO.select_solution(out)
     assert (best["ploidy_0"], best["numClusters"]) == (want["ploidy_0"], want["numClusters"])
+
+
+def test_full_size_viterbi_properties(monkeypatch):
+    """BASELINE configs[1] size (1 M SNPs, 23 chromosomes, K = 75), where the O(N K^2) oracle cannot go: the three
+    forward kernels and the tiled back-trace are the same function, and the decode of the genome is the
+    concatenation of the decodes of its chromosomes (the HMM restarts at every chromosome, R/hmmClonal.R:470-483)."""
+    N, Z = 1_000_000, 3
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=20261020)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=Z, data=data)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    args = (0.45, sP["s_0"], 2.04, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    paths = {}
+    for mode in ("3", "2", "0"):
+        monkeypatch.setenv("TITAN_VIT_MODE", mode)
+        sol = T.Solver(data, g, Z, 1e15, 1.0)
+        paths[mode] = sol.viterbi(*args)
+        sol.close()
+    assert np.array_equal(paths["3"], paths["0"]) and np.array_equal(paths["2"], paths["0"])
+    full = paths["3"]
+    assert full.min() >= 1 and full.max() <= 25 * Z and 1 + np.count_nonzero(np.diff(full)) > 23
+    monkeypatch.setenv("TITAN_VIT_MODE", "-1")
+    for c in (1, 16, 23):                                       # longest, a mid-sized and the last chromosome
+        idx = np.flatnonzero(data["chr"] == c)
+        sub = {k: v[idx] for k, v in data.items()}
+        sol = T.Solver(sub, g, Z, 1e15, 1.0)
+        alone = sol.viterbi(*args)
+        sol.close()
+        assert np.array_equal(alone, full[idx]), c
