@@ -470,3 +470,36 @@ def test_full_size_viterbi_properties(monkeypatch):
         alone = sol.viterbi(*args)
         sol.close()
         assert np.array_equal(alone, full[idx]), c
+
+
+def test_readme_flow_from_allele_count_file(tmp_path):
+    """The whole per-sample flow of scripts/R_scripts/titanCNA.R:204-285 through the mirrored API: allele-count file
+    -> staging -> EM -> Viterbi -> result table -> segments -> corrected copy numbers -> parameter file."""
+    src, _ = synth.make_data(8000, Z=2, maxCN=8, n_chr=5, seed=44, mean_seg=300)
+    rng = np.random.default_rng(0)
+    order = rng.permutation(8000)                                  # the file need not be sorted
+    flip = rng.random(8000) < 0.5                                  # loadAlleleCounts symmetrises the counts itself
+    refc = np.where(flip, src["tumDepth"] - src["ref"], src["ref"]).astype(int)
+    f = tmp_path / "ac.txt"
+    with open(f, "w") as fh:
+        fh.write("chr\tposition\tref\trefCount\tNref\tNrefCount\n")
+        for t in order:
+            fh.write(f"chr{src['chr'][t]}\t{int(src['posn'][t])}\tA\t{refc[t]}\tC\t{int(src['tumDepth'][t]) - refc[t]}\n")
+    counts = T.loadAlleleCounts(str(f))
+    assert np.array_equal(counts["ref"], src["ref"]) and np.array_equal(counts["tumDepth"], src["tumDepth"])
+    bins = {"chr": counts["chr"], "start": counts["posn"], "end": counts["posn"], "log2": src["logR"] / np.log(2)}
+    counts["logR"] = T.staging.logRfromLog2(T.getPositionOverlap(counts["chr"], counts["posn"], bins))
+    assert np.allclose(counts["logR"], src["logR"], rtol=1e-12, atol=1e-15)
+    data = T.filterData(counts, chrs=[str(c) for c in range(1, 23)], minDepth=10, maxDepth=1000)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=2, data=data)
+    cp = T.runEMclonalCN(data, p, maxiter=3, txnExpLen=1e15, txnZstrength=1.0, verbose=False)
+    path = T.viterbiClonalCN(data, cp)
+    out = T.outputTitanResults(data, cp, path, recomputeLogLik=False, verbose=False)
+    segs = T.outputTitanSegments(out["corrResults"], "sample", out["convergeParams"])
+    cpc = out["convergeParams"]
+    corr = T.correctIntegerCN(out["corrResults"], segs, 1 - cpc["n"][-1], cpc["phi"][-1], chrs=[str(c) for c in range(1, 6)])
+    fit = T.outputModelParameters(cpc, corr["cn"], str(tmp_path / "sample_cluster2.params.txt"))
+    text = (tmp_path / "sample_cluster2.params.txt").read_text().splitlines()
+    assert text[0].startswith("Normal contamination estimate:\t") and text[-1].startswith("S_Dbw validity index (Both):\t")
+    assert np.isfinite(fit["S_Dbw"]) and int(np.sum(segs["Length.snp."])) == data["posn"].size
+    assert "Corrected_Copy_Number" in corr["segs"] and len(corr["cn"]["Corrected_Call"]) == data["posn"].size
