@@ -284,3 +284,29 @@ def correct_integer_cn(cn_rows, seg_rows, purity, ploidy, max_auto=None, max_x=N
             elif max_x is not None and str(r[ckey]) in xs and not _isna(r[nkey]) and r[nkey] >= max_x:
                 r["Corrected_Call"] = "HLAMP"
     return cn_rows, seg_rows
+
+
+def subclone_profiles(rows):
+    """R/utils.R:1526-1577 on row dicts -> list of dicts with the Subclone1.* / Subclone2.* fields."""
+    clust = [0 if _isna(r["ClonalCluster"]) else r["ClonalCluster"] for r in rows]
+    ncl = int(max(clust)) if clust else 0
+    pairs = []
+    for r in rows:
+        key = (r["ClonalCluster"], r["CellularPrevalence"])
+        if not any((a == key[0] or (_isna(a) and _isna(key[0]))) and (b == key[1] or (_isna(b) and _isna(key[1]))) for a, b in pairs):
+            pairs.append(key)
+    prev = {cl: [p for c, p in pairs if c == cl] for cl in (1, 2)}
+    out = []
+    for r in rows:
+        o = {}
+        if ncl == 0:
+            o = {"Subclone1.CopyNumber": r["CopyNumber"], "Subclone1.TITANcall": r["TITANcall"], "Subclone1.Prevalence": "NA"}
+        elif ncl == 1:
+            o = {"Subclone1.CopyNumber": r["CopyNumber"], "Subclone1.TITANcall": r["TITANcall"], "Subclone1.Prevalence": prev[1][0]}
+        elif ncl == 2:
+            two = r["ClonalCluster"] == 2
+            o = {"Subclone2.CopyNumber": r["CopyNumber"], "Subclone2.TITANcall": r["TITANcall"], "Subclone2.Prevalence": prev[2][0],
+                 "Subclone1.CopyNumber": 2 if two else r["CopyNumber"], "Subclone1.TITANcall": "HET" if two else r["TITANcall"],
+                 "Subclone1.Prevalence": prev[1][0] - prev[2][0]}
+        out.append(o)
+    return out

@@ -170,3 +170,25 @@ def test_correct_integer_cn_matches_loop_restatement(gender, purity, max_auto):
     # the S_Dbw index prefers the corrected copy number when the table has it (R/utils.R:631-637)
     from titancna_b200 import selection as S
     assert S.computeSDbwIndex(got["cn"], data_type="LogRatio")["S_DbwIndex"] > 0
+
+
+@pytest.mark.parametrize("Z,s_last", [(1, [0.2]), (2, [0.1, 0.45])])
+def test_subclone_profiles_match_loop_restatement(Z, s_last):
+    """R/utils.R:1526-1577 through outputTitanResults(subcloneProfiles=TRUE), the production setting."""
+    rng = np.random.default_rng(Z)
+    N, U = 1500, 25
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=3, seed=9, mean_seg=40)
+    path = np.repeat(rng.integers(1, U * Z + 1, size=N // 5 + 1), 5)[:N].astype(np.int32)
+    cp = _cluster_cp(Z, U, s_last, N=N)
+    tab = R.outputTitanResults(data, cp, path, correctResults=False)["results"]
+    rows = RO.output_results({k: np.asarray(v).tolist() for k, v in data.items()}, cp, path)
+    want = RO.subclone_profiles(rows)
+    for k in want[0]:
+        if k.endswith("TITANcall"):
+            assert list(tab[k]) == [w[k] for w in want], k
+        else:
+            a, b = np.asarray(tab[k], float), np.array([w[k] for w in want], float)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=0, atol=1e-15), k
+    assert ("Subclone2.Prevalence" in tab) == (Z == 2)
+    three = R.outputTitanResults(data, _cluster_cp(3, U, [0.1, 0.2, 0.3], N=N), np.minimum(path, 75), correctResults=False)["results"]
+    assert "Subclone1.CopyNumber" not in three                       # more than two clusters: no profiles (:943-948)

@@ -10,7 +10,8 @@ correctResults=TRUE (removeEmptyClusters, R/utils.R:1420-1524) is covered, inclu
 E-step (recomputeLogLik=TRUE -> runEMclonalCN(maxiter=1, fixed normal, no s / ploidy update)).
 correctIntegerCN (:1175-1340), the step between the segments and the parameter file in the production driver
 (scripts/R_scripts/titanCNA.R:278-281), is covered as well.
-Not covered: subclone profiles, posterior-probability columns, file output.
+Subclone profiles (:1526-1577) for one or two clusters are covered.
+Not covered: posterior-probability columns, file output.
 """
 from __future__ import annotations
 
@@ -54,13 +55,13 @@ def getMajorMinorCN(state, symmetric=True):
 
 
 def outputTitanResults(data, convergeParams, optimalPath, filename=None, is_haplotypeData=False, posteriorProbs=False,
-                       subcloneProfiles=False, correctResults=True, proportionThreshold=0.05,
+                       subcloneProfiles=True, correctResults=True, proportionThreshold=0.05,
                        proportionThresholdClonal=0.05, recomputeLogLik=True, rerunViterbi=False, verbose=True):
     """R/utils.R:865-976.  Returns dict(results = per-SNP table, corrResults = the table after removeEmptyClusters
     (None with correctResults=False), convergeParams = the -- possibly corrected -- parameter list), as the
     reference's list(results, corrResults, convergeParams).  Tables are dicts of equal-length numpy columns."""
-    if filename is not None or posteriorProbs or subcloneProfiles or is_haplotypeData:
-        raise NotImplementedError("file output, posterior columns, subclone profiles and haplotype columns are not covered")
+    if filename is not None or posteriorProbs or is_haplotypeData:
+        raise NotImplementedError("file output, posterior columns and haplotype columns are not covered")
     cp = convergeParams
     if cp.get("useOutlierState") is None:
         raise ValueError("convergeParams does not contain element: useOutlierState.")
@@ -92,7 +93,49 @@ def outputTitanResults(data, convergeParams, optimalPath, filename=None, is_hapl
                                    proportionThresholdClonal=proportionThresholdClonal,
                                    recomputeLogLik=recomputeLogLik, verbose=verbose)
         corrmat, cp = corr["results"], corr["convergeParams"]
+    if subcloneProfiles and s_all.shape[0] <= 2:           # numClust is taken BEFORE the correction (:875,:944)
+        target = corrmat if correctResults else outmat     # the columns land on the table that is written out
+        target.update(getSubcloneProfiles(target))
     return {"results": outmat, "corrResults": corrmat, "convergeParams": cp}
+
+
+def getSubcloneProfiles(titanResults):
+    """R/utils.R:1526-1577: per-subclone copy number / call / prevalence columns for one or two clonal clusters
+    (Subclone1.*, Subclone2.*).  With two clusters, positions of cluster 2 are diploid HET in subclone 1 and the
+    prevalence of subclone 1 is the difference of the two cluster prevalences."""
+    cc = np.asarray(titanResults["ClonalCluster"], float)
+    prev = np.asarray(titanResults["CellularPrevalence"], float)
+    cn = np.asarray(titanResults["CopyNumber"], float)
+    calls = np.asarray(titanResults["TITANcall"], dtype=object)
+    with np.errstate(invalid="ignore"):
+        ncl = int(np.nanmax(np.where(np.isnan(cc), 0, cc))) if cc.size else 0
+
+    def prevalence_of(cl):                                  # unique(cbind(Cluster, Prevalence)) rows of that cluster
+        v = np.unique(prev[cc == cl])
+        return v
+
+    n = cc.size
+    out = {}
+    if ncl == 0:
+        out["Subclone1.CopyNumber"], out["Subclone1.TITANcall"] = cn.copy(), calls.copy()
+        out["Subclone1.Prevalence"] = np.full(n, "NA", dtype=object)
+    elif ncl == 1:
+        p1 = prevalence_of(1)
+        out["Subclone1.CopyNumber"], out["Subclone1.TITANcall"] = cn.copy(), calls.copy()
+        out["Subclone1.Prevalence"] = np.resize(p1, n).astype(float) if p1.size else np.full(n, np.nan)
+    elif ncl == 2:
+        p2, p1 = prevalence_of(2), prevalence_of(1)
+        d = p1 - p2 if p1.size == p2.size else np.resize(p1, max(p1.size, p2.size)) - np.resize(p2, max(p1.size, p2.size))
+        out["Subclone2.CopyNumber"], out["Subclone2.TITANcall"] = cn.copy(), calls.copy()
+        out["Subclone2.Prevalence"] = np.resize(p2, n).astype(float)
+        c1, t1 = cn.copy(), calls.copy()
+        c1[cc == 2] = 2
+        t1[cc == 2] = "HET"
+        out["Subclone1.CopyNumber"], out["Subclone1.TITANcall"] = c1, t1
+        out["Subclone1.Prevalence"] = np.resize(d, n).astype(float)
+    else:
+        raise ValueError("getSubcloneProfiles: more than 2 clonal clusters (outputTitanResults only calls it for <= 2)")
+    return out
 
 
 def removeEmptyClusters(data, convergeParams, results, proportionThreshold=0.001, proportionThresholdClonal=0.05,
