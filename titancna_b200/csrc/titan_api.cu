@@ -985,18 +985,22 @@ static void launch_vit_fast(const VitArgs &A, int nChr, int K, int P, int PER, c
   }
 }
 
-template <int Z>
-static void launch_vit_cluster_z(const VitArgs &A, int nChr, cudaStream_t st) {
-  constexpr int H = 2, W = Z * H;
+template <int Z, int H, int UP>
+static void launch_vit_cluster_t(const VitArgs &A, int nChr, cudaStream_t st) {
+  constexpr int W = Z * H;
   const size_t smem = sizeof(double) * W * 33 * 4 + 16 * (size_t)(2 * 2 * W * 32) + sizeof(double) * (size_t)(A.K + 2) +
                       VitRing::bytes(A.K);
-  if (A.U <= 26) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_cluster_kernel<Z, H, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    viterbi_cluster_kernel<Z, H, 13><<<nChr, 32 * W, smem, st>>>(A);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_cluster_kernel<Z, H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    viterbi_cluster_kernel<Z, H, 16><<<nChr, 32 * W, smem, st>>>(A);
-  }
+  if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_cluster_kernel<Z, H, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  viterbi_cluster_kernel<Z, H, UP><<<nChr, 32 * W, smem, st>>>(A);
+}
+
+template <int Z>
+static void launch_vit_cluster_z(const VitArgs &A, int nChr, cudaStream_t st) {
+  // slices per cluster: measured on B200 at 1 M SNPs -- four warps pay off only for a single cluster (23.5 vs 26.6 ms);
+  // with Z >= 2 the longer gather and the wider barrier cost more than the shorter slice scan saves
+  if (Z == 1 && A.U <= 28) { launch_vit_cluster_t<Z, (Z == 1 ? 4 : 2), (Z == 1 ? 7 : 13)>(A, nChr, st); return; }
+  if (A.U <= 26) launch_vit_cluster_t<Z, 2, 13>(A, nChr, st);
+  else launch_vit_cluster_t<Z, 2, 16>(A, nChr, st);
 }
 
 static bool vit_cluster_ok(const VitArgs &A) { return !A.cls && A.U <= 32 && A.Z >= 1 && A.Z <= 8 && A.py != nullptr; }

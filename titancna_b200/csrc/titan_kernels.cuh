@@ -1683,7 +1683,8 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
   const bool on = g < U;
   const int j = on ? g + zs * U : 0;        // the state this lane owns: source (g, zs) of its table, destination (g, zs)
   const bool het = on && A.het[g];
-  const bool writer = on && h == 0;
+  const bool writer = on && h == 0;            // stores back-pointers and the last delta
+  const bool feeder = on && h == H - 1;        // keeps the input ring filled (the other warp of the cluster when H > 1)
   double *tab = tab_all + warp * TABD;
   const int per = (U + H - 1) / H;
   const int g0 = h * per;
@@ -1713,7 +1714,7 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
   const int last = ce - 1;
   const double *pyj = A.py + j;
   const double *ltj = A.ltab + (size_t)j * 4;
-  if (writer) ring.prologue(A, cs, last, j);      // the H warps of a cluster share the ring entries of their states
+  if (feeder) ring.prologue(A, cs, last, j);      // the H warps of a cluster share the ring entries of their states
   // ---- t = cs ----
   {
     double d0 = -CUDART_INF;
@@ -1776,6 +1777,8 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
       if (writer) {
         A.psi[(size_t)tt * K + j] = (unsigned char)arg;
         if (tt == last) dfin[j] = d;
+      }
+      if (feeder) {
         ring.issue(A, (slot + DV) & (RV - 1), tt + DV, last, j, ring.id[slot * K + j]);
         cp_async_wait<DV - 1>();      // the group of step tt+1 has landed; the next barrier publishes it
       }
