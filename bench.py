@@ -217,11 +217,12 @@ def main():
     T.lib().titan_set_device(local)
 
     Z, K = a.clusters, 25 * a.clusters
-    # every rank = one independent solution of the sweep on the same data (ploidy_0 varies by rank)
+    # every rank = one independent solution on its own copy of the data: the workload `config` names, on every
+    # rank (weak scaling: per-GPU work fixed as N grows)
     data, _ = synth.make_data(a.snps, Z=Z, maxCN=8, n_chr=23, seed=SEED)
     N = data["posn"].size
     p = production_params(T.loadDefaultParameters, data, Z)
-    p["ploidyParams"]["phi_0"] = 2.0 + (rank % 3)
+    p["ploidyParams"]["phi_0"] = 2.0
     g, sP = p["genotypeParams"], p["cellPrevParams"]
 
     t0 = time.perf_counter()
