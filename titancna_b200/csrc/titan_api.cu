@@ -1003,8 +1003,6 @@ static void launch_vit_cluster_z(const VitArgs &A, int nChr, cudaStream_t st) {
   else launch_vit_cluster_t<Z, 2, 16>(A, nChr, st);
 }
 
-static bool vit_cluster_ok(const VitArgs &A) { return !A.cls && A.U <= 32 && A.Z >= 1 && A.Z <= 8 && A.py != nullptr; }
-
 static void launch_vit_cluster(const VitArgs &A, int nChr, cudaStream_t st) {
   switch (A.Z) {
     case 1: launch_vit_cluster_z<1>(A, nChr, st); break;

@@ -966,7 +966,6 @@ __global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
     int j = 0;
     for (int k = 0; k < ntiles; ++k) {
       const double *slot = ws_smem + (size_t)(k % NS) * SD;
-      const double *ms = slot + TS * Z * 32;
       const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
       double *bslot = bring + (size_t)(k % NSB) * BD;
       spin_until_eq(&F->full[k % NS], k + 1);
