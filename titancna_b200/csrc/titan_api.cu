@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <thread>
@@ -1405,6 +1406,21 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
   const int maxit = o->maxiter + 1;   // :92
   const bool nmap = o->normal_map != 0, estS = o->estimateS != 0, estP = o->estimatePloidy != 0;
   double *n = out->n, *phi = out->phi, *loglik = out->loglik;
+  // The N-sized posterior outputs are written once, after the last iteration.  Freshly allocated host arrays
+  // (R's allocMatrix, numpy's zeros) have no pages behind them yet, and faulting 8(U+Z)N bytes in during the
+  // final device-to-host copy costs more than the copy: touch them on a worker thread while the EM runs.
+  struct Prefault {
+    std::thread t;
+    ~Prefault() { if (t.joinable()) t.join(); }
+  } prefault;
+  if (o->want_posteriors && (out->rhoG || out->rhoZ)) {
+    double *pg = out->rhoG, *pz = out->rhoZ;
+    const size_t ng = (size_t)s->N * U, nz = (size_t)s->N * Z;
+    prefault.t = std::thread([pg, pz, ng, nz]() {
+      if (pg) std::memset(pg, 0, ng * sizeof(double));
+      if (pz) std::memset(pz, 0, nz * sizeof(double));
+    });
+  }
   auto col = [](double *base, int rows, int i) { return base + (size_t)rows * i; };
   int i = 0;
   loglik[0] = -std::numeric_limits<double>::infinity();
@@ -1467,6 +1483,7 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
     // rhoG / rhoZ of the last executed E-step (R/hmmClonal.R:356-357): the per-iteration passes do not
     // write the N-sized marginals; its forward variables and verified boundaries are still resident,
     // so only the final backward pass is repeated with the output switched on.
+    if (prefault.t.joinable()) prefault.t.join();
     if (o->want_posteriors && have_last && (out->rhoG || out->rhoZ)) {
       titan_estep_out eo{};
       eo.rhoG = out->rhoG;
