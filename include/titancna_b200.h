@@ -193,13 +193,16 @@ int titan_mstep(const titan_hyper *h, int U, int Z, int nChr, int maxiterUpdate,
 /* Introspection for benchmarks and tests */
 typedef struct titan_timing {
   double last_estep_ms;       /* CUDA-event time of the last titan_estep (all its kernels)           */
-  double last_fwd_ms, last_bwd_ms, last_reduce_ms;   /* all rounds of each direction */
+  double last_fwd_ms, last_bwd_ms, last_reduce_ms;   /* engine 2: emission + all rounds / final pass / reductions */
   double last_fwd_r0_ms, last_bwd_r0_ms;             /* the round-0 launch alone (every chunk runs) */
   double last_viterbi_ms;
   int32_t last_fwd_rounds, last_bwd_rounds;   /* verification rounds the chunked scan needed          */
   int64_t last_fwd_chunk_runs, last_bwd_chunk_runs;
   int64_t kernel_launches;    /* cumulative launches of this library's kernels                       */
   int32_t n_chunks;
+  int32_t engine;             /* 2: emission pass + combined rounds + final pass (default); 1: round-1 kernels */
+  double last_emission_ms;    /* engine 2: the emission pass; last_fwd_r0_ms = round 0 (both directions),     */
+  double last_rounds_ms;      /*           verification rounds >= 1, last_bwd_r0_ms = the final posterior pass */
 } titan_timing;
 int titan_solver_timing(const titan_solver *s, titan_timing *t);
 

@@ -75,7 +75,8 @@ class Timing(C.Structure):
                 ("last_viterbi_ms", C.c_double),
                 ("last_fwd_rounds", C.c_int32), ("last_bwd_rounds", C.c_int32),
                 ("last_fwd_chunk_runs", C.c_int64), ("last_bwd_chunk_runs", C.c_int64),
-                ("kernel_launches", C.c_int64), ("n_chunks", C.c_int32)]
+                ("kernel_launches", C.c_int64), ("n_chunks", C.c_int32), ("engine", C.c_int32),
+                ("last_emission_ms", C.c_double), ("last_rounds_ms", C.c_double)]
 
 
 EXPORTS = [

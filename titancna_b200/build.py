@@ -41,10 +41,28 @@ def _stale(target, sources):
 
 
 def build(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("titan_api.cu", "titan_kernels.cuh", "titan_host.hpp")]
-    srcs.append(os.path.join(ROOT, "include", "titancna_b200.h"))
-    if force or _stale(LIB, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0]]
+    """Every .cu is its own translation unit (compiled in parallel, nvcc cross-compiles without a GPU), linked into one
+    shared object."""
+    units = ["titan_api.cu", "titan_fb2.cu"]
+    headers = [os.path.join(CSRC, f) for f in ("titan_kernels.cuh", "titan_common.cuh", "titan_fb2.h", "titan_host.hpp")]
+    headers.append(os.path.join(ROOT, "include", "titancna_b200.h"))
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs, objs = [], []
+    for u in units:
+        src, obj = os.path.join(CSRC, u), os.path.join(objdir, u.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd))
+            jobs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, j in jobs:
+        if j.wait() != 0:
+            raise subprocess.CalledProcessError(j.returncode, cmd)
+    if force or jobs or _stale(LIB, objs):
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

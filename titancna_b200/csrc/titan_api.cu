@@ -17,6 +17,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "titan_fb2.h"
 #include "titan_host.hpp"
 #include "titan_kernels.cuh"
 
@@ -149,7 +150,10 @@ struct titan_solver {
   std::vector<int> pair_id;             // [N] which pair sits between SNP t-1 and t
 
   // configuration
-  int chunk_len = 1024, warm = 192, max_rounds = 64;
+  int chunk_len = 1024, warm = 192, max_rounds = 0;   // max_rounds 0: bounded by the chunk count (titan_solver_configure)
+  int engine = 2;                  // 2: titan_fb2 (materialised emissions, posterior-weighted boundary test); 1: round-1 kernels (TITAN_ENGINE)
+  int Kp = 0;                      // row stride of the per-SNP K-vectors in HBM: K states + the emission shift, padded to 16 bytes
+  double tol = 1e-8;               // posterior-weighted boundary tolerance of the fb2 engine
   int vit_mode = -1;               // 3: cluster-sliced scan, 2: register-sliced dense scan, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
   int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
   double rtol = 1e-8, atol = 1e-290;   // 100x inside the 1e-6 posterior tolerance; errors do not amplify
@@ -162,6 +166,12 @@ struct titan_solver {
   std::vector<Chunk> chunks_h;
   int nChunks = 0, maxChunksPerChr = 1;
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
+  DevBuf<double> Bm, extf, extb;   // fb2 engine: scaled emissions [N][Kp]; one-step-extended boundary vectors [2][nChunks][K]
+  // per-SNP arrays carry kFbPadRows rows of slack on both sides (TMA copies whole tiles)
+  SnpRec *snp_p() const { return snp.p + kFbPadRows; }
+  TxnRec *txn_p() const { return txn.p + kFbPadRows; }
+  double *alpha_p() const { return alpha.p + (size_t)kFbPadRows * Kp; }
+  double *Bm_p() const { return Bm.p + (size_t)kFbPadRows * Kp; }
   DevBuf<int> chr_chunk0;          // [nChr+1]
   int overlap = 1;                 // run the forward and the backward boundary rounds concurrently on two streams
   int round_batch = 4;             // verification rounds queued per host synchronisation
@@ -229,6 +239,12 @@ static void build_chunks(titan_solver *s) {
   s->startb.alloc(nc * K);
   s->endf.alloc(2 * nc * K);
   s->endb.alloc(2 * nc * K);
+  s->extf.alloc(2 * nc * K);
+  s->extb.alloc(2 * nc * K);
+  // a chunk without a neighbour never writes its extended vector; the neighbour-less tests never read it either,
+  // but keep the buffers defined
+  CK(cudaMemset(s->extf.p, 0, sizeof(double) * 2 * nc * K));
+  CK(cudaMemset(s->extb.p, 0, sizeof(double) * 2 * nc * K));
   s->chunk_ll.alloc(nc);
   s->part.alloc(nc * 6 * K);
   s->slice = 64;
@@ -275,8 +291,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (in.N > 2000000000LL) return fail(TITAN_ERR_UNSUPPORTED, "N=%lld exceeds the 32-bit SNP index range", (long long)in.N);
   if (in.Z < 1 || in.Z > kMaxZ)
     return fail(TITAN_ERR_UNSUPPORTED, "numClusters=%d outside the supported range 1..%d", in.Z, kMaxZ);
-  if (in.U < 1 || in.U > 32)
-    return fail(TITAN_ERR_UNSUPPORTED, "%d genotype states: the warp-per-chunk kernels cover up to 32", in.U);
+  if (in.U < 1 || in.U > 64)
+    return fail(TITAN_ERR_UNSUPPORTED, "%d genotype states: the warp-per-chunk kernels cover up to 64 (two per lane)", in.U);
   if (!in.ZS || in.nZS < in.U) return fail(TITAN_ERR_ARG, "zygosityKey must have %d entries", in.U);
   if (!(in.txnExpLen > 0) || !(in.zStrength > 0))
     return fail(TITAN_ERR_ARG, "txnExpLen / zStrength must be positive scalars (length-0 arguments are rejected, "
@@ -290,6 +306,13 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
       if (in.ZS[a] == in.ZS[b] && in.ZS[a] != -1)
         return fail(TITAN_ERR_UNSUPPORTED, "zygosityKey entries %d and %d are equal (%g): the structured transition "
                                            "needs distinct zygosity classes", a, b, in.ZS[a]);
+  {
+    int nhet = 0;
+    for (int a = 0; a < in.U; ++a) nhet += (in.ZS[a] == -1);
+    if (nhet > 1)
+      return fail(TITAN_ERR_UNSUPPORTED, "%d zygosityKey entries equal -1: the reference puts them in one zygosity class "
+                                         "(src/fwd_backC_clonalCN.c:262), the structured transition covers a single diploid-HET state", nhet);
+  }
   int ndev = 0;
   int rc = titan_device_count(&ndev);
   if (rc != TITAN_OK) return rc;
@@ -300,6 +323,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
   if (const char *e = getenv("TITAN_OVERLAP")) s->overlap = atoi(e);
   if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
+  if (const char *e = getenv("TITAN_ENGINE")) s->engine = atoi(e) == 1 ? 1 : 2;
+  if (in.U > 32) s->engine = 2;
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -309,6 +334,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     for (auto &e : s->ev_sync) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     trace.mark("streams + events");
     s->N = in.N; s->nChr = in.nChr; s->U = in.U; s->Z = in.Z; s->K = in.U * in.Z;
+    s->Kp = (s->K + 2) & ~1;           // K states + the shift m_t, rows a multiple of 16 bytes
     s->chr_start.assign(in.chr_start, in.chr_start + in.nChr + 1);
     s->het.resize(in.U);
     s->h = 0;
@@ -420,9 +446,10 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
       CK(cudaMemcpy(dG.p, s->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(dZ.p, s->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       trace.mark("  rho memcpy");
-      s->txn.alloc(N);
+      s->txn.alloc(N + 2 * kFbPadRows);
+      CK(cudaMemsetAsync(s->txn.p, 0, sizeof(TxnRec) * (N + 2 * kFbPadRows), s->stream));
       trace.mark("  txn alloc");
-      txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h, s->txn.p);
+      txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h, s->txn_p());
       CK(cudaGetLastError());
       trace.mark("  txn launch");
       CK(cudaStreamSynchronize(s->stream));
@@ -433,18 +460,28 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     if (s->legacy_py) {
       s->py.alloc((size_t)N * K);
       CK(cudaMemcpy(s->py.p, in.py, sizeof(double) * N * K, cudaMemcpyHostToDevice));
-      s->snp.alloc(1);
+      s->snp.alloc(1 + 2 * kFbPadRows);
     } else {
       if (!in.ref || !in.depth || !in.logR) return fail(TITAN_ERR_ARG, "ref, tumDepth and logR columns are required");
       rec_builder.join();
       if (bad_snp >= 0)
         return fail(TITAN_ERR_ARG, "NA/NaN in the data columns at SNP %lld (filterData removes these, R/utils.R:273-310)",
                     (long long)bad_snp);
-      s->snp.alloc(N);
-      CK(cudaMemcpy(s->snp.p, rec.data(), sizeof(SnpRec) * N, cudaMemcpyHostToDevice));
+      s->snp.alloc(N + 2 * kFbPadRows);
+      CK(cudaMemset(s->snp.p, 0, sizeof(SnpRec) * (N + 2 * kFbPadRows)));
+      CK(cudaMemcpy(s->snp_p(), rec.data(), sizeof(SnpRec) * N, cudaMemcpyHostToDevice));
     }
     trace.mark("SnpRec (host lgamma) + upload");
-    s->alpha.alloc((size_t)N * K);
+    s->alpha.alloc((size_t)(N + 2 * kFbPadRows) * s->Kp);
+    if (s->engine == 2) {
+      s->Bm.alloc((size_t)(N + 2 * kFbPadRows) * s->Kp);
+      // only the slack rows need defined contents (they are copied with the tiles, never used)
+      const size_t padn = (size_t)kFbPadRows * s->Kp;
+      CK(cudaMemset(s->alpha.p, 0, sizeof(double) * padn));
+      CK(cudaMemset(s->alpha.p + padn + (size_t)N * s->Kp, 0, sizeof(double) * padn));
+      CK(cudaMemset(s->Bm.p, 0, sizeof(double) * padn));
+      CK(cudaMemset(s->Bm.p + padn + (size_t)N * s->Kp, 0, sizeof(double) * padn));
+    }
     trace.mark("alpha alloc");
     s->het_d.alloc(s->U);
     CK(cudaMemcpy(s->het_d.p, s->het.data(), s->U, cudaMemcpyHostToDevice));
@@ -486,8 +523,8 @@ extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup
   try {
     s->chunk_len = chunk_len;
     s->warm = std::max(1, warmup_len);
-    if (rel_tol > 0) s->rtol = rel_tol;
-    if (max_rounds > 0) s->max_rounds = max_rounds;
+    if (rel_tol > 0) { s->rtol = rel_tol; s->tol = rel_tol; }
+    s->max_rounds = std::max(0, max_rounds);
     if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
     CK(cudaSetDevice(s->device));
     build_chunks(s);
@@ -716,6 +753,92 @@ struct Direction {
   }
 };
 
+// fb2 engine: emission pass, round 0, verification rounds (both directions in one launch per round, batches of
+// rounds per host synchronisation), final posterior pass.  Events: ev[0] start, ev[6] after the emission pass,
+// ev[7] after round 0, ev[1] after the last round, ev[9] after the final pass.
+static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool posterior_only, int *rounds_out, int64_t *runs_out) {
+  const int U = s->U, K = s->K;
+  Fb2Args A{};
+  A.Bm = s->Bm_p();
+  A.txn = s->txn_p();
+  A.snp = s->snp_p();
+  A.chunks = s->chunks.p;
+  A.nChunks = s->nChunks;
+  A.U = U; A.K = K; A.Kp = s->Kp;
+  A.warm = s->warm;
+  A.tol = s->tol;
+  A.het = s->het_d.p;
+  A.pi = model_layout(s, s->model.p).pi;
+  A.alpha = s->alpha_p();
+  A.startF = s->startf.p; A.endF = s->endf.p; A.extF = s->extf.p;
+  A.startB = s->startb.p; A.endB = s->endb.p; A.extB = s->extb.p;
+  A.chunk_ll = s->chunk_ll.p;
+  A.rerun = s->rerun.p;
+  A.part = s->part.p;
+  A.rhoG0 = s->rhoG0.p; A.rhoZ0 = s->rhoZ0.p;
+  A.rhoG = (post && !s->legacy_py) ? s->rhoG.p : nullptr;
+  A.rhoZ = (post && !s->legacy_py) ? s->rhoZ.p : nullptr;
+  A.loggamma = (s->legacy_py && want_loggamma) ? s->loggamma.p : nullptr;
+  cudaStream_t st = s->stream;
+  int rounds = 1;
+  int64_t runs = 0;
+  if (!posterior_only) {
+    EmArgs E{};
+    E.snp = s->snp_p();
+    E.py = s->legacy_py ? s->py.p : nullptr;
+    E.M = model_layout(s, s->model.p);
+    E.U = U; E.K = K; E.Kp = s->Kp; E.N = s->N;
+    E.Bm = s->Bm_p();
+    CK(fb2_launch_emission(E, s->Z, st));
+    CK(cudaEventRecord(s->ev[6], st));
+    const int hard_cap = std::min(kRoundSlots - 8, s->max_rounds > 0 ? s->max_rounds : 2 * s->maxChunksPerChr + 4);
+    CK(cudaMemsetAsync(s->rerun.p, 0, sizeof(unsigned int) * (size_t)(hard_cap + 8), st));
+    A.round = 0;
+    CK(fb2_launch_round(A, s->Z, st));
+    CK(cudaEventRecord(s->ev[7], st));
+    s->tm.kernel_launches += 2;
+    runs = 2 * (int64_t)s->nChunks;
+    bool done = s->maxChunksPerChr <= 1;            // plain sequential recursion: nothing to verify
+    int round = 0;
+    unsigned int *ctr_h = s->rerun_h.p;
+    while (!done) {
+      const int queued = std::max(1, std::min(s->round_batch, hard_cap - round));
+      for (int q = 1; q <= queued; ++q) {
+        A.round = round + q;
+        CK(fb2_launch_round(A, s->Z, st));
+        s->tm.kernel_launches++;
+      }
+      CK(cudaMemcpyAsync(ctr_h + round + 1, s->rerun.p + round + 1, sizeof(unsigned int) * (size_t)queued, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (int q = 1; q <= queued; ++q) {
+        ++round;
+        if (ctr_h[round] == 0) { done = true; break; }
+        runs += ctr_h[round];
+      }
+      if (!done && round >= hard_cap)
+        return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
+    }
+    rounds = round + 1;
+    if (getenv("TITAN_TRACE") && atoi(getenv("TITAN_TRACE")) > 1) {
+      fprintf(stderr, "[titan trace] chunk runs per round (both directions, %d chunks):", s->nChunks);
+      for (int r = 1; r <= round; ++r) fprintf(stderr, " %u", ctr_h[r]);
+      fprintf(stderr, "\n");
+    }
+  } else {
+    CK(cudaEventRecord(s->ev[6], st));
+    CK(cudaEventRecord(s->ev[7], st));
+  }
+  CK(cudaEventRecord(s->ev[1], st));
+  CK(cudaEventRecord(s->ev[8], st));
+  CK(fb2_launch_final(A, s->Z, post && !s->legacy_py, s->legacy_py, st));
+  CK(cudaEventRecord(s->ev[9], st));
+  s->tm.kernel_launches++;
+  runs += s->nChunks;
+  *rounds_out = rounds;
+  *runs_out = runs;
+  return TITAN_OK;
+}
+
 // posterior_only: the parameters are those of the previous call, whose forward variables and verified
 // backward boundaries are still resident -- only the final backward pass is run again, now writing
 // the N-sized marginals (what runEMclonalCN returns as rhoG / rhoZ of its last E-step).
@@ -739,8 +862,8 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   if (s->legacy_py && loggamma_out && s->loggamma.n < (size_t)N * K) s->loggamma.alloc((size_t)N * K);
 
   FbArgs A{};
-  A.snp = s->snp.p;
-  A.txn = s->txn.p;
+  A.snp = s->snp_p();
+  A.txn = s->txn_p();
   A.chunks = s->chunks.p;
   A.nChunks = s->nChunks;
   A.U = U;
@@ -768,7 +891,12 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   A.final_pass = 0;
   Direction F{s, A, false, false, s->stream}, B{s, A, true, post, overlap ? s->stream_b : s->stream};
   CK(cudaEventRecord(s->ev[0], s->stream));
-  if (posterior_only) {
+  int fb2_rounds = 0;
+  int64_t fb2_runs = 0;
+  if (s->engine == 2) {
+    rc = estep_fb2(s, post, loggamma_out != nullptr, posterior_only, &fb2_rounds, &fb2_runs);
+    if (rc != TITAN_OK) return rc;
+  } else if (posterior_only) {
     B.st = s->stream;
     B.A.rerun = s->rerun.p + kRoundSlots;
     B.A.startv = s->startb.p;
@@ -829,8 +957,8 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
     }
   }
   CK(cudaEventRecord(s->ev[2], s->stream));
-  const int fr = F.round + 1, br = B.round + 1;
-  const int64_t fruns = F.runs, bruns = B.runs;
+  const int fr = s->engine == 2 ? fb2_rounds : F.round + 1, br = s->engine == 2 ? fb2_rounds : B.round + 1;
+  const int64_t fruns = s->engine == 2 ? fb2_runs : F.runs, bruns = s->engine == 2 ? 0 : B.runs;
   const int width = 6 * K;
   {
     dim3 g1((width + 127) / 128, s->nSlices);
@@ -854,6 +982,13 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[3])); s->tm.last_estep_ms = ms;
   CK(cudaEventElapsedTime(&ms, s->ev[6], s->ev[7])); s->tm.last_fwd_r0_ms = ms;
   CK(cudaEventElapsedTime(&ms, s->ev[8], s->ev[9])); s->tm.last_bwd_r0_ms = ms;
+  s->tm.engine = s->engine;
+  s->tm.last_emission_ms = 0;
+  s->tm.last_rounds_ms = 0;
+  if (s->engine == 2) {
+    CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[6])); s->tm.last_emission_ms = ms;
+    CK(cudaEventElapsedTime(&ms, s->ev[7], s->ev[1])); s->tm.last_rounds_ms = ms;
+  }
   s->tm.last_fwd_rounds = fr; s->tm.last_bwd_rounds = br;
   s->tm.last_fwd_chunk_runs = fruns; s->tm.last_bwd_chunk_runs = bruns;
   if (o) {
@@ -1037,7 +1172,7 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   rc = upload_model(s, p, nullptr, nullptr);
   if (rc != TITAN_OK) return rc;
   VitArgs A{};
-  A.snp = s->snp.p;
+  A.snp = s->snp_p();
   A.chr_start = s->chr_start32.p;
   A.txn_id = s->txn_id.p;
   A.ltab = s->ltab.p;
@@ -1067,7 +1202,7 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
     if (!s->legacy_py) {   // exact log emissions, materialised in the (idle) alpha buffer
       const long long total = (long long)s->N * K;
       const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-      viterbi_emission_kernel<<<blocks, 256, 0, s->stream>>>(s->snp.p, A.M, s->U, K, total, s->alpha.p);
+      viterbi_emission_kernel<<<blocks, 256, 0, s->stream>>>(s->snp_p(), A.M, s->U, K, total, s->alpha.p);
       CK(cudaGetLastError());
       s->tm.kernel_launches += 1;
       s->state_valid = false;
@@ -1110,11 +1245,14 @@ static bool needs_generic(int K, int numClust, const double *zs, int nZS, int us
   if (useOutlier || numClust <= 0 || K % numClust != 0) return true;
   if (const char *e = getenv("TITAN_FORCE_DENSE")) if (atoi(e)) return true;   // cross-check of the structured kernels
   const int U = K / numClust;
-  if (U > 32 || numClust > kMaxZ || nZS < U) return true;
-  for (int a = 0; a < U; ++a)
+  if (U > 64 || numClust > kMaxZ || nZS < U) return true;
+  int nhet = 0;
+  for (int a = 0; a < U; ++a) {
+    nhet += (zs[a] == -1);
     for (int b = a + 1; b < U; ++b)
       if (zs[a] == zs[b] && zs[a] != -1) return true;
-  return false;
+  }
+  return nhet > 1;     // several -1 keys form ONE zygosity class in the reference: dense class-matrix path
 }
 
 struct GenericSetup {
@@ -1249,7 +1387,7 @@ static int legacy_create(const char *who, const double *log_pi, int K, const dou
   int64_t cs[2] = {0, T};
   SolverInit in{T, 1, cs, positions, nullptr, nullptr, nullptr, py, txnLen, zStrength, U, numClust, zs, nZS};
   int rc = solver_create_impl(in, out);
-  if (rc == TITAN_OK) (*out)->rtol = 1e-10;   // compatibility path: tightest setting, it is not the fast path
+  if (rc == TITAN_OK) { (*out)->rtol = 1e-10; (*out)->tol = 1e-10; }   // compatibility path: tightest setting, it is not the fast path
   return rc;
 }
 

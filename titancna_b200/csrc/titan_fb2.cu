@@ -1,0 +1,751 @@
+// titan_fb2.cu -- forward-backward engine of the E-step on sm_100a (fp64 throughout).  See titan_fb2.h.
+//
+// State layout: joint state j = u + z*U (genotype fastest; R/hmmClonal.R:196, src/fwd_backC_clonalCN.c:234-235).
+// One warp owns one position chunk: lane l holds the Z cluster values of genotypes l and (U > 32) l + 32, so the
+// per-genotype sums are thread-local and the per-cluster sums are Z interleaved warp butterflies.
+//
+// Structured transition (src/fwd_backC_clonalCN.c:215-301), regrouped so that every coefficient is non-negative:
+//   destination non-HET:  o[g,z] = k0*W + k1*Wz[z] + k2*Wg[g] + k3*w[g,z]
+//   destination HET    :  o[g,z] = cB*W + k4*Wg[g]                          w = alpha / rowsum(source)
+//
+// Boundary acceptance.  A chunk that started from the vector s although its neighbour actually produced e
+// (both normalised) changes the log-likelihood by sum_j gamma_j (s_j/e_j - 1) to first order and every
+// downstream posterior by at most twice sum_j gamma_j |s_j/e_j - 1|, where gamma is the POSTERIOR at the
+// boundary.  The forward test therefore weighs the mismatch with beta~ at the boundary (published by the
+// backward chunk of the previous round) and vice versa:  sum_j w_j |s_j - e_j| <= tol * sum_j w_j e_j.
+// Components the data on the other side rule out no longer force re-runs (a component-wise relative test keeps
+// every such component's error alive for as long as the diagonal of the transition matrix carries it).
+#include "titan_fb2.h"
+
+namespace titan {
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kNS = 3;   // ring slots per warp
+constexpr int kWPC = 4;  // warps (= chunks) per CTA: a warp's SM sub-partition is its index in the CTA modulo 4, so
+                         // one-warp CTAs would crowd a single scheduler
+
+// Per-warp ring of per-SNP row tiles.  A tile is TS consecutive SNP rows of up to four arrays; lane 0 issues the
+// copies, every lane waits on the slot's mbarrier before reading.  FINAL adds the alpha rows and the records.
+struct Ring {
+  char *base;
+  unsigned long long *bar;
+  int TS, Kp;
+  unsigned rowB, slot_bytes, offT, offA, offS, tx_bytes;
+  bool fin;
+
+  __device__ __forceinline__ void init(char *smem, int TS_, int Kp_, bool fin_, int lane) {
+    TS = TS_; Kp = Kp_; fin = fin_;
+    rowB = (unsigned)Kp * 8u;
+    offT = (unsigned)TS * rowB;
+    offA = offT + (unsigned)TS * 64u;
+    offS = offA + (fin ? (unsigned)TS * rowB : 0u);
+    slot_bytes = offS + (fin ? (unsigned)TS * 32u : 0u);
+    tx_bytes = slot_bytes;
+    base = smem;
+    bar = reinterpret_cast<unsigned long long *>(smem + (size_t)kNS * slot_bytes);
+    if (lane == 0) {
+      for (int s = 0; s < kNS; ++s) mbar_init(bar + s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fence_async_smem();
+    }
+    __syncwarp();
+  }
+  // rowBT: first SNP row of the B / transition tile;  rowAS: first SNP row of the alpha / record tile
+  __device__ __forceinline__ void issue(int k, const Fb2Args &A, long long rowBT, long long rowAS) {
+    const int s = k % kNS;
+    char *slot = base + (size_t)s * slot_bytes;
+    fence_async_smem();          // the slot was read through the generic proxy until the __syncwarp before this call
+    mbar_expect_tx(bar + s, tx_bytes);
+    bulk_g2s(slot, A.Bm + rowBT * Kp, (unsigned)TS * rowB, bar + s);
+    bulk_g2s(slot + offT, A.txn + rowBT, (unsigned)TS * 64u, bar + s);
+    if (fin) {
+      bulk_g2s(slot + offA, A.alpha + rowAS * Kp, (unsigned)TS * rowB, bar + s);
+      bulk_g2s(slot + offS, A.snp + rowAS, (unsigned)TS * 32u, bar + s);
+    }
+  }
+  __device__ __forceinline__ void wait(int k) { mbar_wait(bar + (k % kNS), (unsigned)((k / kNS) & 1)); }
+  __device__ __forceinline__ const char *slot(int k) const { return base + (size_t)(k % kNS) * slot_bytes; }
+};
+
+// ------------------------------------------------------------------------------------------
+// lane geometry and the structured steps
+// ------------------------------------------------------------------------------------------
+template <int GS>
+struct LaneInfo {
+  int g[GS];
+  bool act[GS], het[GS];
+  int het_lane, het_slot;     // where the diploid-HET genotype lives (-1: the table has none)
+};
+
+template <int GS>
+__device__ __forceinline__ void lane_info(LaneInfo<GS> &L, int U, int lane, const unsigned char *het) {
+  L.het_lane = -1;
+  L.het_slot = 0;
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    L.g[s] = lane + 32 * s;
+    L.act[s] = L.g[s] < U;
+    L.het[s] = L.act[s] && het[L.g[s]];
+  }
+  for (int u = 0; u < U; ++u)
+    if (het[u]) { L.het_lane = u & 31; L.het_slot = u >> 5; }
+}
+
+// forward: a <- (A_t^T applied to a) .* (B * 2^-e);  HET destinations differ only in their coefficients
+template <int Z, int GS>
+__device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[GS][Z], const TxnRec &tr, const LaneInfo<GS> &L,
+                                          int &e) {
+  double w[GS][Z], Wz[Z], Wg[GS];
+#pragma unroll
+  for (int z = 0; z < Z; ++z) Wz[z] = 0.0;
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    const double irs = L.het[s] ? tr.irh : tr.irn;
+    Wg[s] = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) { w[s][z] = a[s][z] * irs; Wz[z] += w[s][z]; Wg[s] += w[s][z]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)      // Z interleaved butterflies: Z independent shuffles per stage
+#pragma unroll
+    for (int z = 0; z < Z; ++z) Wz[z] += __shfl_xor_sync(0xffffffffu, Wz[z], o);
+  double W = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) W += Wz[z];
+  const double sc = pow2_rescale(W, e);
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    const bool h = L.het[s];
+    const double cW = h ? tr.cB : tr.k0, cG = h ? tr.k4 : tr.k2, cZ = h ? 0.0 : tr.k1, cw = h ? 0.0 : tr.k3;
+    const double base = cW * W + cG * Wg[s];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) a[s][z] = (base + cZ * Wz[z] + cw * w[s][z]) * (B[s][z] * sc);
+  }
+}
+
+// backward: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two.  The table holds at most one
+// diploid-HET genotype, so the HET mass is a broadcast from its lane instead of a butterfly.
+template <int Z, int GS>
+__device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[GS][Z], const TxnRec &tr, const LaneInfo<GS> &L,
+                                          int &e) {
+  double bb[GS][Z], loc[GS], red[Z];
+#pragma unroll
+  for (int z = 0; z < Z; ++z) red[z] = 0.0;
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    loc[s] = 0.0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      bb[s][z] = b[s][z] * B[s][z];
+      loc[s] += bb[s][z];
+      red[z] += L.het[s] ? 0.0 : bb[s][z];
+    }
+  }
+  double H = 0.0;
+  if (L.het_lane >= 0) {
+    double hl = loc[0];
+#pragma unroll
+    for (int s = 1; s < GS; ++s) hl = (L.het_slot == s) ? loc[s] : hl;
+    H = __shfl_sync(0xffffffffu, hl, L.het_lane);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) red[z] += __shfl_xor_sync(0xffffffffu, red[z], o);
+  double Wn = 0.0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) Wn += red[z];
+  const double sc = pow2_rescale(Wn + H, e);
+  const double common = tr.k0 * Wn + tr.cB * H;
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    const bool h = L.het[s];
+    const double cG = h ? tr.k4 : tr.k2, cw = h ? 0.0 : tr.k3;
+    const double irs = L.act[s] ? (h ? tr.irh : tr.irn) * sc : 0.0;
+    const double base = common + cG * loc[s];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) b[s][z] = (base + tr.k1 * red[z] + cw * bb[s][z]) * irs;
+  }
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void load_row(double (&v)[GS][Z], const double *row, const LaneInfo<GS> &L, int U) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? row[L.g[s] + z * U] : 0.0;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void store_row(double *row, const double (&v)[GS][Z], const LaneInfo<GS> &L, int U, double scale) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+    if (L.act[s])
+#pragma unroll
+      for (int z = 0; z < Z; ++z) row[L.g[s] + z * U] = v[s][z] * scale;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ double vec_sum(const double (&v)[GS][Z]) {
+  double loc = 0.0;
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) loc += v[s][z];
+  return warp_sum(loc);
+}
+
+// posterior-weighted comparison of the boundary vector a chunk used with the one its neighbour produced;
+// `want` is left in v[][] (the vector a re-run starts from)
+template <int Z, int GS>
+__device__ __forceinline__ bool boundary_ok(double (&v)[GS][Z], const double *used, const double *want, const double *wgt,
+                                            const LaneInfo<GS> &L, int U, double tol) {
+  double num = 0.0, den = 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      const int j = L.g[s] + z * U;
+      const double u = L.act[s] ? used[j] : 0.0, w = L.act[s] ? want[j] : 0.0, p = L.act[s] ? wgt[j] : 0.0;
+      v[s][z] = w;
+      num += p * fabs(u - w);
+      den += p * w;
+      bad |= (u != u) || (w != w);
+    }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  const bool ok = (num <= tol * den) && (den > 0.0);      // false for NaN as well
+  return ok && !__any_sync(0xffffffffu, bad);
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void copy_vec(double *dst, const double *src, const LaneInfo<GS> &L, int U) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+    if (L.act[s])
+#pragma unroll
+      for (int z = 0; z < Z; ++z) dst[L.g[s] + z * U] = src[L.g[s] + z * U];
+}
+
+// ------------------------------------------------------------------------------------------
+// forward chunk (reference recursion: src/fwd_backC_clonalCN.c:111-142, here scaled linear space)
+// ------------------------------------------------------------------------------------------
+template <int Z, int GS>
+__device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, char *smem, int TS) {
+  const Chunk ch = A.chunks[c];
+  const int U = A.U, K = A.K, Kp = A.Kp;
+  LaneInfo<GS> L;
+  lane_info<GS>(L, U, lane, A.het);
+  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  double *startv = A.startF + (size_t)c * K;
+  double a[GS][Z];
+  int tb;
+  bool have_start;
+  if (A.round > 0) {
+    bool skip = (ch.t0 == ch.cs);       // chromosome-leading chunks start from pi: exact in round 0
+    if (!skip)
+      skip = boundary_ok<Z, GS>(a, startv, A.endF + prv + (size_t)(c - 1) * K, A.extB + prv + (size_t)c * K, L, U, A.tol);
+    if (skip) {
+      copy_vec<Z, GS>(A.endF + cur + (size_t)c * K, A.endF + prv + (size_t)c * K, L, U);
+      copy_vec<Z, GS>(A.extF + cur + (size_t)c * K, A.extF + prv + (size_t)c * K, L, U);
+      return;
+    }
+    tb = ch.t0;
+    have_start = true;
+  } else {
+    tb = max(ch.t0 - A.warm, ch.cs);
+    have_start = false;
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) a[s][z] = 0.0;
+  }
+  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
+
+  const int n_own = ch.t1 - tb;                 // stream positions q < n_own are SNPs tb + q of this chunk
+  const bool has_ext = ch.t1 < ch.ce;           // one more step: alpha^ at the first SNP of the next chunk
+  const int n = n_own + (has_ext ? 1 : 0);
+  const int q0 = ch.t0 - tb;
+  const int ntiles = (n + TS - 1) / TS;
+  Ring ring;
+  ring.init(smem, TS, Kp, false, lane);
+  if (lane == 0)
+    for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tb + (long long)k * TS, 0);
+
+  double acc_m = 0.0;        // sum of emission shifts over the owned range
+  long long acc_e = 0;       // sum of power-of-two rescale exponents over the owned range
+  double s_start = 1.0;      // mass of the vector entering the owned range
+  double s_end = 1.0;
+  double *arow = A.alpha + (size_t)tb * Kp;
+  int q = 0;
+  for (int k = 0; k < ntiles; ++k) {
+    ring.wait(k);
+    const char *slot = ring.slot(k);
+    const int ns = min(TS, n - k * TS);
+    for (int s = 0; s < ns; ++s, ++q, arow += Kp) {
+      const double *brow = reinterpret_cast<const double *>(slot) + (size_t)s * Kp;
+      double B[GS][Z];
+      load_row<Z, GS>(B, brow, L, U);
+      const double m = brow[K];
+      int e = 0;
+      if (q == 0 && !have_start) {
+        const bool at_start = (tb == ch.cs);
+#pragma unroll
+        for (int g = 0; g < GS; ++g)
+#pragma unroll
+          for (int z = 0; z < Z; ++z)
+            a[g][z] = (at_start ? (L.act[g] ? A.pi[L.g[g] + z * U] : 0.0) : 1.0) * B[g][z];
+      } else {
+        if (q == q0) {        // entering the owned range: record / publish alpha~_{t0-1}
+          s_start = vec_sum<Z, GS>(a);
+          double inv = 1.0;
+          if (!have_start) { inv = 1.0 / s_start; s_start = 1.0; }
+#pragma unroll
+          for (int g = 0; g < GS; ++g)
+#pragma unroll
+            for (int z = 0; z < Z; ++z) a[g][z] *= inv;
+          store_row<Z, GS>(startv, a, L, U, 1.0);
+        }
+        if (q == n_own) {     // leaving the owned range: boundary vector alpha^_{t1-1}
+          s_end = vec_sum<Z, GS>(a);
+          store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, U, 1.0 / s_end);
+        }
+        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * s);
+        fwd_step2<Z, GS>(a, B, tr, L, e);
+      }
+      if (q >= q0 && q < n_own) {
+        acc_m += m;
+        acc_e += e;
+        store_row<Z, GS>(arow, a, L, U, 1.0);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tb + (long long)(k + kNS) * TS, 0);
+  }
+  const double tot = vec_sum<Z, GS>(a);
+  if (has_ext) {
+    store_row<Z, GS>(A.extF + cur + (size_t)c * K, a, L, U, 1.0 / tot);
+  } else {
+    s_end = tot;
+    store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, U, 1.0 / tot);
+  }
+  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
+  if (lane == 0) A.chunk_ll[c] = ll;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward chunk, boundary rounds: the beta recursion alone (src/fwd_backC_clonalCN.c:148-175)
+// b[] holds beta~_{tn}; tn == ce means "past the end" (beta_{ce-1} = 1).  Stream position j is SNP tn - j:
+// step j turns beta~_{tn-j} into beta~_{tn-j-1} with B and the transition record of SNP tn - j.
+// ------------------------------------------------------------------------------------------
+template <int Z, int GS>
+__device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, char *smem, int TS) {
+  const Chunk ch = A.chunks[c];
+  const int U = A.U, K = A.K, Kp = A.Kp;
+  LaneInfo<GS> L;
+  lane_info<GS>(L, U, lane, A.het);
+  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  double *startv = A.startB + (size_t)c * K;
+  double b[GS][Z];
+  int tn;
+  bool from_boundary;
+  if (A.round > 0) {
+    bool skip = (ch.t1 == ch.ce);
+    if (!skip)
+      skip = boundary_ok<Z, GS>(b, startv, A.endB + prv + (size_t)(c + 1) * K, A.extF + prv + (size_t)c * K, L, U, A.tol);
+    if (skip) {
+      copy_vec<Z, GS>(A.endB + cur + (size_t)c * K, A.endB + prv + (size_t)c * K, L, U);
+      copy_vec<Z, GS>(A.extB + cur + (size_t)c * K, A.extB + prv + (size_t)c * K, L, U);
+      return;
+    }
+    tn = ch.t1;
+    from_boundary = true;
+  } else {
+    tn = min(ch.t1 + A.warm, ch.ce);
+    from_boundary = false;
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
+  }
+  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
+
+  const int n_main = tn - ch.t0;                // steps j < n_main produce beta~ at SNPs tn-1 .. t0
+  const bool has_ext = ch.t0 > ch.cs;           // one more step: beta~ at the last SNP of the previous chunk
+  const int n = n_main + (has_ext ? 1 : 0);
+  const int jb = tn - ch.t1;                    // at step jb b[] is beta~_{t1}
+  const int ntiles = (n + TS - 1) / TS;
+  Ring ring;
+  ring.init(smem, TS, Kp, false, lane);
+  if (lane == 0)
+    for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, 0);
+  int j = 0;
+  for (int k = 0; k < ntiles; ++k) {
+    ring.wait(k);
+    const char *slot = ring.slot(k);
+    const int ns = min(TS, n - k * TS);
+    for (int s = 0; s < ns; ++s, ++j) {
+      const int r = TS - 1 - s;                 // tile rows ascend in SNP index, the stream descends
+      if (j == jb && ch.t1 < ch.ce) {           // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
+        double inv = 1.0;
+        if (!from_boundary) inv = 1.0 / vec_sum<Z, GS>(b);
+#pragma unroll
+        for (int g = 0; g < GS; ++g)
+#pragma unroll
+          for (int z = 0; z < Z; ++z) b[g][z] *= inv;
+        store_row<Z, GS>(startv, b, L, U, 1.0);
+      }
+      if (j == n_main) store_row<Z, GS>(A.endB + cur + (size_t)c * K, b, L, U, 1.0 / vec_sum<Z, GS>(b));
+      if (tn - j < ch.ce) {
+        double B[GS][Z];
+        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
+        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
+        int e;
+        bwd_step2<Z, GS>(b, B, tr, L, e);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, 0);
+  }
+  const double inv = 1.0 / vec_sum<Z, GS>(b);
+  if (has_ext) store_row<Z, GS>(A.extB + cur + (size_t)c * K, b, L, U, inv);
+  else store_row<Z, GS>(A.endB + cur + (size_t)c * K, b, L, U, inv);
+}
+
+// one launch per round: CTAs [0, nChunks) run forward chunks, [nChunks, 2 nChunks) backward chunks
+template <int Z, int GS>
+__global__ void __launch_bounds__(32 * kWPC) fb2_round_kernel(Fb2Args A, int TS, int ring_stride) {
+  extern __shared__ __align__(128) char fb2_smem[];
+  if (A.round > 1 && A.rerun[A.round - 1] == 0) return;      // fixed point already reached (queued round)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int id = blockIdx.x * kWPC + warp;                   // the warps of a CTA are independent of one another
+  char *smem = fb2_smem + (size_t)warp * ring_stride;
+  if (id < A.nChunks) fb2_forward<Z, GS>(A, id, lane, smem, TS);
+  else if (id < 2 * A.nChunks) fb2_backward<Z, GS>(A, id - A.nChunks, lane, smem, TS);
+}
+
+// ------------------------------------------------------------------------------------------
+// final pass: beta from the verified boundary, posteriors, marginals, the six weighted sums
+// reference: src/fwd_backC_clonalCN.c:148-192; R/hmmClonal.R:230-234; R/paramEstimation.R:34-40
+// ------------------------------------------------------------------------------------------
+template <int Z, int GS, bool WRITE_POST, bool FROM_PY>
+__global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS, int ring_stride) {
+  extern __shared__ __align__(128) char fb2_smem_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x * kWPC + warp;
+  if (c >= A.nChunks) return;
+  char *fb2_smem = fb2_smem_all + (size_t)warp * ring_stride;
+  const Chunk ch = A.chunks[c];
+  const int U = A.U, K = A.K, Kp = A.Kp;
+  LaneInfo<GS> L;
+  lane_info<GS>(L, U, lane, A.het);
+  double b[GS][Z];
+  if (ch.t1 < ch.ce) load_row<Z, GS>(b, A.startB + (size_t)c * K, L, U);
+  else {
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
+  }
+  const int tn = ch.t1, n = ch.t1 - ch.t0;
+  const int ntiles = (n + TS - 1) / TS;
+  Ring ring;
+  ring.init(fb2_smem, TS, Kp, true, lane);
+  if (lane == 0)
+    for (int k = 0; k < kNS && k < ntiles; ++k)
+      ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, (long long)tn - (long long)(k + 1) * TS);
+  double st[6][GS][Z];
+#pragma unroll
+  for (int qq = 0; qq < 6; ++qq)
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) st[qq][s][z] = 0.0;
+  int j = 0;
+  for (int k = 0; k < ntiles; ++k) {
+    ring.wait(k);
+    const char *slot = ring.slot(k);
+    const int ns = min(TS, n - k * TS);
+    for (int s = 0; s < ns; ++s, ++j) {
+      const int r = TS - 1 - s;
+      const int t = tn - j - 1;                 // the SNP whose posterior this step forms
+      if (tn - j < ch.ce) {
+        double B[GS][Z];
+        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
+        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
+        int e;
+        bwd_step2<Z, GS>(b, B, tr, L, e);
+      }
+      double p[GS][Z];
+      load_row<Z, GS>(p, reinterpret_cast<const double *>(slot + ring.offA) + (size_t)r * Kp, L, U);
+      double loc = 0.0;
+#pragma unroll
+      for (int g = 0; g < GS; ++g)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) { p[g][z] *= b[g][z]; loc += p[g][z]; }
+      const double inv = 1.0 / warp_sum(loc);
+#pragma unroll
+      for (int g = 0; g < GS; ++g)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) p[g][z] *= inv;
+      if (!FROM_PY) {
+        const SnpRec rec = *reinterpret_cast<const SnpRec *>(slot + ring.offS + 32 * r);
+        const double l2 = rec.lr * rec.lr;
+#pragma unroll
+        for (int g = 0; g < GS; ++g)
+#pragma unroll
+          for (int z = 0; z < Z; ++z) {
+            st[0][g][z] += rec.x * p[g][z];
+            st[1][g][z] += rec.nx * p[g][z];
+            st[2][g][z] += rec.lr * p[g][z];
+            st[3][g][z] += rec.lb * p[g][z];
+            st[4][g][z] += p[g][z];
+            st[5][g][z] += l2 * p[g][z];
+          }
+      } else if (A.loggamma != nullptr) {
+#pragma unroll
+        for (int g = 0; g < GS; ++g)
+          if (L.act[g])
+#pragma unroll
+            for (int z = 0; z < Z; ++z) A.loggamma[(size_t)t * K + L.g[g] + z * U] = log(p[g][z]);
+      }
+      const bool first = (t == ch.cs);
+      if (WRITE_POST || first) {
+        double rz[Z];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          double v = 0.0;
+#pragma unroll
+          for (int g = 0; g < GS; ++g) v += p[g][z];
+          rz[z] = warp_sum(v);
+        }
+        double *dG = nullptr, *dZ = nullptr;
+        if (WRITE_POST && A.rhoG != nullptr) { dG = A.rhoG + (size_t)t * U; dZ = A.rhoZ + (size_t)t * Z; }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 1) {
+            if (!(first && A.rhoG0 != nullptr)) break;
+            dG = A.rhoG0 + (size_t)ch.chr * U;
+            dZ = A.rhoZ0 + (size_t)ch.chr * Z;
+          }
+          if (dG == nullptr) continue;
+#pragma unroll
+          for (int g = 0; g < GS; ++g) {
+            double gs = 0.0;
+#pragma unroll
+            for (int z = 0; z < Z; ++z) gs += p[g][z];
+            if (L.act[g]) dG[L.g[g]] = gs;
+          }
+#pragma unroll
+          for (int z = 0; z < Z; ++z)
+            if (lane == z) dZ[z] = rz[z];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && k + kNS < ntiles)
+      ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, (long long)tn - (long long)(k + kNS + 1) * TS);
+  }
+  if (!FROM_PY) {
+    double *dst = A.part + (size_t)c * 6 * K;
+#pragma unroll
+    for (int qq = 0; qq < 6; ++qq)
+#pragma unroll
+      for (int g = 0; g < GS; ++g)
+        if (L.act[g])
+#pragma unroll
+          for (int z = 0; z < Z; ++z) dst[qq * K + L.g[g] + z * U] = st[qq][g][z];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// emission: B[j,t] = exp(py[j,t] - m_t), m_t = max_j py[j,t] rounded to float (any common shift is exact once
+// it is added back to the log-likelihood).  One pass, one warp per run of SNPs, no dependence between SNPs.
+// reference: R/hmmClonal.R:491-523,617-634 (densities and state loops), :160-171 (combine)
+// ------------------------------------------------------------------------------------------
+constexpr int kEmRun = 32;
+
+template <int Z, int GS, bool FROM_PY>
+__global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long ta = gw * kEmRun;
+  if (ta >= E.N) return;
+  const long long te = min(E.N, ta + (long long)kEmRun);
+  const int U = E.U, K = E.K, Kp = E.Kp;
+  bool act[GS];
+  int g[GS];
+  double lmu[GS][Z], l1mu[GS][Z], muC[GS][Z], cN[GS], i2v[GS];
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
+    g[s] = lane + 32 * s;
+    act[s] = g[s] < U;
+    const int gg = act[s] ? g[s] : 0;
+    if (!FROM_PY) {
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        lmu[s][z] = E.M.lmu[gg + z * U];
+        l1mu[s][z] = E.M.l1mu[gg + z * U];
+        muC[s][z] = E.M.muC[gg + z * U];
+      }
+      cN[s] = E.M.cN[gg];
+      i2v[s] = E.M.i2v[gg];
+    }
+  }
+#pragma unroll 2
+  for (long long t = ta; t < te; ++t) {
+    double v[GS][Z];
+    double mx = -CUDART_INF;
+    if (FROM_PY) {
+      const double *row = E.py + (size_t)t * K;
+#pragma unroll
+      for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          v[s][z] = act[s] ? __ldg(row + g[s] + z * U) : -CUDART_INF;
+          mx = fmax(mx, v[s][z]);
+        }
+    } else {
+      const SnpRec r = E.snp[t];
+#pragma unroll
+      for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          const double d = r.lr - muC[s][z];
+          const double e = (r.lb + (r.x * lmu[s][z] + r.nx * l1mu[s][z])) + (cN[s] - d * d * i2v[s]);
+          v[s][z] = act[s] ? e : -CUDART_INF;
+          mx = fmax(mx, v[s][z]);
+        }
+    }
+    const float mf = warp_maxf(__double2float_rn(mx));
+    const double m = (mf == -CUDART_INF_F) ? 0.0 : (double)mf;     // a float-rounded shift may sit an ulp off the max: harmless
+    double *dst = E.Bm + (size_t)t * Kp;
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+      if (act[s])
+#pragma unroll
+        for (int z = 0; z < Z; ++z) dst[g[s] + z * U] = exp(v[s][z] - m);
+    if (lane == 0) dst[K] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+bool fb2_supported(int U, int Z) { return U >= 1 && U <= 64 && Z >= 1 && Z <= 8; }
+
+static size_t ring_bytes(int TS, int Kp, bool fin) {
+  size_t slot = (size_t)TS * Kp * 8 + (size_t)TS * 64;
+  if (fin) slot += (size_t)TS * Kp * 8 + (size_t)TS * 32;
+  return ((kNS * slot + kNS * 8 + 127) / 128) * 128;
+}
+// Steps per tile: the largest power of two that keeps a warp's ring near 10 KB, so that six 4-warp CTAs fit an SM
+// and every chunk of a 1 M-SNP genome is resident in a single wave.
+static int tile_steps(int Kp, bool fin) {
+  for (int ts = 8; ts > 1; ts >>= 1)
+    if (ring_bytes(ts, Kp, fin) <= 10240) return ts;
+  return 1;
+}
+
+#define FB2_DISPATCH(Zv, GSv, ...)                                      \
+  switch ((GSv) * 16 + (Zv)) {                                            \
+    case 17: { constexpr int ZZ = 1, GG = 1; __VA_ARGS__; } break;               \
+    case 18: { constexpr int ZZ = 2, GG = 1; __VA_ARGS__; } break;               \
+    case 19: { constexpr int ZZ = 3, GG = 1; __VA_ARGS__; } break;               \
+    case 20: { constexpr int ZZ = 4, GG = 1; __VA_ARGS__; } break;               \
+    case 21: { constexpr int ZZ = 5, GG = 1; __VA_ARGS__; } break;               \
+    case 22: { constexpr int ZZ = 6, GG = 1; __VA_ARGS__; } break;               \
+    case 23: { constexpr int ZZ = 7, GG = 1; __VA_ARGS__; } break;               \
+    case 24: { constexpr int ZZ = 8, GG = 1; __VA_ARGS__; } break;               \
+    case 33: { constexpr int ZZ = 1, GG = 2; __VA_ARGS__; } break;               \
+    case 34: { constexpr int ZZ = 2, GG = 2; __VA_ARGS__; } break;               \
+    case 35: { constexpr int ZZ = 3, GG = 2; __VA_ARGS__; } break;               \
+    case 36: { constexpr int ZZ = 4, GG = 2; __VA_ARGS__; } break;               \
+    case 37: { constexpr int ZZ = 5, GG = 2; __VA_ARGS__; } break;               \
+    case 38: { constexpr int ZZ = 6, GG = 2; __VA_ARGS__; } break;               \
+    case 39: { constexpr int ZZ = 7, GG = 2; __VA_ARGS__; } break;               \
+    case 40: { constexpr int ZZ = 8, GG = 2; __VA_ARGS__; } break;               \
+    default: return cudaErrorInvalidValue;                                \
+  }
+
+template <class KernelT>
+static cudaError_t set_smem(KernelT kern, size_t smem) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every launch
+}
+
+cudaError_t fb2_launch_emission(const EmArgs &E, int Z, cudaStream_t st) {
+  const int GS = E.U > 32 ? 2 : 1;
+  const long long warps = (E.N + kEmRun - 1) / kEmRun;
+  const unsigned blocks = (unsigned)((warps + 3) / 4);
+  if (E.py != nullptr) { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, true><<<blocks, 128, 0, st>>>(E))); }
+  else { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, false><<<blocks, 128, 0, st>>>(E))); }
+  return cudaGetLastError();
+}
+
+cudaError_t fb2_launch_round(const Fb2Args &A, int Z, cudaStream_t st) {
+  const int GS = A.U > 32 ? 2 : 1;
+  const int TS = tile_steps(A.Kp, false);
+  const size_t ring = ring_bytes(TS, A.Kp, false), smem = kWPC * ring;
+  const unsigned blocks = (unsigned)((2 * A.nChunks + kWPC - 1) / kWPC);
+  cudaError_t e = cudaSuccess;
+  FB2_DISPATCH(Z, GS, {
+    e = set_smem(fb2_round_kernel<ZZ, GG>, smem);
+    if (e == cudaSuccess) fb2_round_kernel<ZZ, GG><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
+  });
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t fb2_launch_final(const Fb2Args &A, int Z, bool write_post, bool from_py, cudaStream_t st) {
+  const int GS = A.U > 32 ? 2 : 1;
+  const int TS = tile_steps(A.Kp, true);
+  const size_t ring = ring_bytes(TS, A.Kp, true), smem = kWPC * ring;
+  const unsigned blocks = (unsigned)((A.nChunks + kWPC - 1) / kWPC);
+  cudaError_t e = cudaSuccess;
+  if (from_py) {
+    FB2_DISPATCH(Z, GS, {
+      e = set_smem(fb2_final_kernel<ZZ, GG, false, true>, smem);
+      if (e == cudaSuccess) fb2_final_kernel<ZZ, GG, false, true><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
+    });
+  } else if (write_post) {
+    FB2_DISPATCH(Z, GS, {
+      e = set_smem(fb2_final_kernel<ZZ, GG, true, false>, smem);
+      if (e == cudaSuccess) fb2_final_kernel<ZZ, GG, true, false><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
+    });
+  } else {
+    FB2_DISPATCH(Z, GS, {
+      e = set_smem(fb2_final_kernel<ZZ, GG, false, false>, smem);
+      if (e == cudaSuccess) fb2_final_kernel<ZZ, GG, false, false><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
+    });
+  }
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace titan
