@@ -166,6 +166,11 @@ struct titan_solver {
   std::vector<Chunk> chunks_h;
   int nChunks = 0, maxChunksPerChr = 1;
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
+  int probes = 1;                  // fb2 engine: probe-accelerated rounds (TITAN_PROBES)
+  int probe_window = 8;            // from the second cycle on, chunks this close downstream of a dirty one are probed too (TITAN_PROBE_WINDOW)
+  DevBuf<unsigned char> pflags;    // [4][nChunks] dirtyF, dirtyB, solvedF, solvedB
+  DevBuf<int> pints;               // [2][nChunks][2] probed states, [2][nChunks][3] probe exponents
+  DevBuf<double> pvec;             // [2][nChunks][3][K] probe results, [2][nChunks][K] predicted boundary vectors
   DevBuf<double> Bm, extf, extb;   // fb2 engine: scaled emissions [N][Kp]; one-step-extended boundary vectors [2][nChunks][K]
   // per-SNP arrays carry kFbPadRows rows of slack on both sides (TMA copies whole tiles)
   SnpRec *snp_p() const { return snp.p + kFbPadRows; }
@@ -241,6 +246,10 @@ static void build_chunks(titan_solver *s) {
   s->endb.alloc(2 * nc * K);
   s->extf.alloc(2 * nc * K);
   s->extb.alloc(2 * nc * K);
+  s->pflags.alloc(6 * nc);
+  s->pints.alloc(10 * nc);
+  s->pvec.alloc(8 * nc * K);
+  CK(cudaMemset(s->pflags.p, 0, 6 * nc));
   // a chunk without a neighbour never writes its extended vector; the neighbour-less tests never read it either,
   // but keep the buffers defined
   CK(cudaMemset(s->extf.p, 0, sizeof(double) * 2 * nc * K));
@@ -324,6 +333,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (const char *e = getenv("TITAN_OVERLAP")) s->overlap = atoi(e);
   if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
   if (const char *e = getenv("TITAN_ENGINE")) s->engine = atoi(e) == 1 ? 1 : 2;
+  if (const char *e = getenv("TITAN_PROBES")) s->probes = atoi(e);
+  if (const char *e = getenv("TITAN_PROBE_WINDOW")) s->probe_window = std::max(0, atoi(e));
   if (in.U > 32) s->engine = 2;
   try {
     CK(cudaGetDevice(&s->device));
@@ -774,6 +785,17 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
   A.startB = s->startb.p; A.endB = s->endb.p; A.extB = s->extb.p;
   A.chunk_ll = s->chunk_ll.p;
   A.rerun = s->rerun.p;
+  {
+    const size_t nc = s->nChunks;
+    A.dirtyF = s->pflags.p; A.dirtyB = s->pflags.p + nc; A.solvedF = s->pflags.p + 2 * nc; A.solvedB = s->pflags.p + 3 * nc;
+    A.probedF = s->pflags.p + 4 * nc; A.probedB = s->pflags.p + 5 * nc;
+    A.probe_window = 0;
+    A.probeJF = s->pints.p; A.probeJB = s->pints.p + 2 * nc; A.probeEF = s->pints.p + 4 * nc; A.probeEB = s->pints.p + 7 * nc;
+    A.probeF = s->pvec.p; A.probeB = s->pvec.p + 3 * nc * K; A.solF = s->pvec.p + 6 * nc * K; A.solB = s->pvec.p + 7 * nc * K;
+    A.chr_chunk0 = s->chr_chunk0.p;
+    A.nChr = s->nChr;
+    A.use_solved = 0;
+  }
   A.part = s->part.p;
   A.rhoG0 = s->rhoG0.p; A.rhoZ0 = s->rhoZ0.p;
   A.rhoG = (post && !s->legacy_py) ? s->rhoG.p : nullptr;
@@ -801,10 +823,19 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
     bool done = s->maxChunksPerChr <= 1;            // plain sequential recursion: nothing to verify
     int round = 0;
     unsigned int *ctr_h = s->rerun_h.p;
+    const bool probes = s->probes != 0 && K >= 3;
     while (!done) {
-      const int queued = std::max(1, std::min(s->round_batch, hard_cap - round));
+      // probe mode: a cycle is boundary test + probe runs, chain solve, one re-run of the dirty chunks (3 launches)
+      const int queued = std::max(1, std::min(probes ? std::max(1, s->round_batch / 2) : s->round_batch, hard_cap - round));
       for (int q = 1; q <= queued; ++q) {
         A.round = round + q;
+        if (probes) {
+          A.use_solved = 1;
+          A.probe_window = (round + q >= 2) ? s->probe_window : 0;   // cycle 1 tests hundreds of chunks: dirty ones only
+          CK(fb2_launch_probe(A, s->Z, st));
+          CK(fb2_launch_solve(A, s->Z, st));
+          s->tm.kernel_launches += 2;
+        }
         CK(fb2_launch_round(A, s->Z, st));
         s->tm.kernel_launches++;
       }

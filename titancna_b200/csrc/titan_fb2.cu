@@ -271,8 +271,12 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
   bool have_start;
   if (A.round > 0) {
     bool skip = (ch.t0 == ch.cs);       // chromosome-leading chunks start from pi: exact in round 0
-    if (!skip)
+    if (A.use_solved) {                 // probe mode: the probe kernel tested the boundary, the chain solve predicted the start
+      skip = skip || !A.solvedF[c];
+      if (!skip) load_row<Z, GS>(a, A.solF + (size_t)c * K, L, U);
+    } else if (!skip) {
       skip = boundary_ok<Z, GS>(a, startv, A.endF + prv + (size_t)(c - 1) * K, A.extB + prv + (size_t)c * K, L, U, A.tol);
+    }
     if (skip) {
       copy_vec<Z, GS>(A.endF + cur + (size_t)c * K, A.endF + prv + (size_t)c * K, L, U);
       copy_vec<Z, GS>(A.extF + cur + (size_t)c * K, A.extF + prv + (size_t)c * K, L, U);
@@ -288,7 +292,7 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
 #pragma unroll
       for (int z = 0; z < Z; ++z) a[s][z] = 0.0;
   }
-  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
+  if (lane == 0 && !(A.use_solved && A.round > 0)) atomicAdd(A.rerun + A.round, 1u);
 
   const int n_own = ch.t1 - tb;                 // stream positions q < n_own are SNPs tb + q of this chunk
   const bool has_ext = ch.t1 < ch.ce;           // one more step: alpha^ at the first SNP of the next chunk
@@ -379,8 +383,12 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
   bool from_boundary;
   if (A.round > 0) {
     bool skip = (ch.t1 == ch.ce);
-    if (!skip)
+    if (A.use_solved) {
+      skip = skip || !A.solvedB[c];
+      if (!skip) load_row<Z, GS>(b, A.solB + (size_t)c * K, L, U);
+    } else if (!skip) {
       skip = boundary_ok<Z, GS>(b, startv, A.endB + prv + (size_t)(c + 1) * K, A.extF + prv + (size_t)c * K, L, U, A.tol);
+    }
     if (skip) {
       copy_vec<Z, GS>(A.endB + cur + (size_t)c * K, A.endB + prv + (size_t)c * K, L, U);
       copy_vec<Z, GS>(A.extB + cur + (size_t)c * K, A.extB + prv + (size_t)c * K, L, U);
@@ -396,7 +404,7 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
 #pragma unroll
       for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
   }
-  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
+  if (lane == 0 && !(A.use_solved && A.round > 0)) atomicAdd(A.rerun + A.round, 1u);
 
   const int n_main = tn - ch.t0;                // steps j < n_main produce beta~ at SNPs tn-1 .. t0
   const bool has_ext = ch.t0 > ch.cs;           // one more step: beta~ at the last SNP of the previous chunk
@@ -444,12 +452,269 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
 template <int Z, int GS>
 __global__ void __launch_bounds__(32 * kWPC) fb2_round_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem[];
-  if (A.round > 1 && A.rerun[A.round - 1] == 0) return;      // fixed point already reached (queued round)
+  if (A.use_solved) {
+    if (A.round > 0 && A.rerun[A.round] == 0) return;        // probe mode: this cycle's boundary test found nothing to re-run
+  } else if (A.round > 1 && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int id = blockIdx.x * kWPC + warp;                   // the warps of a CTA are independent of one another
   char *smem = fb2_smem + (size_t)warp * ring_stride;
   if (id < A.nChunks) fb2_forward<Z, GS>(A, id, lane, smem, TS);
   else if (id < 2 * A.nChunks) fb2_backward<Z, GS>(A, id - A.nChunks, lane, smem, TS);
+}
+
+// ------------------------------------------------------------------------------------------
+// Probe-accelerated rounds.  Re-running a dirty chunk from its neighbour's latest vector moves information by one
+// chunk per round, so a run of m dirty chunks costs m rounds of one chunk latency each.  The chunk map is linear,
+// and what a boundary vector has to get right is small: the posterior at a boundary lives on a handful of states
+// (competing genotypes, the same genotype in two clusters).  So each dirty chunk propagates three pieces of the
+// vector it started from -- the two states of largest posterior weight as unit vectors, and the remainder --
+// on three otherwise idle warps (fb2_probe_kernel), a per-chromosome pass chains the resulting 3-dimensional maps
+// through every run of dirty chunks (fb2_solve_kernel), and the round kernel re-runs the dirty chunks once from
+// the predicted vectors.  The next boundary test decides; nothing is accepted on the strength of a prediction.
+// ------------------------------------------------------------------------------------------
+constexpr int kProbes = 3;
+
+// the two states of largest posterior weight want_j * wgt_j (ties: lowest index), identical in every warp that asks
+template <int Z, int GS>
+__device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const double *wgt, const LaneInfo<GS> &L, int U, int &j1,
+                                            int &j2) {
+  double g[GS][Z];
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) g[s][z] = L.act[s] ? want[s][z] * wgt[L.g[s] + z * U] : -1.0;
+  int found[2] = {-1, -1};
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    double bv = -2.0;
+    int bj = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        const int j = L.g[s] + z * U;
+        const double v = (L.act[s] && j != found[0]) ? g[s][z] : -2.0;
+        if (v > bv || (v == bv && j < bj)) { bv = v; bj = j; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+    }
+    found[pass] = bj;
+  }
+  j1 = found[0];
+  j2 = found[1];
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool backward, int lane, char *smem, int TS) {
+  const Chunk ch = A.chunks[c];
+  const int U = A.U, K = A.K, Kp = A.Kp;
+  LaneInfo<GS> L;
+  lane_info<GS>(L, U, lane, A.het);
+  const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  unsigned char *dirty = backward ? A.dirtyB : A.dirtyF;
+  if (backward ? (ch.t1 == ch.ce) : (ch.t0 == ch.cs)) {      // no neighbour on that side: exact since round 0
+    if (p == 0 && lane == 0) { dirty[c] = 0; (backward ? A.probedB : A.probedF)[c] = 0; }
+    return;
+  }
+  const double *used = (backward ? A.startB : A.startF) + (size_t)c * K;
+  const double *wantp = backward ? A.endB + prv + (size_t)(c + 1) * K : A.endF + prv + (size_t)(c - 1) * K;
+  const double *wgt = (backward ? A.extF : A.extB) + prv + (size_t)c * K;
+  double v[GS][Z];
+  const bool ok = boundary_ok<Z, GS>(v, used, wantp, wgt, L, U, A.tol);
+  // a clean chunk is probed as well when one of the probe_window chunks before it (in recursion order) is dirty:
+  // that chunk's re-run will shift this chunk's input, and the chain solve can then carry the prediction on
+  bool active = !ok;
+  if (!active && A.probe_window > 0) {
+    double tmp[GS][Z];
+    for (int u = 1; u <= A.probe_window && !active; ++u) {
+      const int cu = backward ? c + u : c - u;
+      if (cu < 0 || cu >= A.nChunks) break;
+      const Chunk cc = A.chunks[cu];
+      if (cc.chr != ch.chr || (backward ? (cc.t1 == cc.ce) : (cc.t0 == cc.cs))) break;
+      const double *u_used = (backward ? A.startB : A.startF) + (size_t)cu * K;
+      const double *u_want = backward ? A.endB + prv + (size_t)(cu + 1) * K : A.endF + prv + (size_t)(cu - 1) * K;
+      const double *u_wgt = (backward ? A.extF : A.extB) + prv + (size_t)cu * K;
+      active = !boundary_ok<Z, GS>(tmp, u_used, u_want, u_wgt, L, U, A.tol);
+    }
+  }
+  if (p == 0 && lane == 0) {
+    dirty[c] = ok ? 0 : 1;
+    (backward ? A.probedB : A.probedF)[c] = active ? 1 : 0;
+    if (!ok) atomicAdd(A.rerun + A.round, 1u);
+  }
+  if (!active) return;
+  int j1, j2;
+  top2_states<Z, GS>(v, wgt, L, U, j1, j2);
+  if (p == 0 && lane == 0) {
+    int *J = (backward ? A.probeJB : A.probeJF) + 2 * c;
+    J[0] = j1;
+    J[1] = j2;
+  }
+  // piece p of the vector this chunk last started from
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      const int j = L.g[s] + z * U;
+      const bool top = (j == j1) || (j == j2);
+      double x;
+      if (p < 2) x = (j == (p == 0 ? j1 : j2)) ? 1.0 : 0.0;
+      else x = top ? 0.0 : used[L.act[s] ? j : 0];
+      v[s][z] = L.act[s] ? x : 0.0;
+    }
+  long long E = 0;
+  Ring ring;
+  ring.init(smem, TS, Kp, false, lane);
+  const int n = ch.t1 - ch.t0;
+  const int ntiles = (n + TS - 1) / TS;
+  if (!backward) {
+    if (lane == 0)
+      for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)ch.t0 + (long long)k * TS, 0);
+    for (int k = 0; k < ntiles; ++k) {
+      ring.wait(k);
+      const char *slot = ring.slot(k);
+      const int ns = min(TS, n - k * TS);
+      for (int s = 0; s < ns; ++s) {
+        double B[GS][Z];
+        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)s * Kp, L, U);
+        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * s);
+        int e;
+        fwd_step2<Z, GS>(v, B, tr, L, e);
+        E += e;
+      }
+      __syncwarp();
+      if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)ch.t0 + (long long)(k + kNS) * TS, 0);
+    }
+  } else {
+    const int tn = ch.t1;
+    if (lane == 0)
+      for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, 0);
+    for (int k = 0; k < ntiles; ++k) {
+      ring.wait(k);
+      const char *slot = ring.slot(k);
+      const int ns = min(TS, n - k * TS);
+      for (int s = 0; s < ns; ++s) {
+        const int r = TS - 1 - s;
+        double B[GS][Z];
+        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
+        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
+        int e;
+        bwd_step2<Z, GS>(v, B, tr, L, e);
+        E += e;
+      }
+      __syncwarp();
+      if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, 0);
+    }
+  }
+  store_row<Z, GS>((backward ? A.probeB : A.probeF) + ((size_t)c * kProbes + p) * K, v, L, U, 1.0);
+  if (lane == 0) ((backward ? A.probeEB : A.probeEF) + (size_t)c * kProbes)[p] = (int)max(-2000000000LL, min(2000000000LL, E));
+}
+
+// warp id -> (direction, chunk, probe); clean chunks cost one boundary test
+template <int Z, int GS>
+__global__ void __launch_bounds__(32 * kWPC) fb2_probe_kernel(Fb2Args A, int TS, int ring_stride) {
+  extern __shared__ __align__(128) char fb2_smem[];
+  if (A.round > 1 && A.rerun[A.round - 1] == 0) return;      // the previous test already found every boundary clean
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int id = blockIdx.x * kWPC + warp;
+  if (id >= 2 * A.nChunks * kProbes) return;
+  const int p = id % kProbes, cd = id / kProbes;
+  const bool backward = cd >= A.nChunks;
+  fb2_probe<Z, GS>(A, backward ? cd - A.nChunks : cd, p, backward, lane, fb2_smem + (size_t)warp * ring_stride, TS);
+}
+
+// One warp per (chromosome, direction): walk the chunks in recursion order carrying the best available boundary
+// vector; for a dirty chunk express that vector in the chunk's three probe pieces and predict the chunk's end.
+template <int Z, int GS>
+__global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
+  if (A.rerun[A.round] == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int id = blockIdx.x * kWPC + (threadIdx.x >> 5);
+  if (id >= 2 * A.nChr) return;
+  const bool backward = id >= A.nChr;
+  const int chr = backward ? id - A.nChr : id;
+  const int U = A.U, K = A.K;
+  LaneInfo<GS> L;
+  lane_info<GS>(L, U, lane, A.het);
+  const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
+  const int c_lo = A.chr_chunk0[chr], c_hi = A.chr_chunk0[chr + 1];     // chunks [c_lo, c_hi)
+  const unsigned char *dirty = backward ? A.dirtyB : A.dirtyF;
+  unsigned char *solved = backward ? A.solvedB : A.solvedF;
+  const unsigned char *probed = backward ? A.probedB : A.probedF;
+  const double *endv = (backward ? A.endB : A.endF) + prv;
+  const double *startv = backward ? A.startB : A.startF;
+  const double *probe = backward ? A.probeB : A.probeF;
+  const int *probeE = backward ? A.probeEB : A.probeEF;
+  const int *probeJ = backward ? A.probeJB : A.probeJF;
+  double *sol = backward ? A.solB : A.solF;
+  double cur[GS][Z];
+  bool have = false;              // cur[] holds a PREDICTED end vector of the previous chunk in recursion order
+  const int nC = c_hi - c_lo;
+  for (int i = 0; i < nC; ++i) {
+    const int c = backward ? c_hi - 1 - i : c_lo + i;
+    bool run = (i > 0) && dirty[c];
+    if (i > 0 && !run && have && probed[c]) {
+      // clean against its neighbour's current end, but that neighbour is about to be re-run: test the prediction
+      double tmp[GS][Z];
+      const double *wgt = (backward ? A.extF : A.extB) + prv + (size_t)c * K;
+      store_row<Z, GS>(sol + (size_t)c * K, cur, L, U, 1.0);
+      __syncwarp();
+      run = !boundary_ok<Z, GS>(tmp, startv + (size_t)c * K, sol + (size_t)c * K, wgt, L, U, A.tol);
+    }
+    if (!run) {                   // first chunk in recursion order, or clean: keeps its own end
+      if (lane == 0) solved[c] = 0;
+      have = false;
+      continue;
+    }
+    if (!have) load_row<Z, GS>(cur, endv + (size_t)(backward ? c + 1 : c - 1) * K, L, U);     // the neighbour's actual end
+    store_row<Z, GS>(sol + (size_t)c * K, cur, L, U, 1.0);
+    if (lane == 0) solved[c] = 1;
+    // coefficients of cur[] in the three pieces of the vector the chunk started from
+    const int j1 = probeJ[2 * c], j2 = probeJ[2 * c + 1];
+    double x1 = 0.0, x2 = 0.0, rn = 0.0, ro = 0.0;
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        const int j = L.g[s] + z * U;
+        const double v = cur[s][z], o = L.act[s] ? startv[(size_t)c * K + j] : 0.0;
+        x1 += (j == j1) ? v : 0.0;
+        x2 += (j == j2) ? v : 0.0;
+        const bool rest = L.act[s] && j != j1 && j != j2;
+        rn += rest ? v : 0.0;
+        ro += rest ? o : 0.0;
+      }
+    x1 = warp_sum(x1); x2 = warp_sum(x2); rn = warp_sum(rn); ro = warp_sum(ro);
+    const double x3 = ro > 0.0 ? rn / ro : 0.0;
+    const int E0 = probeE[c * kProbes], E1 = probeE[c * kProbes + 1], E2 = probeE[c * kProbes + 2];
+    int Em = -2147483647;
+    if (x1 > 0.0) Em = max(Em, E0);
+    if (x2 > 0.0) Em = max(Em, E1);
+    if (x3 > 0.0) Em = max(Em, E2);
+    const double f0 = x1 > 0.0 ? scalbn(x1, max(E0 - Em, -2000)) : 0.0, f1 = x2 > 0.0 ? scalbn(x2, max(E1 - Em, -2000)) : 0.0,
+                 f2 = x3 > 0.0 ? scalbn(x3, max(E2 - Em, -2000)) : 0.0;
+    double e[GS][Z], p0[GS][Z], p1[GS][Z], p2[GS][Z];
+    load_row<Z, GS>(p0, probe + ((size_t)c * kProbes + 0) * K, L, U);
+    load_row<Z, GS>(p1, probe + ((size_t)c * kProbes + 1) * K, L, U);
+    load_row<Z, GS>(p2, probe + ((size_t)c * kProbes + 2) * K, L, U);
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) e[s][z] = f0 * p0[s][z] + f1 * p1[s][z] + f2 * p2[s][z];
+    const double tot = vec_sum<Z, GS>(e);
+    have = (tot > 0.0) && (tot < CUDART_INF);
+    if (have) {
+      const double inv = 1.0 / tot;
+#pragma unroll
+      for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) cur[s][z] = e[s][z] * inv;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -721,6 +986,26 @@ cudaError_t fb2_launch_round(const Fb2Args &A, int Z, cudaStream_t st) {
     if (e == cudaSuccess) fb2_round_kernel<ZZ, GG><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
   });
   return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t fb2_launch_probe(const Fb2Args &A, int Z, cudaStream_t st) {
+  const int GS = A.U > 32 ? 2 : 1;
+  const int TS = tile_steps(A.Kp, false);
+  const size_t ring = ring_bytes(TS, A.Kp, false), smem = kWPC * ring;
+  const unsigned blocks = (unsigned)((2 * A.nChunks * kProbes + kWPC - 1) / kWPC);
+  cudaError_t e = cudaSuccess;
+  FB2_DISPATCH(Z, GS, {
+    e = set_smem(fb2_probe_kernel<ZZ, GG>, smem);
+    if (e == cudaSuccess) fb2_probe_kernel<ZZ, GG><<<blocks, 32 * kWPC, smem, st>>>(A, TS, (int)ring);
+  });
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t fb2_launch_solve(const Fb2Args &A, int Z, cudaStream_t st) {
+  const int GS = A.U > 32 ? 2 : 1;
+  const unsigned blocks = (unsigned)((2 * A.nChr + kWPC - 1) / kWPC);
+  FB2_DISPATCH(Z, GS, (fb2_solve_kernel<ZZ, GG><<<blocks, 32 * kWPC, 0, st>>>(A)));
+  return cudaGetLastError();
 }
 
 cudaError_t fb2_launch_final(const Fb2Args &A, int Z, bool write_post, bool from_py, cudaStream_t st) {

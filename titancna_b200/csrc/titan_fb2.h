@@ -35,6 +35,16 @@ struct Fb2Args {
   double *startB, *endB, *extB;
   double *chunk_ll;            // [nChunks]
   unsigned int *rerun;         // [rounds] chunk runs (both directions) of each round
+  // probe-accelerated rounds (see fb2_probe_kernel): per direction [nChunks] flags and [nChunks][3][K] probe results
+  int use_solved;              // round kernel: chunks flagged in solved* start from sol* without a test
+  int probe_window;            // also probe this many chunks downstream of a dirty one (a re-run shifts its successors' inputs)
+  unsigned char *dirtyF, *dirtyB, *solvedF, *solvedB, *probedF, *probedB;
+  int *probeJF, *probeJB;      // [nChunks][2] the two states probed individually
+  int *probeEF, *probeEB;      // [nChunks][3] accumulated power-of-two exponents of the probe results
+  double *probeF, *probeB;     // [nChunks][3][K]
+  double *solF, *solB;         // [nChunks][K] boundary vectors predicted by the chain solve
+  const int *chr_chunk0;       // [nChr+1] first chunk of every chromosome
+  int nChr;
   // final pass
   double *part;                // [nChunks][6][K]
   double *rhoG0, *rhoZ0;       // [nChr][U], [nChr][Z]
@@ -54,6 +64,8 @@ struct EmArgs {
 // all launchers return the CUDA launch status; Z in 1..8, U <= 64
 cudaError_t fb2_launch_emission(const EmArgs &E, int Z, cudaStream_t st);
 cudaError_t fb2_launch_round(const Fb2Args &A, int Z, cudaStream_t st);
+cudaError_t fb2_launch_probe(const Fb2Args &A, int Z, cudaStream_t st);    // boundary test + probe runs of the dirty chunks
+cudaError_t fb2_launch_solve(const Fb2Args &A, int Z, cudaStream_t st);    // per-chromosome chain solve from the probe results
 cudaError_t fb2_launch_final(const Fb2Args &A, int Z, bool write_post, bool from_py, cudaStream_t st);
 bool fb2_supported(int U, int Z);
 
