@@ -151,12 +151,10 @@ struct titan_solver {
 
   // configuration
   int chunk_len = 1024, warm = 192, max_rounds = 0;   // max_rounds 0: bounded by the chunk count (titan_solver_configure)
-  int engine = 2;                  // 2: titan_fb2 (materialised emissions, posterior-weighted boundary test); 1: round-1 kernels (TITAN_ENGINE)
+  int engine = 2;                  // titan_fb2: materialised emissions, posterior-weighted boundary test, probe-accelerated rounds
   int Kp = 0;                      // row stride of the per-SNP K-vectors in HBM: K states + the emission shift, padded to 16 bytes
   double tol = 1e-8;               // posterior-weighted boundary tolerance of the fb2 engine
   int vit_mode = -1;               // 3: cluster-sliced scan, 2: register-sliced dense scan, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
-  int ws_mode = 1;                 // 0: warp-per-chunk kernels only, 1: automatic, 2: warp-specialised only
-  double rtol = 1e-8, atol = 1e-290;   // 100x inside the 1e-6 posterior tolerance; errors do not amplify
 
   // device data
   DevBuf<SnpRec> snp;
@@ -165,12 +163,13 @@ struct titan_solver {
   DevBuf<Chunk> chunks;
   std::vector<Chunk> chunks_h;
   int nChunks = 0, maxChunksPerChr = 1;
-  DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, tmp, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
+  DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
   int probes = 1;                  // fb2 engine: probe-accelerated rounds (TITAN_PROBES)
   int probe_window = 8;            // from the second cycle on, chunks this close downstream of a dirty one are probed too (TITAN_PROBE_WINDOW)
   DevBuf<unsigned char> pflags;    // [4][nChunks] dirtyF, dirtyB, solvedF, solvedB
   DevBuf<int> pints;               // [2][nChunks][2] probed states, [2][nChunks][3] probe exponents
   DevBuf<double> pvec;             // [2][nChunks][3][K] probe results, [2][nChunks][K] predicted boundary vectors
+  DevBuf<double> subb;             // [nChunks][3][K] beta~ at the quarter boundaries of every chunk
   DevBuf<double> Bm, extf, extb;   // fb2 engine: scaled emissions [N][Kp]; one-step-extended boundary vectors [2][nChunks][K]
   // per-SNP arrays carry kFbPadRows rows of slack on both sides (TMA copies whole tiles)
   SnpRec *snp_p() const { return snp.p + kFbPadRows; }
@@ -178,16 +177,12 @@ struct titan_solver {
   double *alpha_p() const { return alpha.p + (size_t)kFbPadRows * Kp; }
   double *Bm_p() const { return Bm.p + (size_t)kFbPadRows * Kp; }
   DevBuf<int> chr_chunk0;          // [nChr+1]
-  int overlap = 1;                 // run the forward and the backward boundary rounds concurrently on two streams
   int round_batch = 4;             // verification rounds queued per host synchronisation
-  cudaStream_t stream_b = nullptr; // second stream (backward boundary rounds)
-  cudaEvent_t ev_sync[2] = {nullptr, nullptr};
   DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
   DevBuf<double> model;            // packed ModelConsts arrays
   DevBuf<unsigned char> het_d;
   PinBuf<double> model_h, out_h;
   PinBuf<unsigned int> rerun_h;
-  int nSlices = 1, slice = 64;
 
   // Viterbi (lazy)
   DevBuf<int> chr_start32, txn_id, path, tile_first;
@@ -205,12 +200,8 @@ struct titan_solver {
   ~titan_solver() {
     if (vit_builder.joinable()) vit_builder.join();
     if (stream) cudaStreamSynchronize(stream);          // members (device buffers) go back to the pool after this body
-    if (stream_b) cudaStreamSynchronize(stream_b);
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
-    for (auto &e : ev_sync)
-      if (e) cudaEventDestroy(e);
-    if (stream_b) cudaStreamDestroy(stream_b);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -246,6 +237,7 @@ static void build_chunks(titan_solver *s) {
   s->endb.alloc(2 * nc * K);
   s->extf.alloc(2 * nc * K);
   s->extb.alloc(2 * nc * K);
+  s->subb.alloc(3 * nc * K);
   s->pflags.alloc(6 * nc);
   s->pints.alloc(10 * nc);
   s->pvec.alloc(8 * nc * K);
@@ -256,9 +248,6 @@ static void build_chunks(titan_solver *s) {
   CK(cudaMemset(s->extb.p, 0, sizeof(double) * 2 * nc * K));
   s->chunk_ll.alloc(nc);
   s->part.alloc(nc * 6 * K);
-  s->slice = 64;
-  s->nSlices = (s->nChunks + s->slice - 1) / s->slice;
-  s->tmp.alloc((size_t)s->nSlices * 6 * K);
   s->tm.n_chunks = s->nChunks;
   std::vector<int> cc0(s->nChr + 1, 0);
   for (const Chunk &ch : s->chunks_h) cc0[ch.chr + 1]++;
@@ -328,21 +317,15 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
 
   std::unique_ptr<titan_solver> S(new titan_solver());
   titan_solver *s = S.get();
-  if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
-  if (const char *e = getenv("TITAN_OVERLAP")) s->overlap = atoi(e);
   if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
-  if (const char *e = getenv("TITAN_ENGINE")) s->engine = atoi(e) == 1 ? 1 : 2;
   if (const char *e = getenv("TITAN_PROBES")) s->probes = atoi(e);
   if (const char *e = getenv("TITAN_PROBE_WINDOW")) s->probe_window = std::max(0, atoi(e));
-  if (in.U > 32) s->engine = 2;
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
     for (auto &e : s->ev) CK(cudaEventCreate(&e));
-    CK(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
-    for (auto &e : s->ev_sync) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     trace.mark("streams + events");
     s->N = in.N; s->nChr = in.nChr; s->U = in.U; s->Z = in.Z; s->K = in.U * in.Z;
     s->Kp = (s->K + 2) & ~1;           // K states + the shift m_t, rows a multiple of 16 bytes
@@ -484,7 +467,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     }
     trace.mark("SnpRec (host lgamma) + upload");
     s->alpha.alloc((size_t)(N + 2 * kFbPadRows) * s->Kp);
-    if (s->engine == 2) {
+    {
       s->Bm.alloc((size_t)(N + 2 * kFbPadRows) * s->Kp);
       // only the slack rows need defined contents (they are copied with the tiles, never used)
       const size_t padn = (size_t)kFbPadRows * s->Kp;
@@ -534,9 +517,8 @@ extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup
   try {
     s->chunk_len = chunk_len;
     s->warm = std::max(1, warmup_len);
-    if (rel_tol > 0) { s->rtol = rel_tol; s->tol = rel_tol; }
+    if (rel_tol > 0) s->tol = rel_tol;
     s->max_rounds = std::max(0, max_rounds);
-    if (const char *e = getenv("TITAN_WS_MODE")) s->ws_mode = atoi(e);
     CK(cudaSetDevice(s->device));
     build_chunks(s);
     s->state_valid = false;
@@ -638,132 +620,6 @@ static int upload_model(titan_solver *s, const titan_params *p, double *muR_out,
 // ---------------------------------------------------------------------------------------------
 // E-step launch sequence
 // ---------------------------------------------------------------------------------------------
-template <int Z>
-static void launch_fwd(const titan_solver *s, const FbArgs &A, cudaStream_t st) {
-  const int wpb = 4;
-  dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
-  if (s->legacy_py) fwd_chunk_kernel<Z, true><<<grid, block, 0, st>>>(A);
-  else fwd_chunk_kernel<Z, false><<<grid, block, 0, st>>>(A);
-}
-
-template <int Z>
-static void launch_bwd(const titan_solver *s, const FbArgs &A, bool write_post, cudaStream_t st) {
-  const int wpb = 4;
-  dim3 grid((A.nChunks + wpb - 1) / wpb), block(32 * wpb);
-  if (s->legacy_py) bwd_chunk_kernel<Z, true, false><<<grid, block, 0, st>>>(A);
-  else if (write_post) bwd_chunk_kernel<Z, false, true><<<grid, block, 0, st>>>(A);
-  else bwd_chunk_kernel<Z, false, false><<<grid, block, 0, st>>>(A);
-}
-
-template <int Z>
-static void launch_fwd_ws(const titan_solver *s, const FbArgs &A, cudaStream_t st) {
-  static bool attr_set[2] = {false, false};
-  const size_t smem = ws_fwd_smem<Z>();
-  if (s->legacy_py) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
-    fwd_chunk_ws_kernel<Z, true><<<A.nChunks, 128, smem, st>>>(A);
-  } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(fwd_chunk_ws_kernel<Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
-    fwd_chunk_ws_kernel<Z, false><<<A.nChunks, 128, smem, st>>>(A);
-  }
-}
-
-template <int Z>
-static void launch_bwd_ws(const titan_solver *s, const FbArgs &A, bool write_post, cudaStream_t st) {
-  static bool attr_set[3] = {false, false, false};
-  const size_t smem = ws_bwd_smem<Z>();
-  if (s->legacy_py) {
-    if (!attr_set[2]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[2] = true; }
-    bwd_chunk_ws_kernel<Z, true, false><<<A.nChunks, 128, smem, st>>>(A);
-  } else if (write_post) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
-    bwd_chunk_ws_kernel<Z, false, true><<<A.nChunks, 128, smem, st>>>(A);
-  } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(bwd_chunk_ws_kernel<Z, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
-    bwd_chunk_ws_kernel<Z, false, false><<<A.nChunks, 128, smem, st>>>(A);
-  }
-}
-
-#define Z_DISPATCH(Zv, CALL)            \
-  switch (Zv) {                         \
-    case 1: { constexpr int ZZ = 1; CALL; } break; \
-    case 2: { constexpr int ZZ = 2; CALL; } break; \
-    case 3: { constexpr int ZZ = 3; CALL; } break; \
-    case 4: { constexpr int ZZ = 4; CALL; } break; \
-    case 5: { constexpr int ZZ = 5; CALL; } break; \
-    case 6: { constexpr int ZZ = 6; CALL; } break; \
-    case 7: { constexpr int ZZ = 7; CALL; } break; \
-    case 8: { constexpr int ZZ = 8; CALL; } break; \
-    default: break;                     \
-  }
-
-// One direction of the chunked scan: round 0, then verification rounds until a round re-runs nothing.
-// The object only LAUNCHES; the caller drives both directions so that their (latency-bound)
-// verification rounds can overlap on two streams.
-struct Direction {
-  titan_solver *s;
-  FbArgs A;
-  bool backward, write_post;
-  cudaStream_t st;
-  unsigned int *ctr, *ctr_h;
-  int round = 0, hard_cap = 0;
-  int64_t runs = 0;
-  bool done = false;
-
-  void launch(int r) {
-    A.round = r;
-    // round 0 with many chunks is throughput-bound: one warp per chunk.  Verification rounds (few
-    // chunks re-run) and the plain sequential mode are latency-bound: one warp-specialised CTA per chunk.
-    const bool ws = s->ws_mode == 2 || (s->ws_mode == 1 && (r > 0 || s->nChunks < 4 * 148));
-    if (backward) {
-      if (ws) { Z_DISPATCH(s->Z, launch_bwd_ws<ZZ>(s, A, write_post, st)); }
-      else { Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, A, write_post, st)); }
-    } else {
-      if (ws) { Z_DISPATCH(s->Z, launch_fwd_ws<ZZ>(s, A, st)); }
-      else { Z_DISPATCH(s->Z, launch_fwd<ZZ>(s, A, st)); }
-    }
-    s->tm.kernel_launches++;
-  }
-  void start(cudaEvent_t e0, cudaEvent_t e1) {
-    ctr = s->rerun.p + (backward ? kRoundSlots : 0);
-    ctr_h = s->rerun_h.p + (backward ? kRoundSlots : 0);
-    hard_cap = std::min(kRoundSlots - 8, s->maxChunksPerChr + 2);
-    CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * (size_t)(hard_cap + 8), st));
-    A.rerun = ctr;
-    A.startv = backward ? s->startb.p : s->startf.p;
-    A.endv = backward ? s->endb.p : s->endf.p;
-    CK(cudaEventRecord(e0, st));
-    launch(0);
-    CK(cudaEventRecord(e1, st));
-    CK(cudaGetLastError());
-    runs = s->nChunks;
-    round = 0;
-    done = s->maxChunksPerChr <= 1;      // plain sequential recursion: nothing to verify
-  }
-  // Queue up to `batch` verification rounds and the read-back of their counters.  A round whose
-  // predecessor re-ran nothing exits at once on the device, so queueing past the fixed point is cheap
-  // and the host synchronises once per batch instead of once per round.
-  int queued = 0;
-  void next_rounds(int batch) {
-    queued = std::max(1, std::min(batch, hard_cap - round));
-    for (int q = 1; q <= queued; ++q) {
-      launch(round + q);
-      CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync(ctr_h + round + 1, ctr + round + 1, sizeof(unsigned int) * (size_t)queued, cudaMemcpyDeviceToHost, st));
-  }
-  int finish_rounds() {                  // after the stream has been synchronised
-    for (int q = 1; q <= queued; ++q) {
-      ++round;
-      if (ctr_h[round] == 0) { done = true; break; }
-      runs += ctr_h[round];
-    }
-    if (!done && round >= hard_cap)
-      return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
-    return TITAN_OK;
-  }
-};
-
 // fb2 engine: emission pass, round 0, verification rounds (both directions in one launch per round, batches of
 // rounds per host synchronisation), final posterior pass.  Events: ev[0] start, ev[6] after the emission pass,
 // ev[7] after round 0, ev[1] after the last round, ev[9] after the final pass.
@@ -784,6 +640,7 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
   A.startF = s->startf.p; A.endF = s->endf.p; A.extF = s->extf.p;
   A.startB = s->startb.p; A.endB = s->endb.p; A.extB = s->extb.p;
   A.chunk_ll = s->chunk_ll.p;
+  A.subB = s->subb.p;
   A.rerun = s->rerun.p;
   {
     const size_t nc = s->nChunks;
@@ -892,111 +749,19 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   }
   if (s->legacy_py && loggamma_out && s->loggamma.n < (size_t)N * K) s->loggamma.alloc((size_t)N * K);
 
-  FbArgs A{};
-  A.snp = s->snp_p();
-  A.txn = s->txn_p();
-  A.chunks = s->chunks.p;
-  A.nChunks = s->nChunks;
-  A.U = U;
-  A.warm = s->warm;
-  A.rtol = s->rtol;
-  A.atol = s->atol;
-  A.M = model_layout(s, s->model.p);
-  A.het = s->het_d.p;
-  A.py = s->legacy_py ? s->py.p : nullptr;
-  A.alpha = s->alpha.p;
-  A.chunk_ll = s->chunk_ll.p;
-  A.part = s->part.p;
-  A.rhoG0 = s->rhoG0.p;
-  A.rhoZ0 = s->rhoZ0.p;
-  A.rhoG = (post && !s->legacy_py) ? s->rhoG.p : nullptr;
-  A.rhoZ = (post && !s->legacy_py) ? s->rhoZ.p : nullptr;
-  A.loggamma = (s->legacy_py && loggamma_out) ? s->loggamma.p : nullptr;
-
-  // Forward and backward recursions are independent chains (only the posteriors need both), so the
-  // backward BOUNDARY rounds (beta only) run concurrently with the forward rounds on a second
-  // stream; a final backward pass from the verified boundaries forms posteriors and statistics.
-  const bool chunked = s->maxChunksPerChr > 1;
-  const bool overlap = chunked && s->overlap != 0;
-  A.beta_only = 0;
-  A.final_pass = 0;
-  Direction F{s, A, false, false, s->stream}, B{s, A, true, post, overlap ? s->stream_b : s->stream};
   CK(cudaEventRecord(s->ev[0], s->stream));
   int fb2_rounds = 0;
   int64_t fb2_runs = 0;
-  if (s->engine == 2) {
-    rc = estep_fb2(s, post, loggamma_out != nullptr, posterior_only, &fb2_rounds, &fb2_runs);
-    if (rc != TITAN_OK) return rc;
-  } else if (posterior_only) {
-    B.st = s->stream;
-    B.A.rerun = s->rerun.p + kRoundSlots;
-    B.A.startv = s->startb.p;
-    B.A.endv = s->endb.p;
-    B.A.final_pass = 1;
-    B.A.round = 0;
-    CK(cudaEventRecord(s->ev[6], s->stream));
-    CK(cudaEventRecord(s->ev[7], s->stream));
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    CK(cudaEventRecord(s->ev[8], s->stream));
-    Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, B.A, post, s->stream));
-    CK(cudaEventRecord(s->ev[9], s->stream));
-    s->tm.kernel_launches++;
-    CK(cudaGetLastError());
-    B.runs = s->nChunks;
-  } else if (overlap) {
-    CK(cudaEventRecord(s->ev_sync[0], s->stream));             // model constants are uploaded on the main stream
-    CK(cudaStreamWaitEvent(s->stream_b, s->ev_sync[0], 0));
-    B.A.beta_only = 1;
-    F.start(s->ev[6], s->ev[7]);
-    B.start(s->ev[8], s->ev[9]);
-    while (!F.done || !B.done) {
-      const bool f = !F.done, b = !B.done;
-      if (f) F.next_rounds(s->round_batch);
-      if (b) B.next_rounds(s->round_batch);
-      if (f) CK(cudaStreamSynchronize(F.st));
-      if (b) CK(cudaStreamSynchronize(B.st));
-      if (f && (rc = F.finish_rounds()) != TITAN_OK) return rc;
-      if (b && (rc = B.finish_rounds()) != TITAN_OK) return rc;
-    }
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    CK(cudaEventRecord(s->ev_sync[1], s->stream_b));
-    CK(cudaStreamWaitEvent(s->stream, s->ev_sync[1], 0));
-    // final pass: every chunk once from its verified boundary vector (one warp per chunk, all chunks)
-    B.st = s->stream;
-    B.A.beta_only = 0;
-    B.A.final_pass = 1;
-    B.A.round = B.round + 1;
-    CK(cudaEventRecord(s->ev[8], s->stream));
-    Z_DISPATCH(s->Z, launch_bwd<ZZ>(s, B.A, post, s->stream));
-    CK(cudaEventRecord(s->ev[9], s->stream));
-    s->tm.kernel_launches++;
-    CK(cudaGetLastError());
-    B.runs += s->nChunks;
-  } else {
-    F.start(s->ev[6], s->ev[7]);
-    while (!F.done) {
-      F.next_rounds(s->round_batch);
-      CK(cudaStreamSynchronize(F.st));
-      if ((rc = F.finish_rounds()) != TITAN_OK) return rc;
-    }
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    B.start(s->ev[8], s->ev[9]);
-    while (!B.done) {
-      B.next_rounds(s->round_batch);
-      CK(cudaStreamSynchronize(B.st));
-      if ((rc = B.finish_rounds()) != TITAN_OK) return rc;
-    }
-  }
+  rc = estep_fb2(s, post, loggamma_out != nullptr, posterior_only, &fb2_rounds, &fb2_runs);
+  if (rc != TITAN_OK) return rc;
   CK(cudaEventRecord(s->ev[2], s->stream));
-  const int fr = s->engine == 2 ? fb2_rounds : F.round + 1, br = s->engine == 2 ? fb2_rounds : B.round + 1;
-  const int64_t fruns = s->engine == 2 ? fb2_runs : F.runs, bruns = s->engine == 2 ? 0 : B.runs;
+  const int fr = fb2_rounds, br = fb2_rounds;
+  const int64_t fruns = fb2_runs, bruns = 0;
   const int width = 6 * K;
   {
-    dim3 g1((width + 127) / 128, s->nSlices);
-    reduce_slices_kernel<<<g1, 128, 0, s->stream>>>(s->part.p, s->nChunks, width, s->slice, s->tmp.p);
-    reduce_final_kernel<<<(width + nChr + 127) / 128, 128, 0, s->stream>>>(s->tmp.p, s->nSlices, width, s->chunk_ll.p,
-                                                                          s->chunks.p, s->nChunks, nChr, s->out.p);
-    s->tm.kernel_launches += 2;
+    reduce_kernel<<<(width + 31) / 32 + 1, 256, 0, s->stream>>>(s->part.p, s->nChunks, width, s->chunk_ll.p, s->chr_chunk0.p, nChr,
+                                                                  s->out.p);
+    s->tm.kernel_launches += 1;
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(s->ev[3], s->stream));
@@ -1016,10 +781,8 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   s->tm.engine = s->engine;
   s->tm.last_emission_ms = 0;
   s->tm.last_rounds_ms = 0;
-  if (s->engine == 2) {
-    CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[6])); s->tm.last_emission_ms = ms;
-    CK(cudaEventElapsedTime(&ms, s->ev[7], s->ev[1])); s->tm.last_rounds_ms = ms;
-  }
+  CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[6])); s->tm.last_emission_ms = ms;
+  CK(cudaEventElapsedTime(&ms, s->ev[7], s->ev[1])); s->tm.last_rounds_ms = ms;
   s->tm.last_fwd_rounds = fr; s->tm.last_bwd_rounds = br;
   s->tm.last_fwd_chunk_runs = fruns; s->tm.last_bwd_chunk_runs = bruns;
   if (o) {
@@ -1418,7 +1181,7 @@ static int legacy_create(const char *who, const double *log_pi, int K, const dou
   int64_t cs[2] = {0, T};
   SolverInit in{T, 1, cs, positions, nullptr, nullptr, nullptr, py, txnLen, zStrength, U, numClust, zs, nZS};
   int rc = solver_create_impl(in, out);
-  if (rc == TITAN_OK) { (*out)->rtol = 1e-10; (*out)->tol = 1e-10; }   // compatibility path: tightest setting, it is not the fast path
+  if (rc == TITAN_OK) (*out)->tol = 1e-10;   // compatibility path: tightest setting, it is not the fast path
   return rc;
 }
 

@@ -13,8 +13,19 @@ struct __align__(16) SnpRec {   // parameter-independent per-SNP columns (HBM, r
   double lb;   // lgamma(N+1)-lgamma(x+1)-lgamma(N-x+1), host libm (R/hmmClonal.R:618)
 };
 
-struct __align__(16) TxnRec {   // structured transition between SNP t-1 and t (unused at chr start)
-  double k0, k1, k2, k3, cB, k4, irn, irh;   // irn/irh = 1/rowsum of a non-HET / HET source
+// Structured transition between SNP t-1 and t (unused at a chromosome start), stored once per lane class so that a
+// lane reads its own coefficients without selects: half 0 serves non-HET genotypes, half 1 the diploid-HET genotype.
+//   forward  (destination class):  o = cW*W + cG*Wg + cZ*Wz[z] + cw*w[z],  w = alpha*irs(source class)
+//   backward (source class):       o = (k0*Wn + cB*H + cG*loc + k1*Wz[z] + cw*bb[z]) * irs
+// k0 = oG(1-rhoZ), k1 = oG(2rhoZ-1), k2 = (rhoG-oG)(1-rhoZ), k3 = (rhoG-oG)(2rhoZ-1), cB = oG*rhoZ, k4 = (rhoG-oG)rhoZ
+struct __align__(16) TxnHalf {
+  double irs;          // 1/rowsum of a source of this class
+  double cW, cG;       // k0, k2  |  cB, k4
+  double cZ, cw;       // k1, k3  |  0, 0
+  double k0, cB, k1;   // the class-independent terms of the backward step
+};
+struct __align__(16) TxnRec {
+  TxnHalf h[2];
 };
 
 struct Chunk {
@@ -47,13 +58,13 @@ __device__ __forceinline__ float warp_maxf(float v) {
   return v;
 }
 
-// 2^-exponent(v) for positive finite v (exact power of two; 1.0 for 0 / subnormal / non-finite input).
-// Branch-free: it sits on the recursion's critical path.
+// 2^-exponent(v) for positive v: an exact power of two taken from the exponent field with integer instructions (it
+// sits on the recursion's critical path).  Zero gives 2^1023 (0 stays 0); a non-finite v gives garbage next to a
+// vector that is already non-finite -- the host rejects non-finite log-likelihoods.
 __device__ __forceinline__ double pow2_rescale(double v, int &e_out) {
   const int be = (__double2hiint(v) >> 20) & 0x7ff;
-  const bool ok = (unsigned)(be - 1) < 0x7feu;
-  e_out = ok ? be - 1023 : 0;
-  return __hiloint2double(ok ? ((2046 - be) << 20) : 0x3ff00000, 0);   // biased exponent 1023 - e
+  e_out = be - 1023;
+  return __hiloint2double((2046 - be) << 20, 0);   // biased exponent 1023 - e
 }
 
 }  // namespace titan

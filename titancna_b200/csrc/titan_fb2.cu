@@ -17,6 +17,8 @@
 // every such component's error alive for as long as the diagonal of the transition matrix carries it).
 #include "titan_fb2.h"
 
+#include <algorithm>
+
 namespace titan {
 
 // ------------------------------------------------------------------------------------------
@@ -48,64 +50,88 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int kNS = 3;   // ring slots per warp
-constexpr int kWPC = 4;  // warps (= chunks) per CTA: a warp's SM sub-partition is its index in the CTA modulo 4, so
-                         // one-warp CTAs would crowd a single scheduler
+constexpr int kWPC = 4;  // warps per CTA: a warp's SM sub-partition is its index in the CTA modulo 4, so one-warp CTAs
+                         // would crowd a single scheduler.  Round kernels: four independent chunks; final pass: the
+                         // four quarters of one chunk.
 
 // Per-warp ring of per-SNP row tiles.  A tile is TS consecutive SNP rows of up to four arrays; lane 0 issues the
-// copies, every lane waits on the slot's mbarrier before reading.  FINAL adds the alpha rows and the records.
+// copies, every lane waits on the slot's mbarrier before reading.  `fin` adds the alpha rows and the records.
+// The cursor walks the stream one position at a time: position i of the stream is SNP first + dir*i, tiles are
+// fetched kNS - 1 ahead.
 struct Ring {
   char *base;
   unsigned long long *bar;
-  int TS, Kp;
-  unsigned rowB, slot_bytes, offT, offA, offS, tx_bytes;
+  const Fb2Args *A;
+  int TS, Kp, dir, k, s, ntiles;
+  long long first;
+  unsigned rowB, slot_bytes, offT, offA, offS;
   bool fin;
+  int lane;
 
-  __device__ __forceinline__ void init(char *smem, int TS_, int Kp_, bool fin_, int lane) {
-    TS = TS_; Kp = Kp_; fin = fin_;
+  __device__ __forceinline__ void issue(int kk) {
+    const int sl = kk % kNS;
+    char *slot = base + (size_t)sl * slot_bytes;
+    // ascending streams: tile kk holds SNP rows first + kk*TS ..; descending ones: rows first - (kk+1)*TS + 1 .. first - kk*TS
+    const long long rowBT = dir > 0 ? first + (long long)kk * TS : first - (long long)(kk + 1) * TS + 1;
+    fence_async_smem();          // the slot was read through the generic proxy until the __syncwarp before this call
+    mbar_expect_tx(bar + sl, slot_bytes);
+    bulk_g2s(slot, A->Bm + rowBT * Kp, (unsigned)TS * rowB, bar + sl);
+    bulk_g2s(slot + offT, A->txn + rowBT, (unsigned)TS * (unsigned)sizeof(TxnRec), bar + sl);
+    if (fin) {                   // posteriors are formed one SNP below the emission row of the same stream position
+      bulk_g2s(slot + offA, A->alpha + (rowBT - 1) * Kp, (unsigned)TS * rowB, bar + sl);
+      bulk_g2s(slot + offS, A->snp + (rowBT - 1), (unsigned)TS * 32u, bar + sl);
+    }
+  }
+  __device__ __forceinline__ void start(const Fb2Args &A_, char *smem, int TS_, bool fin_, int lane_, int dir_, long long first_,
+                                        int npos) {
+    A = &A_; TS = TS_; Kp = A_.Kp; fin = fin_; lane = lane_; dir = dir_; first = first_;
     rowB = (unsigned)Kp * 8u;
     offT = (unsigned)TS * rowB;
-    offA = offT + (unsigned)TS * 64u;
+    offA = offT + (unsigned)TS * (unsigned)sizeof(TxnRec);
     offS = offA + (fin ? (unsigned)TS * rowB : 0u);
     slot_bytes = offS + (fin ? (unsigned)TS * 32u : 0u);
-    tx_bytes = slot_bytes;
     base = smem;
     bar = reinterpret_cast<unsigned long long *>(smem + (size_t)kNS * slot_bytes);
+    ntiles = (npos + TS - 1) / TS;
+    k = 0;
+    s = 0;
     if (lane == 0) {
-      for (int s = 0; s < kNS; ++s) mbar_init(bar + s, 1);
+      for (int i = 0; i < kNS; ++i) mbar_init(bar + i, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       fence_async_smem();
+      for (int i = 0; i < kNS && i < ntiles; ++i) issue(i);
     }
     __syncwarp();
+    if (ntiles > 0) mbar_wait(bar, 0u);
   }
-  // rowBT: first SNP row of the B / transition tile;  rowAS: first SNP row of the alpha / record tile
-  __device__ __forceinline__ void issue(int k, const Fb2Args &A, long long rowBT, long long rowAS) {
-    const int s = k % kNS;
-    char *slot = base + (size_t)s * slot_bytes;
-    fence_async_smem();          // the slot was read through the generic proxy until the __syncwarp before this call
-    mbar_expect_tx(bar + s, tx_bytes);
-    bulk_g2s(slot, A.Bm + rowBT * Kp, (unsigned)TS * rowB, bar + s);
-    bulk_g2s(slot + offT, A.txn + rowBT, (unsigned)TS * 64u, bar + s);
-    if (fin) {
-      bulk_g2s(slot + offA, A.alpha + rowAS * Kp, (unsigned)TS * rowB, bar + s);
-      bulk_g2s(slot + offS, A.snp + rowAS, (unsigned)TS * 32u, bar + s);
+  // row of the current stream position inside its tile (tiles ascend in SNP index whatever the direction)
+  __device__ __forceinline__ int row() const { return dir > 0 ? s : TS - 1 - s; }
+  __device__ __forceinline__ const char *slot() const { return base + (size_t)(k % kNS) * slot_bytes; }
+  __device__ __forceinline__ void advance() {
+    if (++s == TS) {
+      __syncwarp();
+      if (lane == 0 && k + kNS < ntiles) issue(k + kNS);
+      ++k;
+      s = 0;
+      if (k < ntiles) mbar_wait(bar + (k % kNS), (unsigned)((k / kNS) & 1));
     }
   }
-  __device__ __forceinline__ void wait(int k) { mbar_wait(bar + (k % kNS), (unsigned)((k / kNS) & 1)); }
-  __device__ __forceinline__ const char *slot(int k) const { return base + (size_t)(k % kNS) * slot_bytes; }
 };
 
 // ------------------------------------------------------------------------------------------
 // lane geometry and the structured steps
 // ------------------------------------------------------------------------------------------
-template <int GS>
+template <int Z, int GS>
 struct LaneInfo {
   int g[GS];
   bool act[GS], het[GS];
+  unsigned off[GS][Z];        // byte offset of state (g, z) inside a K-vector row (0 for inactive slots)
+  unsigned hoff[GS];          // byte offset of this slot's coefficient half inside a TxnRec
   int het_lane, het_slot;     // where the diploid-HET genotype lives (-1: the table has none)
 };
 
-template <int GS>
-__device__ __forceinline__ void lane_info(LaneInfo<GS> &L, int U, int lane, const unsigned char *het) {
+template <int Z, int GS>
+__device__ __forceinline__ void lane_info(LaneInfo<Z, GS> &L, int U, int lane, const unsigned char *het) {
   L.het_lane = -1;
   L.het_slot = 0;
 #pragma unroll
@@ -113,47 +139,53 @@ __device__ __forceinline__ void lane_info(LaneInfo<GS> &L, int U, int lane, cons
     L.g[s] = lane + 32 * s;
     L.act[s] = L.g[s] < U;
     L.het[s] = L.act[s] && het[L.g[s]];
+    L.hoff[s] = L.het[s] ? (unsigned)sizeof(TxnHalf) : 0u;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) L.off[s][z] = L.act[s] ? 8u * (unsigned)(L.g[s] + z * U) : 0u;
   }
   for (int u = 0; u < U; ++u)
     if (het[u]) { L.het_lane = u & 31; L.het_slot = u >> 5; }
 }
 
-// forward: a <- (A_t^T applied to a) .* (B * 2^-e);  HET destinations differ only in their coefficients
+// forward: a <- (A_t^T applied to a) .* (B * 2^-e);  the lane's coefficient half does the HET / non-HET selection
 template <int Z, int GS>
-__device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[GS][Z], const TxnRec &tr, const LaneInfo<GS> &L,
+__device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[GS][Z], const char *trow, const LaneInfo<Z, GS> &L,
                                           int &e) {
   double w[GS][Z], Wz[Z], Wg[GS];
+  double2 c01[GS], c23[GS];
+  double c4[GS];
 #pragma unroll
   for (int z = 0; z < Z; ++z) Wz[z] = 0.0;
 #pragma unroll
   for (int s = 0; s < GS; ++s) {
-    const double irs = L.het[s] ? tr.irh : tr.irn;
+    const char *cf = trow + L.hoff[s];
+    c01[s] = *reinterpret_cast<const double2 *>(cf);          // irs, cW
+    c23[s] = *reinterpret_cast<const double2 *>(cf + 16);     // cG, cZ
+    c4[s] = *reinterpret_cast<const double *>(cf + 32);       // cw
     Wg[s] = 0.0;
 #pragma unroll
-    for (int z = 0; z < Z; ++z) { w[s][z] = a[s][z] * irs; Wz[z] += w[s][z]; Wg[s] += w[s][z]; }
+    for (int z = 0; z < Z; ++z) { w[s][z] = a[s][z] * c01[s].x; Wz[z] += w[s][z]; Wg[s] += w[s][z]; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)      // Z interleaved butterflies: Z independent shuffles per stage
 #pragma unroll
     for (int z = 0; z < Z; ++z) Wz[z] += __shfl_xor_sync(0xffffffffu, Wz[z], o);
-  double W = 0.0;
+  double W = Wz[0];
 #pragma unroll
-  for (int z = 0; z < Z; ++z) W += Wz[z];
+  for (int z = 1; z < Z; ++z) W += Wz[z];
   const double sc = pow2_rescale(W, e);
 #pragma unroll
   for (int s = 0; s < GS; ++s) {
-    const bool h = L.het[s];
-    const double cW = h ? tr.cB : tr.k0, cG = h ? tr.k4 : tr.k2, cZ = h ? 0.0 : tr.k1, cw = h ? 0.0 : tr.k3;
-    const double base = cW * W + cG * Wg[s];
+    const double base = c01[s].y * W + c23[s].x * Wg[s];
 #pragma unroll
-    for (int z = 0; z < Z; ++z) a[s][z] = (base + cZ * Wz[z] + cw * w[s][z]) * (B[s][z] * sc);
+    for (int z = 0; z < Z; ++z) a[s][z] = (base + c23[s].y * Wz[z] + c4[s] * w[s][z]) * (B[s][z] * sc);
   }
 }
 
 // backward: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two.  The table holds at most one
 // diploid-HET genotype, so the HET mass is a broadcast from its lane instead of a butterfly.
 template <int Z, int GS>
-__device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[GS][Z], const TxnRec &tr, const LaneInfo<GS> &L,
+__device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[GS][Z], const char *trow, const LaneInfo<Z, GS> &L,
                                           int &e) {
   double bb[GS][Z], loc[GS], red[Z];
 #pragma unroll
@@ -179,37 +211,44 @@ __device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
     for (int z = 0; z < Z; ++z) red[z] += __shfl_xor_sync(0xffffffffu, red[z], o);
-  double Wn = 0.0;
+  double Wn = red[0];
 #pragma unroll
-  for (int z = 0; z < Z; ++z) Wn += red[z];
+  for (int z = 1; z < Z; ++z) Wn += red[z];
   const double sc = pow2_rescale(Wn + H, e);
-  const double common = tr.k0 * Wn + tr.cB * H;
 #pragma unroll
   for (int s = 0; s < GS; ++s) {
-    const bool h = L.het[s];
-    const double cG = h ? tr.k4 : tr.k2, cw = h ? 0.0 : tr.k3;
-    const double irs = L.act[s] ? (h ? tr.irh : tr.irn) * sc : 0.0;
-    const double base = common + cG * loc[s];
+    const TxnHalf c = *reinterpret_cast<const TxnHalf *>(trow + L.hoff[s]);
+    const double irs = L.act[s] ? c.irs * sc : 0.0;
+    const double base = c.k0 * Wn + c.cB * H + c.cG * loc[s];
 #pragma unroll
-    for (int z = 0; z < Z; ++z) b[s][z] = (base + tr.k1 * red[z] + cw * bb[s][z]) * irs;
+    for (int z = 0; z < Z; ++z) b[s][z] = (base + c.k1 * red[z] + c.cw * bb[s][z]) * irs;
   }
 }
 
 template <int Z, int GS>
-__device__ __forceinline__ void load_row(double (&v)[GS][Z], const double *row, const LaneInfo<GS> &L, int U) {
+__device__ __forceinline__ void load_row(double (&v)[GS][Z], const void *row, const LaneInfo<Z, GS> &L) {
 #pragma unroll
   for (int s = 0; s < GS; ++s)
 #pragma unroll
-    for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? row[L.g[s] + z * U] : 0.0;
+    for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? *reinterpret_cast<const double *>(static_cast<const char *>(row) + L.off[s][z]) : 0.0;
 }
 
 template <int Z, int GS>
-__device__ __forceinline__ void store_row(double *row, const double (&v)[GS][Z], const LaneInfo<GS> &L, int U, double scale) {
+__device__ __forceinline__ void store_row(void *row, const double (&v)[GS][Z], const LaneInfo<Z, GS> &L, double scale) {
 #pragma unroll
   for (int s = 0; s < GS; ++s)
     if (L.act[s])
 #pragma unroll
-      for (int z = 0; z < Z; ++z) row[L.g[s] + z * U] = v[s][z] * scale;
+      for (int z = 0; z < Z; ++z) *reinterpret_cast<double *>(static_cast<char *>(row) + L.off[s][z]) = v[s][z] * scale;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void store_row(void *row, const double (&v)[GS][Z], const LaneInfo<Z, GS> &L) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+    if (L.act[s])
+#pragma unroll
+      for (int z = 0; z < Z; ++z) *reinterpret_cast<double *>(static_cast<char *>(row) + L.off[s][z]) = v[s][z];
 }
 
 template <int Z, int GS>
@@ -222,23 +261,32 @@ __device__ __forceinline__ double vec_sum(const double (&v)[GS][Z]) {
   return warp_sum(loc);
 }
 
+template <int Z, int GS>
+__device__ __forceinline__ void scale_vec(double (&v)[GS][Z], double f) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) v[s][z] *= f;
+}
+
 // posterior-weighted comparison of the boundary vector a chunk used with the one its neighbour produced;
 // `want` is left in v[][] (the vector a re-run starts from)
 template <int Z, int GS>
 __device__ __forceinline__ bool boundary_ok(double (&v)[GS][Z], const double *used, const double *want, const double *wgt,
-                                            const LaneInfo<GS> &L, int U, double tol) {
+                                            const LaneInfo<Z, GS> &L, double tol) {
+  double u[GS][Z], p[GS][Z];
+  load_row<Z, GS>(u, used, L);
+  load_row<Z, GS>(v, want, L);
+  load_row<Z, GS>(p, wgt, L);
   double num = 0.0, den = 0.0;
   bool bad = false;
 #pragma unroll
   for (int s = 0; s < GS; ++s)
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
-      const int j = L.g[s] + z * U;
-      const double u = L.act[s] ? used[j] : 0.0, w = L.act[s] ? want[j] : 0.0, p = L.act[s] ? wgt[j] : 0.0;
-      v[s][z] = w;
-      num += p * fabs(u - w);
-      den += p * w;
-      bad |= (u != u) || (w != w);
+      num += p[s][z] * fabs(u[s][z] - v[s][z]);
+      den += p[s][z] * v[s][z];
+      bad |= (u[s][z] != u[s][z]) || (v[s][z] != v[s][z]);
     }
   num = warp_sum(num);
   den = warp_sum(den);
@@ -247,12 +295,30 @@ __device__ __forceinline__ bool boundary_ok(double (&v)[GS][Z], const double *us
 }
 
 template <int Z, int GS>
-__device__ __forceinline__ void copy_vec(double *dst, const double *src, const LaneInfo<GS> &L, int U) {
-#pragma unroll
-  for (int s = 0; s < GS; ++s)
-    if (L.act[s])
-#pragma unroll
-      for (int z = 0; z < Z; ++z) dst[L.g[s] + z * U] = src[L.g[s] + z * U];
+__device__ __forceinline__ void copy_vec(double *dst, const double *src, const LaneInfo<Z, GS> &L) {
+  double v[GS][Z];
+  load_row<Z, GS>(v, src, L);
+  store_row<Z, GS>(dst, v, L);
+}
+
+// one forward step at the cursor's position; OWNED steps store alpha~ and account for the log-likelihood
+template <int Z, int GS, bool OWNED>
+__device__ __forceinline__ void fwd_one(double (&a)[GS][Z], Ring &ring, const LaneInfo<Z, GS> &L, int K, double &acc_m, int &acc_e,
+                                        char *&arow) {
+  const char *slot = ring.slot();
+  const int r = ring.row();
+  const char *brow = slot + (size_t)r * ring.rowB;
+  double B[GS][Z];
+  load_row<Z, GS>(B, brow, L);
+  int e;
+  fwd_step2<Z, GS>(a, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+  if (OWNED) {
+    acc_m += reinterpret_cast<const double *>(brow)[K];
+    acc_e += e;
+    store_row<Z, GS>(arow, a, L);
+    arow += ring.rowB;
+  }
+  ring.advance();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -261,9 +327,9 @@ __device__ __forceinline__ void copy_vec(double *dst, const double *src, const L
 template <int Z, int GS>
 __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, char *smem, int TS) {
   const Chunk ch = A.chunks[c];
-  const int U = A.U, K = A.K, Kp = A.Kp;
-  LaneInfo<GS> L;
-  lane_info<GS>(L, U, lane, A.het);
+  const int U = A.U, K = A.K;
+  LaneInfo<Z, GS> L;
+  lane_info<Z, GS>(L, U, lane, A.het);
   const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   double *startv = A.startF + (size_t)c * K;
   double a[GS][Z];
@@ -273,13 +339,13 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
     bool skip = (ch.t0 == ch.cs);       // chromosome-leading chunks start from pi: exact in round 0
     if (A.use_solved) {                 // probe mode: the probe kernel tested the boundary, the chain solve predicted the start
       skip = skip || !A.solvedF[c];
-      if (!skip) load_row<Z, GS>(a, A.solF + (size_t)c * K, L, U);
+      if (!skip) load_row<Z, GS>(a, A.solF + (size_t)c * K, L);
     } else if (!skip) {
-      skip = boundary_ok<Z, GS>(a, startv, A.endF + prv + (size_t)(c - 1) * K, A.extB + prv + (size_t)c * K, L, U, A.tol);
+      skip = boundary_ok<Z, GS>(a, startv, A.endF + prv + (size_t)(c - 1) * K, A.extB + prv + (size_t)c * K, L, A.tol);
     }
     if (skip) {
-      copy_vec<Z, GS>(A.endF + cur + (size_t)c * K, A.endF + prv + (size_t)c * K, L, U);
-      copy_vec<Z, GS>(A.extF + cur + (size_t)c * K, A.extF + prv + (size_t)c * K, L, U);
+      copy_vec<Z, GS>(A.endF + cur + (size_t)c * K, A.endF + prv + (size_t)c * K, L);
+      copy_vec<Z, GS>(A.extF + cur + (size_t)c * K, A.extF + prv + (size_t)c * K, L);
       return;
     }
     tb = ch.t0;
@@ -287,95 +353,86 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
   } else {
     tb = max(ch.t0 - A.warm, ch.cs);
     have_start = false;
-#pragma unroll
-    for (int s = 0; s < GS; ++s)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) a[s][z] = 0.0;
   }
   if (lane == 0 && !(A.use_solved && A.round > 0)) atomicAdd(A.rerun + A.round, 1u);
 
   const int n_own = ch.t1 - tb;                 // stream positions q < n_own are SNPs tb + q of this chunk
   const bool has_ext = ch.t1 < ch.ce;           // one more step: alpha^ at the first SNP of the next chunk
-  const int n = n_own + (has_ext ? 1 : 0);
   const int q0 = ch.t0 - tb;
-  const int ntiles = (n + TS - 1) / TS;
   Ring ring;
-  ring.init(smem, TS, Kp, false, lane);
-  if (lane == 0)
-    for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tb + (long long)k * TS, 0);
+  ring.start(A, smem, TS, false, lane, +1, tb, n_own + (has_ext ? 1 : 0));
 
   double acc_m = 0.0;        // sum of emission shifts over the owned range
-  long long acc_e = 0;       // sum of power-of-two rescale exponents over the owned range
+  int acc_e = 0;             // sum of power-of-two rescale exponents over the owned range
   double s_start = 1.0;      // mass of the vector entering the owned range
-  double s_end = 1.0;
-  double *arow = A.alpha + (size_t)tb * Kp;
+  char *arow = reinterpret_cast<char *>(A.alpha + (size_t)ch.t0 * A.Kp);
   int q = 0;
-  for (int k = 0; k < ntiles; ++k) {
-    ring.wait(k);
-    const char *slot = ring.slot(k);
-    const int ns = min(TS, n - k * TS);
-    for (int s = 0; s < ns; ++s, ++q, arow += Kp) {
-      const double *brow = reinterpret_cast<const double *>(slot) + (size_t)s * Kp;
-      double B[GS][Z];
-      load_row<Z, GS>(B, brow, L, U);
-      const double m = brow[K];
-      int e = 0;
-      if (q == 0 && !have_start) {
-        const bool at_start = (tb == ch.cs);
+  if (!have_start) {
+    // stream position 0 has no predecessor vector: chromosome start (pi) or a flat speculative start
+    const char *brow = ring.slot() + (size_t)ring.row() * ring.rowB;
+    double B[GS][Z];
+    load_row<Z, GS>(B, brow, L);
+    if (tb == ch.cs) {
+      load_row<Z, GS>(a, A.pi, L);
 #pragma unroll
-        for (int g = 0; g < GS; ++g)
+      for (int g = 0; g < GS; ++g)
 #pragma unroll
-          for (int z = 0; z < Z; ++z)
-            a[g][z] = (at_start ? (L.act[g] ? A.pi[L.g[g] + z * U] : 0.0) : 1.0) * B[g][z];
-      } else {
-        if (q == q0) {        // entering the owned range: record / publish alpha~_{t0-1}
-          s_start = vec_sum<Z, GS>(a);
-          double inv = 1.0;
-          if (!have_start) { inv = 1.0 / s_start; s_start = 1.0; }
+        for (int z = 0; z < Z; ++z) a[g][z] *= B[g][z];
+    } else {
 #pragma unroll
-          for (int g = 0; g < GS; ++g)
+      for (int g = 0; g < GS; ++g)
 #pragma unroll
-            for (int z = 0; z < Z; ++z) a[g][z] *= inv;
-          store_row<Z, GS>(startv, a, L, U, 1.0);
-        }
-        if (q == n_own) {     // leaving the owned range: boundary vector alpha^_{t1-1}
-          s_end = vec_sum<Z, GS>(a);
-          store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, U, 1.0 / s_end);
-        }
-        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * s);
-        fwd_step2<Z, GS>(a, B, tr, L, e);
-      }
-      if (q >= q0 && q < n_own) {
-        acc_m += m;
-        acc_e += e;
-        store_row<Z, GS>(arow, a, L, U, 1.0);
-      }
+        for (int z = 0; z < Z; ++z) a[g][z] = B[g][z];
     }
-    __syncwarp();
-    if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tb + (long long)(k + kNS) * TS, 0);
+    if (q0 == 0) {           // only a chromosome-leading chunk owns its very first position
+      acc_m += reinterpret_cast<const double *>(brow)[K];
+      store_row<Z, GS>(arow, a, L);
+      arow += ring.rowB;
+    }
+    ring.advance();
+    q = 1;
+    for (; q < q0; ++q) fwd_one<Z, GS, false>(a, ring, L, K, acc_m, acc_e, arow);      // warm-up: nothing stored
   }
-  const double tot = vec_sum<Z, GS>(a);
+  if (ch.t0 != ch.cs) {      // entering the owned range: record / publish alpha~_{t0-1}
+    s_start = vec_sum<Z, GS>(a);
+    if (!have_start) { scale_vec<Z, GS>(a, 1.0 / s_start); s_start = 1.0; }
+    store_row<Z, GS>(startv, a, L);
+  }
+  for (; q < n_own; ++q) fwd_one<Z, GS, true>(a, ring, L, K, acc_m, acc_e, arow);
+  const double s_end = vec_sum<Z, GS>(a);
+  store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, 1.0 / s_end);
+  if (lane == 0) A.chunk_ll[c] = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
   if (has_ext) {
-    store_row<Z, GS>(A.extF + cur + (size_t)c * K, a, L, U, 1.0 / tot);
-  } else {
-    s_end = tot;
-    store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, U, 1.0 / tot);
+    fwd_one<Z, GS, false>(a, ring, L, K, acc_m, acc_e, arow);
+    store_row<Z, GS>(A.extF + cur + (size_t)c * K, a, L, 1.0 / vec_sum<Z, GS>(a));
   }
-  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
-  if (lane == 0) A.chunk_ll[c] = ll;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void bwd_one(double (&b)[GS][Z], Ring &ring, const LaneInfo<Z, GS> &L) {
+  const char *slot = ring.slot();
+  const int r = ring.row();
+  double B[GS][Z];
+  load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
+  int e;
+  bwd_step2<Z, GS>(b, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+  ring.advance();
 }
 
 // ------------------------------------------------------------------------------------------
 // backward chunk, boundary rounds: the beta recursion alone (src/fwd_backC_clonalCN.c:148-175)
 // b[] holds beta~_{tn}; tn == ce means "past the end" (beta_{ce-1} = 1).  Stream position j is SNP tn - j:
 // step j turns beta~_{tn-j} into beta~_{tn-j-1} with B and the transition record of SNP tn - j.
+// The vectors entering the lower three quarters of the chunk are parked for the final pass (subB).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quarter_start(const Chunk &ch, int k) { return ch.t0 + (int)(((long long)(ch.t1 - ch.t0) * k) / kWPC); }
+
 template <int Z, int GS>
 __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, char *smem, int TS) {
   const Chunk ch = A.chunks[c];
-  const int U = A.U, K = A.K, Kp = A.Kp;
-  LaneInfo<GS> L;
-  lane_info<GS>(L, U, lane, A.het);
+  const int U = A.U, K = A.K;
+  LaneInfo<Z, GS> L;
+  lane_info<Z, GS>(L, U, lane, A.het);
   const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   double *startv = A.startB + (size_t)c * K;
   double b[GS][Z];
@@ -385,13 +442,13 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
     bool skip = (ch.t1 == ch.ce);
     if (A.use_solved) {
       skip = skip || !A.solvedB[c];
-      if (!skip) load_row<Z, GS>(b, A.solB + (size_t)c * K, L, U);
+      if (!skip) load_row<Z, GS>(b, A.solB + (size_t)c * K, L);
     } else if (!skip) {
-      skip = boundary_ok<Z, GS>(b, startv, A.endB + prv + (size_t)(c + 1) * K, A.extF + prv + (size_t)c * K, L, U, A.tol);
+      skip = boundary_ok<Z, GS>(b, startv, A.endB + prv + (size_t)(c + 1) * K, A.extF + prv + (size_t)c * K, L, A.tol);
     }
     if (skip) {
-      copy_vec<Z, GS>(A.endB + cur + (size_t)c * K, A.endB + prv + (size_t)c * K, L, U);
-      copy_vec<Z, GS>(A.extB + cur + (size_t)c * K, A.extB + prv + (size_t)c * K, L, U);
+      copy_vec<Z, GS>(A.endB + cur + (size_t)c * K, A.endB + prv + (size_t)c * K, L);
+      copy_vec<Z, GS>(A.extB + cur + (size_t)c * K, A.extB + prv + (size_t)c * K, L);
       return;
     }
     tn = ch.t1;
@@ -408,47 +465,33 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
 
   const int n_main = tn - ch.t0;                // steps j < n_main produce beta~ at SNPs tn-1 .. t0
   const bool has_ext = ch.t0 > ch.cs;           // one more step: beta~ at the last SNP of the previous chunk
-  const int n = n_main + (has_ext ? 1 : 0);
-  const int jb = tn - ch.t1;                    // at step jb b[] is beta~_{t1}
-  const int ntiles = (n + TS - 1) / TS;
   Ring ring;
-  ring.init(smem, TS, Kp, false, lane);
-  if (lane == 0)
-    for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, 0);
+  ring.start(A, smem, TS, false, lane, -1, tn, n_main + (has_ext ? 1 : 0));
   int j = 0;
-  for (int k = 0; k < ntiles; ++k) {
-    ring.wait(k);
-    const char *slot = ring.slot(k);
-    const int ns = min(TS, n - k * TS);
-    for (int s = 0; s < ns; ++s, ++j) {
-      const int r = TS - 1 - s;                 // tile rows ascend in SNP index, the stream descends
-      if (j == jb && ch.t1 < ch.ce) {           // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
-        double inv = 1.0;
-        if (!from_boundary) inv = 1.0 / vec_sum<Z, GS>(b);
-#pragma unroll
-        for (int g = 0; g < GS; ++g)
-#pragma unroll
-          for (int z = 0; z < Z; ++z) b[g][z] *= inv;
-        store_row<Z, GS>(startv, b, L, U, 1.0);
-      }
-      if (j == n_main) store_row<Z, GS>(A.endB + cur + (size_t)c * K, b, L, U, 1.0 / vec_sum<Z, GS>(b));
-      if (tn - j < ch.ce) {
-        double B[GS][Z];
-        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
-        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
-        int e;
-        bwd_step2<Z, GS>(b, B, tr, L, e);
-      }
-    }
-    __syncwarp();
-    if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, 0);
+  if (tn == ch.ce) {                            // position 0 is past the end: beta_{ce-1} = 1, no step
+    ring.advance();
+    j = 1;
   }
-  const double inv = 1.0 / vec_sum<Z, GS>(b);
-  if (has_ext) store_row<Z, GS>(A.extB + cur + (size_t)c * K, b, L, U, inv);
-  else store_row<Z, GS>(A.endB + cur + (size_t)c * K, b, L, U, inv);
+  for (; j < tn - ch.t1; ++j) bwd_one<Z, GS>(b, ring, L);       // warm-up down to beta~_{t1}
+  if (ch.t1 < ch.ce) {                          // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
+    if (!from_boundary) scale_vec<Z, GS>(b, 1.0 / vec_sum<Z, GS>(b));
+    store_row<Z, GS>(startv, b, L);
+  }
+  // quarters kWPC-2 .. 0 of the chunk start from beta~ at the first SNP of the quarter above them
+  for (int k = kWPC - 1; k >= 1; --k) {
+    const int jq = tn - quarter_start(ch, k);   // after jq steps b[] is beta~ at SNP quarter_start(k)
+    for (; j < jq; ++j) bwd_one<Z, GS>(b, ring, L);
+    store_row<Z, GS>(A.subB + ((size_t)c * (kWPC - 1) + (k - 1)) * K, b, L);
+  }
+  for (; j < n_main; ++j) bwd_one<Z, GS>(b, ring, L);
+  store_row<Z, GS>(A.endB + cur + (size_t)c * K, b, L, 1.0 / vec_sum<Z, GS>(b));
+  if (has_ext) {
+    bwd_one<Z, GS>(b, ring, L);
+    store_row<Z, GS>(A.extB + cur + (size_t)c * K, b, L, 1.0 / vec_sum<Z, GS>(b));
+  }
 }
 
-// one launch per round: CTAs [0, nChunks) run forward chunks, [nChunks, 2 nChunks) backward chunks
+// one launch per round: warps [0, nChunks) run forward chunks, [nChunks, 2 nChunks) backward chunks
 template <int Z, int GS>
 __global__ void __launch_bounds__(32 * kWPC) fb2_round_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem[];
@@ -474,9 +517,10 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_round_kernel(Fb2Args A, int TS,
 // ------------------------------------------------------------------------------------------
 constexpr int kProbes = 3;
 
+
 // the two states of largest posterior weight want_j * wgt_j (ties: lowest index), identical in every warp that asks
 template <int Z, int GS>
-__device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const double *wgt, const LaneInfo<GS> &L, int U, int &j1,
+__device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const double *wgt, const LaneInfo<Z, GS> &L, int U, int &j1,
                                             int &j2) {
   double g[GS][Z];
 #pragma unroll
@@ -508,12 +552,13 @@ __device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const d
   j2 = found[1];
 }
 
+
 template <int Z, int GS>
 __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool backward, int lane, char *smem, int TS) {
   const Chunk ch = A.chunks[c];
-  const int U = A.U, K = A.K, Kp = A.Kp;
-  LaneInfo<GS> L;
-  lane_info<GS>(L, U, lane, A.het);
+  const int U = A.U, K = A.K;
+  LaneInfo<Z, GS> L;
+  lane_info<Z, GS>(L, U, lane, A.het);
   const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   unsigned char *dirty = backward ? A.dirtyB : A.dirtyF;
   if (backward ? (ch.t1 == ch.ce) : (ch.t0 == ch.cs)) {      // no neighbour on that side: exact since round 0
@@ -524,7 +569,7 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
   const double *wantp = backward ? A.endB + prv + (size_t)(c + 1) * K : A.endF + prv + (size_t)(c - 1) * K;
   const double *wgt = (backward ? A.extF : A.extB) + prv + (size_t)c * K;
   double v[GS][Z];
-  const bool ok = boundary_ok<Z, GS>(v, used, wantp, wgt, L, U, A.tol);
+  const bool ok = boundary_ok<Z, GS>(v, used, wantp, wgt, L, A.tol);
   // a clean chunk is probed as well when one of the probe_window chunks before it (in recursion order) is dirty:
   // that chunk's re-run will shift this chunk's input, and the chain solve can then carry the prediction on
   bool active = !ok;
@@ -538,7 +583,7 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
       const double *u_used = (backward ? A.startB : A.startF) + (size_t)cu * K;
       const double *u_want = backward ? A.endB + prv + (size_t)(cu + 1) * K : A.endF + prv + (size_t)(cu - 1) * K;
       const double *u_wgt = (backward ? A.extF : A.extB) + prv + (size_t)cu * K;
-      active = !boundary_ok<Z, GS>(tmp, u_used, u_want, u_wgt, L, U, A.tol);
+      active = !boundary_ok<Z, GS>(tmp, u_used, u_want, u_wgt, L, A.tol);
     }
   }
   if (p == 0 && lane == 0) {
@@ -555,6 +600,7 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
     J[1] = j2;
   }
   // piece p of the vector this chunk last started from
+  load_row<Z, GS>(v, used, L);
 #pragma unroll
   for (int s = 0; s < GS; ++s)
 #pragma unroll
@@ -563,54 +609,25 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
       const bool top = (j == j1) || (j == j2);
       double x;
       if (p < 2) x = (j == (p == 0 ? j1 : j2)) ? 1.0 : 0.0;
-      else x = top ? 0.0 : used[L.act[s] ? j : 0];
+      else x = top ? 0.0 : v[s][z];
       v[s][z] = L.act[s] ? x : 0.0;
     }
   long long E = 0;
-  Ring ring;
-  ring.init(smem, TS, Kp, false, lane);
   const int n = ch.t1 - ch.t0;
-  const int ntiles = (n + TS - 1) / TS;
-  if (!backward) {
-    if (lane == 0)
-      for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)ch.t0 + (long long)k * TS, 0);
-    for (int k = 0; k < ntiles; ++k) {
-      ring.wait(k);
-      const char *slot = ring.slot(k);
-      const int ns = min(TS, n - k * TS);
-      for (int s = 0; s < ns; ++s) {
-        double B[GS][Z];
-        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)s * Kp, L, U);
-        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * s);
-        int e;
-        fwd_step2<Z, GS>(v, B, tr, L, e);
-        E += e;
-      }
-      __syncwarp();
-      if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)ch.t0 + (long long)(k + kNS) * TS, 0);
-    }
-  } else {
-    const int tn = ch.t1;
-    if (lane == 0)
-      for (int k = 0; k < kNS && k < ntiles; ++k) ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, 0);
-    for (int k = 0; k < ntiles; ++k) {
-      ring.wait(k);
-      const char *slot = ring.slot(k);
-      const int ns = min(TS, n - k * TS);
-      for (int s = 0; s < ns; ++s) {
-        const int r = TS - 1 - s;
-        double B[GS][Z];
-        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
-        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
-        int e;
-        bwd_step2<Z, GS>(v, B, tr, L, e);
-        E += e;
-      }
-      __syncwarp();
-      if (lane == 0 && k + kNS < ntiles) ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, 0);
-    }
+  Ring ring;
+  ring.start(A, smem, TS, false, lane, backward ? -1 : +1, backward ? ch.t1 : ch.t0, n);
+  for (int q = 0; q < n; ++q) {
+    const char *slot = ring.slot();
+    const int r = ring.row();
+    double B[GS][Z];
+    load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
+    int e;
+    if (backward) bwd_step2<Z, GS>(v, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+    else fwd_step2<Z, GS>(v, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+    E += e;
+    ring.advance();
   }
-  store_row<Z, GS>((backward ? A.probeB : A.probeF) + ((size_t)c * kProbes + p) * K, v, L, U, 1.0);
+  store_row<Z, GS>((backward ? A.probeB : A.probeF) + ((size_t)c * kProbes + p) * K, v, L);
   if (lane == 0) ((backward ? A.probeEB : A.probeEF) + (size_t)c * kProbes)[p] = (int)max(-2000000000LL, min(2000000000LL, E));
 }
 
@@ -638,8 +655,8 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
   const bool backward = id >= A.nChr;
   const int chr = backward ? id - A.nChr : id;
   const int U = A.U, K = A.K;
-  LaneInfo<GS> L;
-  lane_info<GS>(L, U, lane, A.het);
+  LaneInfo<Z, GS> L;
+  lane_info<Z, GS>(L, U, lane, A.het);
   const size_t prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
   const int c_lo = A.chr_chunk0[chr], c_hi = A.chr_chunk0[chr + 1];     // chunks [c_lo, c_hi)
   const unsigned char *dirty = backward ? A.dirtyB : A.dirtyF;
@@ -661,17 +678,17 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
       // clean against its neighbour's current end, but that neighbour is about to be re-run: test the prediction
       double tmp[GS][Z];
       const double *wgt = (backward ? A.extF : A.extB) + prv + (size_t)c * K;
-      store_row<Z, GS>(sol + (size_t)c * K, cur, L, U, 1.0);
+      store_row<Z, GS>(sol + (size_t)c * K, cur, L);
       __syncwarp();
-      run = !boundary_ok<Z, GS>(tmp, startv + (size_t)c * K, sol + (size_t)c * K, wgt, L, U, A.tol);
+      run = !boundary_ok<Z, GS>(tmp, startv + (size_t)c * K, sol + (size_t)c * K, wgt, L, A.tol);
     }
     if (!run) {                   // first chunk in recursion order, or clean: keeps its own end
       if (lane == 0) solved[c] = 0;
       have = false;
       continue;
     }
-    if (!have) load_row<Z, GS>(cur, endv + (size_t)(backward ? c + 1 : c - 1) * K, L, U);     // the neighbour's actual end
-    store_row<Z, GS>(sol + (size_t)c * K, cur, L, U, 1.0);
+    if (!have) load_row<Z, GS>(cur, endv + (size_t)(backward ? c + 1 : c - 1) * K, L);     // the neighbour's actual end
+    store_row<Z, GS>(sol + (size_t)c * K, cur, L);
     if (lane == 0) solved[c] = 1;
     // coefficients of cur[] in the three pieces of the vector the chunk started from
     const int j1 = probeJ[2 * c], j2 = probeJ[2 * c + 1];
@@ -698,9 +715,9 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
     const double f0 = x1 > 0.0 ? scalbn(x1, max(E0 - Em, -2000)) : 0.0, f1 = x2 > 0.0 ? scalbn(x2, max(E1 - Em, -2000)) : 0.0,
                  f2 = x3 > 0.0 ? scalbn(x3, max(E2 - Em, -2000)) : 0.0;
     double e[GS][Z], p0[GS][Z], p1[GS][Z], p2[GS][Z];
-    load_row<Z, GS>(p0, probe + ((size_t)c * kProbes + 0) * K, L, U);
-    load_row<Z, GS>(p1, probe + ((size_t)c * kProbes + 1) * K, L, U);
-    load_row<Z, GS>(p2, probe + ((size_t)c * kProbes + 2) * K, L, U);
+    load_row<Z, GS>(p0, probe + ((size_t)c * kProbes + 0) * K, L);
+    load_row<Z, GS>(p1, probe + ((size_t)c * kProbes + 1) * K, L);
+    load_row<Z, GS>(p2, probe + ((size_t)c * kProbes + 2) * K, L);
 #pragma unroll
     for (int s = 0; s < GS; ++s)
 #pragma unroll
@@ -718,34 +735,21 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
 }
 
 // ------------------------------------------------------------------------------------------
-// final pass: beta from the verified boundary, posteriors, marginals, the six weighted sums
+// final pass: beta from the verified boundaries, posteriors, marginals, the six weighted sums.
+// One CTA per chunk, one warp per quarter of the chunk (the backward chunk parked beta~ at the quarter
+// boundaries), partial sums combined in shared memory in a fixed order.
 // reference: src/fwd_backC_clonalCN.c:148-192; R/hmmClonal.R:230-234; R/paramEstimation.R:34-40
 // ------------------------------------------------------------------------------------------
 template <int Z, int GS, bool WRITE_POST, bool FROM_PY>
 __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem_all[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x * kWPC + warp;
-  if (c >= A.nChunks) return;
-  char *fb2_smem = fb2_smem_all + (size_t)warp * ring_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
   const Chunk ch = A.chunks[c];
-  const int U = A.U, K = A.K, Kp = A.Kp;
-  LaneInfo<GS> L;
-  lane_info<GS>(L, U, lane, A.het);
-  double b[GS][Z];
-  if (ch.t1 < ch.ce) load_row<Z, GS>(b, A.startB + (size_t)c * K, L, U);
-  else {
-#pragma unroll
-    for (int s = 0; s < GS; ++s)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
-  }
-  const int tn = ch.t1, n = ch.t1 - ch.t0;
-  const int ntiles = (n + TS - 1) / TS;
-  Ring ring;
-  ring.init(fb2_smem, TS, Kp, true, lane);
-  if (lane == 0)
-    for (int k = 0; k < kNS && k < ntiles; ++k)
-      ring.issue(k, A, (long long)tn - (long long)(k + 1) * TS + 1, (long long)tn - (long long)(k + 1) * TS);
+  const int U = A.U, K = A.K;
+  LaneInfo<Z, GS> L;
+  lane_info<Z, GS>(L, U, lane, A.het);
+  const int ta = quarter_start(ch, warp), tn = quarter_start(ch, warp + 1);      // this warp owns SNPs [ta, tn)
+  const int n = tn - ta;
   double st[6][GS][Z];
 #pragma unroll
   for (int qq = 0; qq < 6; ++qq)
@@ -753,33 +757,37 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
     for (int s = 0; s < GS; ++s)
 #pragma unroll
       for (int z = 0; z < Z; ++z) st[qq][s][z] = 0.0;
-  int j = 0;
-  for (int k = 0; k < ntiles; ++k) {
-    ring.wait(k);
-    const char *slot = ring.slot(k);
-    const int ns = min(TS, n - k * TS);
-    for (int s = 0; s < ns; ++s, ++j) {
-      const int r = TS - 1 - s;
+  if (n > 0) {
+    double b[GS][Z];
+    if (warp < kWPC - 1) load_row<Z, GS>(b, A.subB + ((size_t)c * (kWPC - 1) + warp) * K, L);
+    else if (ch.t1 < ch.ce) load_row<Z, GS>(b, A.startB + (size_t)c * K, L);
+    else {
+#pragma unroll
+      for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
+    }
+    Ring ring;
+    ring.start(A, fb2_smem_all + (size_t)warp * ring_stride, TS, true, lane, -1, tn, n);
+    for (int j = 0; j < n; ++j) {
+      const char *slot = ring.slot();
+      const int r = ring.row();
       const int t = tn - j - 1;                 // the SNP whose posterior this step forms
       if (tn - j < ch.ce) {
         double B[GS][Z];
-        load_row<Z, GS>(B, reinterpret_cast<const double *>(slot) + (size_t)r * Kp, L, U);
-        const TxnRec tr = *reinterpret_cast<const TxnRec *>(slot + ring.offT + 64 * r);
+        load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
         int e;
-        bwd_step2<Z, GS>(b, B, tr, L, e);
+        bwd_step2<Z, GS>(b, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
       }
       double p[GS][Z];
-      load_row<Z, GS>(p, reinterpret_cast<const double *>(slot + ring.offA) + (size_t)r * Kp, L, U);
+      load_row<Z, GS>(p, slot + ring.offA + (size_t)r * ring.rowB, L);
       double loc = 0.0;
 #pragma unroll
       for (int g = 0; g < GS; ++g)
 #pragma unroll
         for (int z = 0; z < Z; ++z) { p[g][z] *= b[g][z]; loc += p[g][z]; }
       const double inv = 1.0 / warp_sum(loc);
-#pragma unroll
-      for (int g = 0; g < GS; ++g)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) p[g][z] *= inv;
+      scale_vec<Z, GS>(p, inv);
       if (!FROM_PY) {
         const SnpRec rec = *reinterpret_cast<const SnpRec *>(slot + ring.offS + 32 * r);
         const double l2 = rec.lr * rec.lr;
@@ -795,11 +803,12 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
             st[5][g][z] += l2 * p[g][z];
           }
       } else if (A.loggamma != nullptr) {
+        double lg[GS][Z];
 #pragma unroll
         for (int g = 0; g < GS; ++g)
-          if (L.act[g])
 #pragma unroll
-            for (int z = 0; z < Z; ++z) A.loggamma[(size_t)t * K + L.g[g] + z * U] = log(p[g][z]);
+          for (int z = 0; z < Z; ++z) lg[g][z] = log(p[g][z]);
+        store_row<Z, GS>(A.loggamma + (size_t)t * K, lg, L);
       }
       const bool first = (t == ch.cs);
       if (WRITE_POST || first) {
@@ -833,20 +842,34 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
             if (lane == z) dZ[z] = rz[z];
         }
       }
+      ring.advance();
     }
-    __syncwarp();
-    if (lane == 0 && k + kNS < ntiles)
-      ring.issue(k + kNS, A, (long long)tn - (long long)(k + kNS + 1) * TS + 1, (long long)tn - (long long)(k + kNS + 1) * TS);
   }
   if (!FROM_PY) {
-    double *dst = A.part + (size_t)c * 6 * K;
+    // combine the four quarters in a fixed order: quarter sums to shared memory, warp 0 adds them up
+    __syncthreads();                              // every ring of the CTA has been drained
+    double *sm = reinterpret_cast<double *>(fb2_smem_all);
+    double *mine = sm + (size_t)warp * 6 * K;
 #pragma unroll
-    for (int qq = 0; qq < 6; ++qq)
+    for (int qq = 0; qq < 6; ++qq) store_row<Z, GS>(mine + qq * K, st[qq], L);
+    __syncthreads();
+    if (warp == 0) {
+      double *dst = A.part + (size_t)c * 6 * K;
 #pragma unroll
-      for (int g = 0; g < GS; ++g)
-        if (L.act[g])
+      for (int qq = 0; qq < 6; ++qq) {
+        double acc[GS][Z], v[GS][Z];
+        load_row<Z, GS>(acc, sm + qq * K, L);
 #pragma unroll
-          for (int z = 0; z < Z; ++z) dst[qq * K + L.g[g] + z * U] = st[qq][g][z];
+        for (int w = 1; w < kWPC; ++w) {
+          load_row<Z, GS>(v, sm + ((size_t)w * 6 + qq) * K, L);
+#pragma unroll
+          for (int g = 0; g < GS; ++g)
+#pragma unroll
+            for (int z = 0; z < Z; ++z) acc[g][z] += v[g][z];
+        }
+        store_row<Z, GS>(dst + qq * K, acc, L);
+      }
+    }
   }
 }
 
@@ -927,7 +950,7 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
 bool fb2_supported(int U, int Z) { return U >= 1 && U <= 64 && Z >= 1 && Z <= 8; }
 
 static size_t ring_bytes(int TS, int Kp, bool fin) {
-  size_t slot = (size_t)TS * Kp * 8 + (size_t)TS * 64;
+  size_t slot = (size_t)TS * Kp * 8 + (size_t)TS * sizeof(TxnRec);
   if (fin) slot += (size_t)TS * Kp * 8 + (size_t)TS * 32;
   return ((kNS * slot + kNS * 8 + 127) / 128) * 128;
 }
@@ -1011,8 +1034,9 @@ cudaError_t fb2_launch_solve(const Fb2Args &A, int Z, cudaStream_t st) {
 cudaError_t fb2_launch_final(const Fb2Args &A, int Z, bool write_post, bool from_py, cudaStream_t st) {
   const int GS = A.U > 32 ? 2 : 1;
   const int TS = tile_steps(A.Kp, true);
-  const size_t ring = ring_bytes(TS, A.Kp, true), smem = kWPC * ring;
-  const unsigned blocks = (unsigned)((A.nChunks + kWPC - 1) / kWPC);
+  const size_t ring = ring_bytes(TS, A.Kp, true);
+  const size_t smem = std::max(kWPC * ring, (size_t)kWPC * 6 * A.K * sizeof(double));     // rings, then the quarter sums
+  const unsigned blocks = (unsigned)A.nChunks;
   cudaError_t e = cudaSuccess;
   if (from_py) {
     FB2_DISPATCH(Z, GS, {

@@ -33,6 +33,7 @@ struct Fb2Args {
   double *alpha;               // [N][Kp] scaled forward variables
   double *startF, *endF, *extF;   // [nChunks][K], [2][nChunks][K], [2][nChunks][K]
   double *startB, *endB, *extB;
+  double *subB;                // [nChunks][3][K] beta~ entering the lower three quarters of a chunk (final pass)
   double *chunk_ll;            // [nChunks]
   unsigned int *rerun;         // [rounds] chunk runs (both directions) of each round
   // probe-accelerated rounds (see fb2_probe_kernel): per direction [nChunks] flags and [nChunks][3][K] probe results

@@ -1,1074 +1,44 @@
-// titan_kernels.cuh -- sm_100a kernels of the TitanCNA E-step hot path (fp64 throughout).
-//
-// State space: joint state j = u + z*U (genotype u fastest; reference R/hmmClonal.R:196,
-// src/fwd_backC_clonalCN.c:234-235).  One WARP owns one position chunk of one chromosome:
-// lane g holds the Z cluster values of genotype g in registers, so the per-genotype sum is
-// thread-local and the per-cluster sums are Z butterfly reductions over the warp.
-//
-// Transition structure (src/fwd_backC_clonalCN.c:215-301): raw[i,j] is one of four values,
-// selected by (same genotype?, same cluster or destination is diploid-HET?), rows divided by
-// their sum.  Regrouped so every coefficient is non-negative (no cancellation):
-//   destination non-HET:  o[g,z] = k0*W + k1*Wz[z] + k2*Wg[g] + k3*w[g,z]
-//   destination HET    :  o[g,z] = cB*W + k4*Wg[g]
-// with w = alpha/rowsum(source), k0 = oG(1-rhoZ), k1 = oG(2rhoZ-1), k2 = (rhoG-oG)(1-rhoZ),
-// k3 = (rhoG-oG)(2rhoZ-1), cB = oG*rhoZ, k4 = (rhoG-oG)rhoZ, oG = (1-rhoG)/(K-1).
+// titan_kernels.cuh -- sm_100a kernels of the TitanCNA hot path other than the forward-backward engine
+// (titan_fb2.cu): deterministic reductions, transition coefficients, the dense compatibility kernels and Viterbi.
 #pragma once
 #include "titan_common.cuh"
 
 namespace titan {
 
 // ------------------------------------------------------------------------------------------
-// emission: B[z] = exp(py[g,z,t] - m_t), m_t ~ max_j py[j,t] rounded to float (any common shift
-// is exact as long as it is accounted for in the log-likelihood).
-// reference: R/hmmClonal.R:617-634 (densities), :491-523 (state loops)
-// ------------------------------------------------------------------------------------------
-template <int Z>
-struct LaneModel {
-  double lmu[Z], l1mu[Z], muC[Z];
-  double cN, i2v;
-  bool active, het;
-};
-
-template <int Z>
-__device__ __forceinline__ void load_lane_model(LaneModel<Z> &L, const ModelConsts &M, int U, int lane,
-                                                const unsigned char *het_flags) {
-  L.active = lane < U;
-  L.het = L.active && het_flags[lane];
-  int g = L.active ? lane : 0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    L.lmu[z] = M.lmu[g + z * U];
-    L.l1mu[z] = M.l1mu[g + z * U];
-    L.muC[z] = M.muC[g + z * U];
-  }
-  L.cN = M.cN[g];
-  L.i2v = M.i2v[g];
-}
-
-template <int Z>
-__device__ __forceinline__ double emission(const LaneModel<Z> &L, const SnpRec &r, double (&B)[Z]) {
-  double py[Z];
-  double mx = -CUDART_INF;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    double d = r.lr - L.muC[z];
-    double v = (r.lb + (r.x * L.lmu[z] + r.nx * L.l1mu[z])) + (L.cN - d * d * L.i2v);
-    py[z] = L.active ? v : -CUDART_INF;
-    mx = fmax(mx, py[z]);
-  }
-  float mf = warp_maxf(__double2float_rn(mx));
-  double m = (double)mf;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) B[z] = L.active ? exp(py[z] - m) : 0.0;
-  return m;
-}
-
-// same, log-emissions read from a materialised K x T matrix (legacy .Call boundary)
-template <int Z>
-__device__ __forceinline__ double emission_from_py(const double *__restrict__ py_t, int U, int lane, bool active,
-                                                   double (&B)[Z]) {
-  double py[Z];
-  double mx = -CUDART_INF;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    py[z] = active ? __ldg(py_t + lane + z * U) : -CUDART_INF;
-    mx = fmax(mx, py[z]);
-  }
-  float mf = warp_maxf(__double2float_rn(mx));
-  // a float-rounded shift can sit below the true max by one float ulp; harmless
-  double m = (mf == -CUDART_INF_F) ? 0.0 : (double)mf;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) B[z] = active ? exp(py[z] - m) : 0.0;
-  return m;
-}
-
-struct FbArgs {
-  const SnpRec *snp;          // [N]
-  const TxnRec *txn;          // [N]
-  const Chunk *chunks;        // [nChunks]
-  int nChunks;
-  int U;
-  int warm;                   // warm-up length (SNPs) for speculative chunk starts
-  int round;                  // 0 = first pass; >0 = verification / re-run pass
-  int beta_only;              // backward kernels: recursion + boundary vectors only (no alpha reads, posteriors, sums)
-  int final_pass;             // backward kernels: every chunk runs once from its own verified start vector
-  double rtol, atol;
-  ModelConsts M;
-  const unsigned char *het;   // [U]
-  const double *py;           // [K x N] materialised log emissions (legacy mode) or nullptr
-  double *alpha;              // [N][K] scaled forward variables
-  double *startv;             // [nChunks][K] boundary vector each chunk last started from
-  double *endv;               // [2][nChunks][K] boundary vector each chunk produced (double-buffered by round)
-  double *chunk_ll;           // [nChunks] log-likelihood piece of each chunk
-  unsigned int *rerun;        // [max_rounds] number of chunks (re)run in each round
-  // backward / posterior outputs
-  double *part;               // [nChunks][6][K] per-chunk statistic partial sums
-  double *rhoG0, *rhoZ0;      // [nChr][U], [nChr][Z]
-  double *rhoG, *rhoZ;        // optional [N][U], [N][Z]
-  double *loggamma;           // optional [N][K] (legacy mode)
-};
-
-template <int Z>
-__device__ __forceinline__ bool vec_mismatch(const double (&a)[Z], const double (&b)[Z], double rtol, double atol) {
-  bool bad = false;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) {
-    double hi = fmax(a[z], b[z]);
-    bad |= (fabs(a[z] - b[z]) > rtol * hi) && (hi > atol);
-    bad |= (a[z] != a[z]) || (b[z] != b[z]);
-  }
-  return __any_sync(0xffffffffu, bad);
-}
-
-// ------------------------------------------------------------------------------------------
-// Record streaming.  The recursion is a dependent chain, so every cycle of load latency inside
-// a step is paid 10^5 times per chromosome.  Each warp therefore stages its per-SNP records
-// (SnpRec 32 B + TxnRec 64 B) through a private shared-memory ring of two 16-step tiles: a
-// tile is fetched from HBM with coalesced 16-byte loads one-and-a-half tiles ahead of its use,
-// parked in registers, and dropped into the ring when the tile before it retires.  Steps then
-// read their records with broadcast shared-memory loads one step ahead of the recursion.
-// DIR = +1 walks t upwards (forward pass), -1 downwards (backward pass).
-// ------------------------------------------------------------------------------------------
-constexpr int kTile = 16;
-constexpr int kTileBytes = kTile * (32 + 64);          // 1536
-constexpr int kWarpSmem = 2 * kTileBytes;              // 3072 B per warp
-
-template <int DIR>
-struct RecStream {
-  const SnpRec *snp;
-  const TxnRec *txn;
-  char *sm;
-  int tbeg, lo, hi, lane;
-  uint4 r0, r1, r2;
-
-  __device__ __forceinline__ int gidx(int q) const { return min(max(tbeg + DIR * q, lo), hi); }
-  __device__ __forceinline__ void gload(int k) {
-    r0 = __ldg(reinterpret_cast<const uint4 *>(snp + gidx(kTile * k + (lane >> 1))) + (lane & 1));
-    r1 = __ldg(reinterpret_cast<const uint4 *>(txn + gidx(kTile * k + (lane >> 2))) + (lane & 3));
-    r2 = __ldg(reinterpret_cast<const uint4 *>(txn + gidx(kTile * k + 8 + (lane >> 2))) + (lane & 3));
-  }
-  __device__ __forceinline__ void sstore(int k) {
-    char *b = sm + (k & 1) * kTileBytes;
-    reinterpret_cast<uint4 *>(b)[lane] = r0;
-    reinterpret_cast<uint4 *>(b + kTile * 32)[lane] = r1;
-    reinterpret_cast<uint4 *>(b + kTile * 32)[32 + lane] = r2;
-  }
-  __device__ __forceinline__ void init(const SnpRec *s, const TxnRec *t, char *smem, int tbeg_, int lo_, int hi_, int lane_) {
-    snp = s; txn = t; sm = smem; tbeg = tbeg_; lo = lo_; hi = hi_; lane = lane_;
-    gload(0); sstore(0);
-    gload(1); sstore(1);
-    gload(2);
-    __syncwarp();
-  }
-  // call at the top of step q: when a new tile starts, retire the previous one
-  __device__ __forceinline__ void advance(int q) {
-    if ((q & (kTile - 1)) == 0 && q > 0) {
-      const int k = q / kTile;
-      __syncwarp();
-      sstore(k + 1);
-      gload(k + 2);
-      __syncwarp();
-    }
-  }
-  __device__ __forceinline__ void get(int q, SnpRec &s, TxnRec &t) const {
-    const char *b = sm + ((q / kTile) & 1) * kTileBytes;
-    const int i = q & (kTile - 1);
-    s = *reinterpret_cast<const SnpRec *>(b + 32 * i);
-    t = *reinterpret_cast<const TxnRec *>(b + kTile * 32 + 64 * i);
-  }
-};
-
-// one structured forward step: a <- (A_t^T applied to a) .* (B * 2^-e).
-// HET destinations differ only in their coefficients (select, no divergent branch):
-//   o = cW*W + cG*Wg + cZ*Wz[z] + cw*w[z]
-template <int Z>
-__device__ __forceinline__ void fwd_step(double (&a)[Z], const double (&B)[Z], const TxnRec &tr, bool het, int &e) {
-  const double irs = het ? tr.irh : tr.irn;
-  const double cW = het ? tr.cB : tr.k0, cG = het ? tr.k4 : tr.k2, cZ = het ? 0.0 : tr.k1, cw = het ? 0.0 : tr.k3;
-  double w[Z], Wz[Z];
-#pragma unroll
-  for (int z = 0; z < Z; ++z) { w[z] = a[z] * irs; Wz[z] = w[z]; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)      // Z interleaved butterflies: Z independent shuffles per stage
-#pragma unroll
-    for (int z = 0; z < Z; ++z) Wz[z] += __shfl_xor_sync(0xffffffffu, Wz[z], o);
-  double Wg = 0.0, W = 0.0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) { Wg += w[z]; W += Wz[z]; }
-  const double sc = pow2_rescale(W, e);
-  const double base = cW * W + cG * Wg;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) a[z] = (base + cZ * Wz[z] + cw * w[z]) * (B[z] * sc);
-}
-
-// one structured backward step: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two
-template <int Z>
-__device__ __forceinline__ void bwd_step(double (&b)[Z], const double (&B)[Z], const TxnRec &tr, bool het, bool active, int &e) {
-  const double cG = het ? tr.k4 : tr.k2, cw = het ? 0.0 : tr.k3;
-  double bb[Z], red[Z + 1];
-  double loc = 0.0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) { bb[z] = b[z] * B[z]; loc += bb[z]; red[z] = het ? 0.0 : bb[z]; }
-  red[Z] = het ? loc : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int z = 0; z <= Z; ++z) red[z] += __shfl_xor_sync(0xffffffffu, red[z], o);
-  const double H = red[Z];
-  double Wn = 0.0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) Wn += red[z];
-  const double sc = pow2_rescale(Wn + H, e);
-  const double irs = active ? (het ? tr.irh : tr.irn) * sc : 0.0;
-  const double base = tr.k0 * Wn + tr.cB * H + cG * loc;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) b[z] = (base + tr.k1 * red[z] + cw * bb[z]) * irs;
-}
-
-// ------------------------------------------------------------------------------------------
-// Forward pass over one chunk per warp.
-// reference recursion: src/fwd_backC_clonalCN.c:111-142 (log space, dense) -- here scaled linear
-// space with the structured O(K) step; log-likelihood pieces are exact for any scaling.
-// The loop body holds two independent instruction streams -- the recursion for SNP t and the
-// emission (exp) for SNP t+1 -- so that their latencies overlap.
-// ------------------------------------------------------------------------------------------
-template <int Z, bool FROM_PY>
-__global__ void __launch_bounds__(128) fwd_chunk_kernel(FbArgs A) {
-  __shared__ __align__(16) char smem_all[4 * kWarpSmem];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= A.nChunks) return;
-  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
-  const Chunk c = A.chunks[warp];
-  const int U = A.U, K = U * Z;
-  const bool active = lane < U;
-  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
-  double *endv_cur = A.endv + cur + (size_t)warp * K;
-  const double *endv_prv_self = A.endv + prv + (size_t)warp * K;
-  double *startv = A.startv + (size_t)warp * K;
-
-  double a[Z];
-  int tb;               // first SNP index processed
-  bool have_start;      // a[] already holds alpha~_{tb-1}
-  if (A.round > 0) {
-    if (c.t0 == c.cs) {   // chromosome-leading chunks start from pi: exact in round 0
-      if (active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-    double used[Z], want[Z];
-    const double *pe = A.endv + prv + (size_t)(warp - 1) * K;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      used[z] = active ? startv[lane + z * U] : 0.0;
-      want[z] = active ? pe[lane + z * U] : 0.0;
-    }
-    if (!vec_mismatch<Z>(used, want, A.rtol, A.atol)) {
-      if (active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-#pragma unroll
-    for (int z = 0; z < Z; ++z) a[z] = want[z];
-    tb = c.t0;
-    have_start = true;
-  } else {
-    tb = max(c.t0 - A.warm, c.cs);
-    have_start = false;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) a[z] = 0.0;
-  }
-  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
-
-  LaneModel<Z> L;
-  if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
-  const bool het = active && A.het[lane];
-
-  RecStream<1> rs;
-  rs.init(A.snp, A.txn, smem_all + (threadIdx.x >> 5) * kWarpSmem, tb, c.cs, c.ce - 1, lane);
-  const int n = c.t1 - tb;           // steps q = 0..n-1, t = tb + q
-  const int q0 = c.t0 - tb;          // first owned step
-
-  SnpRec rec;
-  TxnRec tr;
-  double B[Z];
-  double m;
-  rs.get(0, rec, tr);
-  if (FROM_PY) m = emission_from_py<Z>(A.py + (size_t)tb * K, U, lane, active, B);
-  else m = emission<Z>(L, rec, B);
-
-  double acc_m = 0.0;     // sum of emission shifts over the owned range
-  long long acc_e = 0;    // sum of power-of-two rescale exponents over the owned range
-  double s_start = 1.0;   // mass of the vector entering the owned range (1 for a chromosome-leading chunk)
-  int q = 0;
-  // ---- step q = 0 without a predecessor vector (chromosome start or speculative flat start) ----
-  if (!have_start) {
-    if (tb == c.cs) {
-#pragma unroll
-      for (int z = 0; z < Z; ++z) a[z] = (active ? A.M.pi[lane + z * U] : 0.0) * B[z];
-    } else {
-#pragma unroll
-      for (int z = 0; z < Z; ++z) a[z] = B[z];
-    }
-    if (q0 == 0) {        // only a chromosome-leading chunk owns its very first step
-      acc_m += m;
-      if (active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) A.alpha[(size_t)tb * K + lane + z * U] = a[z];
-    }
-    q = 1;
-    if (n > 1) {
-      rs.get(1, rec, tr);
-      if (FROM_PY) m = emission_from_py<Z>(A.py + (size_t)(tb + 1) * K, U, lane, active, B);
-      else m = emission<Z>(L, rec, B);
-    }
-  }
-  // ---- warm-up steps (not owned, nothing stored) ----
-  for (; q < q0; ++q) {
-    rs.advance(q);
-    SnpRec recn;
-    TxnRec trn;
-    rs.get(min(q + 1, n - 1), recn, trn);
-    double Bn[Z];
-    double mn;
-    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)min(tb + q + 1, c.t1 - 1) * K, U, lane, active, Bn);
-    else mn = emission<Z>(L, recn, Bn);
-    int e;
-    fwd_step<Z>(a, B, tr, het, e);
-    tr = trn; m = mn;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
-  }
-  // ---- entering the owned range: record / publish the boundary vector alpha~_{t0-1} ----
-  if (c.t0 != c.cs) {
-    double loc = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) loc += a[z];
-    s_start = warp_sum(loc);
-    if (!have_start) {
-      const double inv = 1.0 / s_start;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) a[z] *= inv;
-      s_start = 1.0;
-    }
-    if (active)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) startv[lane + z * U] = a[z];
-  }
-  // ---- owned steps ----
-  for (; q < n; ++q) {
-    rs.advance(q);
-    SnpRec recn;
-    TxnRec trn;
-    rs.get(min(q + 1, n - 1), recn, trn);
-    double Bn[Z];
-    double mn;
-    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)min(tb + q + 1, c.t1 - 1) * K, U, lane, active, Bn);
-    else mn = emission<Z>(L, recn, Bn);
-    int e;
-    fwd_step<Z>(a, B, tr, het, e);
-    acc_m += m;
-    acc_e += e;
-    if (active) {
-      double *dst = A.alpha + (size_t)(tb + q) * K + lane;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) dst[z * U] = a[z];
-    }
-    tr = trn; m = mn;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
-  }
-  // chunk end: boundary vector (normalised) + log-likelihood piece
-  double loc = 0.0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) loc += a[z];
-  const double s_end = warp_sum(loc);
-  const double inv = 1.0 / s_end;
-  if (active) {
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = a[z] * inv;
-  }
-  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
-  if (lane == 0) A.chunk_ll[warp] = ll;
-}
-
-// ------------------------------------------------------------------------------------------
-// Backward pass + posteriors + sufficient statistics over one chunk per warp.
-// reference: src/fwd_backC_clonalCN.c:148-192 (beta, gamma); R/hmmClonal.R:230-234 (exp, marginals);
-// R/paramEstimation.R:34-40 (a,b,c,d,e,g)
-// Iteration for SNP t (descending): beta~_t from beta~_{t+1} and B_{t+1} (carried), posterior at t,
-// and -- independent of both -- the emission B_t for the next iteration.
-// ------------------------------------------------------------------------------------------
-template <int Z, bool FROM_PY, bool WRITE_POST>
-__global__ void __launch_bounds__(128) bwd_chunk_kernel(FbArgs A) {
-  __shared__ __align__(16) char smem_all[4 * kWarpSmem];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= A.nChunks) return;
-  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
-  const Chunk c = A.chunks[warp];
-  const int U = A.U, K = U * Z;
-  const bool active = lane < U;
-  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
-  double *endv_cur = A.endv + cur + (size_t)warp * K;
-  const double *endv_prv_self = A.endv + prv + (size_t)warp * K;
-  double *startv = A.startv + (size_t)warp * K;
-
-  // b[] holds beta~_{tn}; tn == c.ce means "past the end" (beta_{ce-1} = 1)
-  double b[Z];
-  int tn;
-  bool from_boundary;   // b[] was read from the next chunk's published boundary vector
-  const bool beta_only = A.beta_only != 0;
-  if (A.final_pass && c.t1 != c.ce) {
-    // posterior pass after the boundaries are verified: start from my own (exact) boundary vector
-#pragma unroll
-    for (int z = 0; z < Z; ++z) b[z] = active ? startv[lane + z * U] : 0.0;
-    tn = c.t1;
-    from_boundary = true;
-  } else if (A.round > 0 && !A.final_pass) {
-    if (c.t1 == c.ce) {
-      if (active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-    double used[Z], want[Z];
-    const double *pe = A.endv + prv + (size_t)(warp + 1) * K;   // next chunk's beta~ at its first SNP
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      used[z] = active ? startv[lane + z * U] : 0.0;
-      want[z] = active ? pe[lane + z * U] : 0.0;
-    }
-    if (!vec_mismatch<Z>(used, want, A.rtol, A.atol)) {
-      if (active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-#pragma unroll
-    for (int z = 0; z < Z; ++z) b[z] = want[z];
-    tn = c.t1;
-    from_boundary = true;
-  } else {
-    tn = min(c.t1 + A.warm, c.ce);
-    from_boundary = false;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) b[z] = active ? 1.0 : 0.0;
-  }
-  if (lane == 0) atomicAdd(A.rerun + A.round, 1u);
-
-  LaneModel<Z> L;
-  if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
-  const bool het = active && A.het[lane];
-
-  // stream position q <-> SNP index t = (tn - 1) - q + 1 = tn - q : q = 0 is SNP tn (clamped when tn == ce)
-  RecStream<-1> rs;
-  rs.init(A.snp, A.txn, smem_all + (threadIdx.x >> 5) * kWarpSmem, tn, c.cs, c.ce - 1, lane);
-  SnpRec rec;          // record of SNP t+1 (emission input of the beta step)
-  TxnRec tr;           // transition between t and t+1
-  double B[Z];         // B_{t+1}
-  double mB = 0.0;     // its emission shift
-  rs.get(0, rec, tr);
-  if (tn < c.ce) {
-    if (FROM_PY) mB = emission_from_py<Z>(A.py + (size_t)tn * K, U, lane, active, B);
-    else mB = emission<Z>(L, rec, B);
-  } else {
-#pragma unroll
-    for (int z = 0; z < Z; ++z) B[z] = 0.0;
-  }
-
-  double st[6][Z];
-#pragma unroll
-  for (int qq = 0; qq < 6; ++qq)
-#pragma unroll
-    for (int z = 0; z < Z; ++z) st[qq][z] = 0.0;
-
-  int q = 1;           // step q produces beta~ at SNP t = tn - q
-  // ---- warm-up steps: t = tn-1 .. t1 ----
-  for (; tn - q >= c.t1; ++q) {
-    rs.advance(q);
-    SnpRec recn;
-    TxnRec trn;
-    rs.get(q, recn, trn);                 // record of SNP t (next iteration's emission input)
-    double Bn[Z];
-    double mn;
-    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)(tn - q) * K, U, lane, active, Bn);
-    else mn = emission<Z>(L, recn, Bn);
-    int e;
-    if (tn - q + 1 < c.ce) bwd_step<Z>(b, B, tr, het, active, e);
-    tr = trn; mB = mn;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
-  }
-  // ---- boundary: b[] is beta~_{t1}; normalise what the warm-up produced and publish it ----
-  if (c.t1 < c.ce) {
-    if (!from_boundary) {
-      double loc = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) loc += b[z];
-      const double inv = 1.0 / warp_sum(loc);
-#pragma unroll
-      for (int z = 0; z < Z; ++z) b[z] *= inv;
-    }
-    if (active)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) startv[lane + z * U] = b[z];
-  }
-  // ---- owned steps: t = t1-1 .. t0 ----
-  for (; tn - q >= c.t0; ++q) {
-    const int t = tn - q;
-    rs.advance(q);
-    SnpRec recn;
-    TxnRec trn;
-    rs.get(q, recn, trn);                 // record of SNP t: statistics now, emission input next iteration
-    double Bn[Z];
-    double mn;
-    if (FROM_PY) mn = emission_from_py<Z>(A.py + (size_t)t * K, U, lane, active, Bn);
-    else mn = emission<Z>(L, recn, Bn);
-    double al[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) al[z] = (active && !beta_only) ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
-    if (t + 1 < c.ce) {
-      int e;
-      bwd_step<Z>(b, B, tr, het, active, e);
-    }
-    mB = mn;
-    if (beta_only) {
-      tr = trn;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) B[z] = Bn[z];
-      continue;
-    }
-    // ---- posterior gamma_t ~ alpha~_t * beta~_t ----
-    double p[Z];
-    double loc = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) { p[z] = al[z] * b[z]; loc += p[z]; }
-    const double inv = 1.0 / warp_sum(loc);
-    double gsum = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) { p[z] *= inv; gsum += p[z]; }
-    if (!FROM_PY) {
-      const double l2 = recn.lr * recn.lr;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        st[0][z] += recn.x * p[z];
-        st[1][z] += recn.nx * p[z];
-        st[2][z] += recn.lr * p[z];
-        st[3][z] += recn.lb * p[z];
-        st[4][z] += p[z];
-        st[5][z] += l2 * p[z];
-      }
-    } else if (A.loggamma != nullptr && active) {
-#pragma unroll
-      for (int z = 0; z < Z; ++z) A.loggamma[(size_t)t * K + lane + z * U] = log(p[z]);
-    }
-    const bool first = (t == c.cs);
-    if (WRITE_POST || first) {
-      double rz[Z];
-#pragma unroll
-      for (int z = 0; z < Z; ++z) rz[z] = warp_sum(p[z]);
-      if (WRITE_POST && A.rhoG != nullptr) {
-        if (active) A.rhoG[(size_t)t * U + lane] = gsum;
-#pragma unroll
-        for (int z = 0; z < Z; ++z)
-          if (lane == z) A.rhoZ[(size_t)t * Z + z] = rz[z];
-      }
-      if (first && A.rhoG0 != nullptr) {
-        if (active) A.rhoG0[(size_t)c.chr * U + lane] = gsum;
-#pragma unroll
-        for (int z = 0; z < Z; ++z)
-          if (lane == z) A.rhoZ0[(size_t)c.chr * Z + z] = rz[z];
-      }
-    }
-    tr = trn;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) B[z] = Bn[z];
-  }
-  // boundary vector for the previous chunk: beta~ at this chunk's first SNP, normalised
-  {
-    double loc = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) loc += b[z];
-    const double s_end = warp_sum(loc);
-    const double inv = 1.0 / s_end;
-    double endn[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endn[z] = b[z] * inv;
-    if (active)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
-  }
-  if (!FROM_PY && active && !beta_only) {
-    double *dst = A.part + (size_t)warp * 6 * K;
-#pragma unroll
-    for (int qq = 0; qq < 6; ++qq)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Warp-specialised chunk kernels: one CTA per chunk.
-//
-// A lone warp running emission + recursion issues ~365 instructions per SNP at ~4 cycles each
-// (ncu: stall_wait dominates): the dependent chain, not the pipes, sets the pace.  When few
-// chunks are in flight (verification rounds >= 1, or the plain sequential mode) the SM is
-// otherwise idle, so the step is split by dependence class across the warps of a CTA:
-//   producers   evaluate emission tiles B = exp(py - m) (no dependence on the recursion) into a
-//               shared-memory ring, together with the tile's transition records;
-//   consumer    (warp 0) runs nothing but the structured recursion, ~100 instructions per SNP;
-//   posterior   (backward only, warp 1) turns beta~ tiles handed over by the consumer into
-//               posteriors and sufficient statistics, off the recursion's critical path.
-// Hand-off is by volatile shared-memory counters; every warp of the CTA is resident, so the
-// spins cannot deadlock.
-// ------------------------------------------------------------------------------------------
-template <int Z>
-struct WsCfg {
-  static constexpr int TS = (Z <= 5) ? 8 : 4;              // steps per tile
-  static constexpr int NS = 4;                              // emission ring slots
-  static constexpr int NSB = 3;                             // beta ring slots (backward)
-  static constexpr int SLOT_DOUBLES = TS * Z * 32 + TS + TS * 8;   // B, m, TxnRec
-  static constexpr int BETA_DOUBLES = TS * Z * 32;
-};
-template <int Z> __host__ __device__ constexpr size_t ws_fwd_smem() { return sizeof(double) * WsCfg<Z>::NS * WsCfg<Z>::SLOT_DOUBLES + 64; }
-template <int Z> __host__ __device__ constexpr size_t ws_bwd_smem() {
-  return sizeof(double) * (WsCfg<Z>::NS * WsCfg<Z>::SLOT_DOUBLES + WsCfg<Z>::NSB * WsCfg<Z>::BETA_DOUBLES) + 64;
-}
-
-struct WsFlags {            // lives at the end of the dynamic shared memory block
-  volatile int full[4];     // emission slot s holds tile (full[s] - 1)
-  volatile int consumed;    // emission tiles retired by the consumer
-  volatile int bfull[3];    // beta slot s holds tile (bfull[s] - 1)
-  volatile int bconsumed;   // beta tiles retired by the posterior warp
-};
-
-__device__ __forceinline__ void spin_until_ge(volatile int *p, int v) {
-  while (*p < v) { }
-  __threadfence_block();
-}
-__device__ __forceinline__ void spin_until_eq(volatile int *p, int v) {
-  while (*p != v) { }
-  __threadfence_block();
-}
-
-// producer: emission tiles k = first, first+stride, ... for stream positions q <-> SNP tbeg + DIR*q
-template <int Z, int DIR, bool FROM_PY>
-__device__ __forceinline__ void ws_produce(const FbArgs &A, const LaneModel<Z> &L, double *ring, WsFlags *F, int first,
-                                           int stride, int ntiles, int n, int tbeg, int lo, int hi, int lane, bool active) {
-  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, SD = WsCfg<Z>::SLOT_DOUBLES;
-  constexpr int SB = 4;
-  const int U = A.U, K = U * Z;
-  for (int k = first; k < ntiles; k += stride) {
-    double *slot = ring + (size_t)(k % NS) * SD;
-    double *Bs = slot, *ms = slot + TS * Z * 32;
-    uint4 *txs = reinterpret_cast<uint4 *>(slot + TS * Z * 32 + TS);
-    spin_until_ge(&F->consumed, k - NS + 1);
-    if (lane < TS * 4) {     // transition records of the tile, 16-byte pieces
-      const int t = min(max(tbeg + DIR * min(k * TS + (lane >> 2), n - 1), lo), hi);
-      txs[lane] = __ldg(reinterpret_cast<const uint4 *>(A.txn + t) + (lane & 3));
-    }
-#pragma unroll
-    for (int s0 = 0; s0 < TS; s0 += SB) {
-      double v[SB][Z];
-      float mf[SB];
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        const int t = min(max(tbeg + DIR * min(k * TS + s0 + i, n - 1), lo), hi);
-        double mx = -CUDART_INF;
-        if (FROM_PY) {
-          const double *row = A.py + (size_t)t * K;
-#pragma unroll
-          for (int z = 0; z < Z; ++z) {
-            v[i][z] = active ? __ldg(row + lane + z * U) : -CUDART_INF;
-            mx = fmax(mx, v[i][z]);
-          }
-        } else {
-          const SnpRec r = A.snp[t];
-#pragma unroll
-          for (int z = 0; z < Z; ++z) {
-            const double d = r.lr - L.muC[z];
-            const double e = (r.lb + (r.x * L.lmu[z] + r.nx * L.l1mu[z])) + (L.cN - d * d * L.i2v);
-            v[i][z] = active ? e : -CUDART_INF;
-            mx = fmax(mx, v[i][z]);
-          }
-        }
-        mf[i] = __double2float_rn(mx);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < SB; ++i) mf[i] = fmaxf(mf[i], __shfl_xor_sync(0xffffffffu, mf[i], o));
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        const double m = (mf[i] == -CUDART_INF_F) ? 0.0 : (double)mf[i];
-#pragma unroll
-        for (int z = 0; z < Z; ++z) Bs[((s0 + i) * Z + z) * 32 + lane] = active ? exp(v[i][z] - m) : 0.0;
-        if (lane == 0) ms[s0 + i] = m;
-      }
-    }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) F->full[k % NS] = k + 1;
-  }
-}
-
-template <int Z, bool FROM_PY>
-__global__ void __launch_bounds__(128) fwd_chunk_ws_kernel(FbArgs A) {
-  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, SD = WsCfg<Z>::SLOT_DOUBLES;
-  extern __shared__ __align__(16) double ws_smem[];
-  WsFlags *F = reinterpret_cast<WsFlags *>(ws_smem + NS * SD);
-  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
-  const Chunk c = A.chunks[chunk];
-  const int U = A.U, K = U * Z;
-  const bool active = lane < U;
-  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
-  double *endv_cur = A.endv + cur + (size_t)chunk * K;
-  const double *endv_prv_self = A.endv + prv + (size_t)chunk * K;
-  double *startv = A.startv + (size_t)chunk * K;
-
-  double a[Z];
-  int tb;
-  bool have_start;
-  if (A.round > 0) {
-    bool skip = (c.t0 == c.cs);
-    if (!skip) {
-      double used[Z], want[Z];
-      const double *pe = A.endv + prv + (size_t)(chunk - 1) * K;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        used[z] = active ? startv[lane + z * U] : 0.0;
-        want[z] = active ? pe[lane + z * U] : 0.0;
-        a[z] = want[z];
-      }
-      skip = !vec_mismatch<Z>(used, want, A.rtol, A.atol);
-    }
-    if (skip) {   // uniform over the CTA: every warp read the same values
-      if (warp == 0 && active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-    tb = c.t0;
-    have_start = true;
-  } else {
-    tb = max(c.t0 - A.warm, c.cs);
-    have_start = false;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) a[z] = 0.0;
-  }
-  if (threadIdx.x == 0) {
-    atomicAdd(A.rerun + A.round, 1u);
-    for (int i = 0; i < 4; ++i) F->full[i] = 0;
-    F->consumed = 0;
-  }
-  __syncthreads();   // nothing above wrote startv / endv; flags are initialised
-
-  const int n = c.t1 - tb, q0 = c.t0 - tb;
-  const int ntiles = (n + TS - 1) / TS;
-  if (warp > 0) {
-    LaneModel<Z> L;
-    if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
-    else { L.active = active; L.het = false; }
-    ws_produce<Z, 1, FROM_PY>(A, L, ws_smem, F, warp - 1, 3, ntiles, n, tb, c.cs, c.ce - 1, lane, active);
-    return;
-  }
-  // ---------------- consumer: the recursion alone ----------------
-  const bool het = active && A.het[lane];
-  double acc_m = 0.0;
-  long long acc_e = 0;
-  double s_start = 1.0;
-  double *arow = A.alpha + (size_t)tb * K + lane;
-  int q = 0;
-  for (int k = 0; k < ntiles; ++k) {
-    const double *slot = ws_smem + (size_t)(k % NS) * SD;
-    const double *ms = slot + TS * Z * 32;
-    const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
-    spin_until_eq(&F->full[k % NS], k + 1);
-    const int ns = min(TS, n - k * TS);
-    for (int s = 0; s < ns; ++s, ++q, arow += K) {
-      double B[Z];
-#pragma unroll
-      for (int z = 0; z < Z; ++z) B[z] = slot[(s * Z + z) * 32 + lane];
-      int e = 0;
-      if (q == 0 && !have_start) {
-        const bool at_start = (tb == c.cs);
-#pragma unroll
-        for (int z = 0; z < Z; ++z) a[z] = (at_start ? (active ? A.M.pi[lane + z * U] : 0.0) : 1.0) * B[z];
-      } else {
-        if (q == q0) {   // entering the owned range: record / publish alpha~_{t0-1}
-          double loc = 0.0;
-#pragma unroll
-          for (int z = 0; z < Z; ++z) loc += a[z];
-          s_start = warp_sum(loc);
-          if (!have_start) {
-            const double inv = 1.0 / s_start;
-#pragma unroll
-            for (int z = 0; z < Z; ++z) a[z] *= inv;
-            s_start = 1.0;
-          }
-          if (active)
-#pragma unroll
-            for (int z = 0; z < Z; ++z) startv[lane + z * U] = a[z];
-        }
-        fwd_step<Z>(a, B, txs[s], het, e);
-      }
-      if (q >= q0) {
-        acc_m += ms[s];
-        acc_e += e;
-        if (active)
-#pragma unroll
-          for (int z = 0; z < Z; ++z) arow[z * U] = a[z];
-      }
-    }
-    __syncwarp();
-    if (lane == 0) F->consumed = k + 1;
-  }
-  double loc = 0.0;
-#pragma unroll
-  for (int z = 0; z < Z; ++z) loc += a[z];
-  const double s_end = warp_sum(loc);
-  const double inv = 1.0 / s_end;
-  if (active)
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = a[z] * inv;
-  const double ll = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
-  if (lane == 0) A.chunk_ll[chunk] = ll;
-}
-
-// backward: warp 0 = beta recursion, warp 1 = posteriors + statistics, warps 2-3 = emission producers
-template <int Z, bool FROM_PY, bool WRITE_POST>
-__global__ void __launch_bounds__(128) bwd_chunk_ws_kernel(FbArgs A) {
-  constexpr int TS = WsCfg<Z>::TS, NS = WsCfg<Z>::NS, NSB = WsCfg<Z>::NSB, SD = WsCfg<Z>::SLOT_DOUBLES,
-                BD = WsCfg<Z>::BETA_DOUBLES;
-  extern __shared__ __align__(16) double ws_smem[];
-  double *bring = ws_smem + NS * SD;
-  WsFlags *F = reinterpret_cast<WsFlags *>(bring + NSB * BD);
-  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (A.round > 1 && !A.final_pass && A.rerun[A.round - 1] == 0) return;   // fixed point already reached (queued round)
-  const Chunk c = A.chunks[chunk];
-  const int U = A.U, K = U * Z;
-  const bool active = lane < U;
-  const size_t cur = (size_t)(A.round & 1) * A.nChunks * K, prv = (size_t)((A.round & 1) ^ 1) * A.nChunks * K;
-  double *endv_cur = A.endv + cur + (size_t)chunk * K;
-  const double *endv_prv_self = A.endv + prv + (size_t)chunk * K;
-  double *startv = A.startv + (size_t)chunk * K;
-
-  double b[Z];
-  int tn;
-  bool from_boundary;
-  if (A.round > 0) {
-    bool skip = (c.t1 == c.ce);
-    if (!skip) {
-      double used[Z], want[Z];
-      const double *pe = A.endv + prv + (size_t)(chunk + 1) * K;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        used[z] = active ? startv[lane + z * U] : 0.0;
-        want[z] = active ? pe[lane + z * U] : 0.0;
-        b[z] = want[z];
-      }
-      skip = !vec_mismatch<Z>(used, want, A.rtol, A.atol);
-    }
-    if (skip) {
-      if (warp == 0 && active)
-#pragma unroll
-        for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endv_prv_self[lane + z * U];
-      return;
-    }
-    tn = c.t1;
-    from_boundary = true;
-  } else {
-    tn = min(c.t1 + A.warm, c.ce);
-    from_boundary = false;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) b[z] = active ? 1.0 : 0.0;
-  }
-  if (threadIdx.x == 0) {
-    atomicAdd(A.rerun + A.round, 1u);
-    for (int i = 0; i < 4; ++i) F->full[i] = 0;
-    for (int i = 0; i < 3; ++i) F->bfull[i] = 0;
-    F->consumed = 0;
-    F->bconsumed = 0;
-  }
-  __syncthreads();
-
-  // step j = 0..n-1 produces beta~ at SNP t = tn - j - 1 from B at stream position j (SNP tn - j)
-  const int n = tn - c.t0, jb = tn - c.t1;
-  const int ntiles = (n + TS - 1) / TS;
-  if (warp >= 2) {
-    LaneModel<Z> L;
-    if (!FROM_PY) load_lane_model<Z>(L, A.M, U, lane, A.het);
-    else { L.active = active; L.het = false; }
-    ws_produce<Z, -1, FROM_PY>(A, L, ws_smem, F, warp - 2, 2, ntiles, n, tn, c.cs, c.ce - 1, lane, active);
-    return;
-  }
-  const bool beta_only = A.beta_only != 0;
-  if (warp == 1 && beta_only) return;
-  if (warp == 0) {
-    // ---------------- beta recursion ----------------
-    const bool het = active && A.het[lane];
-    int j = 0;
-    for (int k = 0; k < ntiles; ++k) {
-      const double *slot = ws_smem + (size_t)(k % NS) * SD;
-      const TxnRec *txs = reinterpret_cast<const TxnRec *>(slot + TS * Z * 32 + TS);
-      double *bslot = bring + (size_t)(k % NSB) * BD;
-      spin_until_eq(&F->full[k % NS], k + 1);
-      if (!beta_only) spin_until_ge(&F->bconsumed, k - NSB + 1);
-      const int ns = min(TS, n - k * TS);
-      for (int s = 0; s < ns; ++s, ++j) {
-        if (j == jb && c.t1 < c.ce) {   // b[] is beta~_{t1}: normalise what the warm-up produced, publish it
-          if (!from_boundary) {
-            double loc = 0.0;
-#pragma unroll
-            for (int z = 0; z < Z; ++z) loc += b[z];
-            const double inv = 1.0 / warp_sum(loc);
-#pragma unroll
-            for (int z = 0; z < Z; ++z) b[z] *= inv;
-          }
-          if (active)
-#pragma unroll
-            for (int z = 0; z < Z; ++z) startv[lane + z * U] = b[z];
-        }
-        if (tn - j < c.ce) {
-          double B[Z];
-#pragma unroll
-          for (int z = 0; z < Z; ++z) B[z] = slot[(s * Z + z) * 32 + lane];
-          int e;
-          bwd_step<Z>(b, B, txs[s], het, active, e);
-        }
-        if (!beta_only)
-#pragma unroll
-          for (int z = 0; z < Z; ++z) bslot[(s * Z + z) * 32 + lane] = b[z];
-      }
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) { F->consumed = k + 1; F->bfull[k % NSB] = k + 1; }
-    }
-    double loc = 0.0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) loc += b[z];
-    const double s_end = warp_sum(loc);
-    const double inv = 1.0 / s_end;
-    double endn[Z];
-#pragma unroll
-    for (int z = 0; z < Z; ++z) endn[z] = b[z] * inv;
-    if (active)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) endv_cur[lane + z * U] = endn[z];
-    return;
-  }
-  // ---------------- warp 1: posteriors + sufficient statistics ----------------
-  double st[6][Z];
-#pragma unroll
-  for (int qq = 0; qq < 6; ++qq)
-#pragma unroll
-    for (int z = 0; z < Z; ++z) st[qq][z] = 0.0;
-  for (int k = 0; k < ntiles; ++k) {
-    const double *bslot = bring + (size_t)(k % NSB) * BD;
-    const int ns = min(TS, n - k * TS);
-    // alpha rows and records of the tile's owned SNPs: independent loads, issued before the wait
-    double al[TS][Z];
-    SnpRec rec[TS];
-#pragma unroll
-    for (int s = 0; s < TS; ++s) {
-      const int t = min(max(tn - (k * TS + s) - 1, c.t0), c.t1 - 1);
-#pragma unroll
-      for (int z = 0; z < Z; ++z) al[s][z] = active ? A.alpha[(size_t)t * K + lane + z * U] : 0.0;
-      if (!FROM_PY) rec[s] = A.snp[t];
-    }
-    spin_until_eq(&F->bfull[k % NSB], k + 1);
-#pragma unroll
-    for (int s = 0; s < TS; ++s) {
-      const int t = tn - (k * TS + s) - 1;
-      if (s >= ns || t >= c.t1) continue;
-      double p[Z];
-      double loc = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) { p[z] = al[s][z] * bslot[(s * Z + z) * 32 + lane]; loc += p[z]; }
-      const double inv = 1.0 / warp_sum(loc);
-      double gsum = 0.0;
-#pragma unroll
-      for (int z = 0; z < Z; ++z) { p[z] *= inv; gsum += p[z]; }
-      if (!FROM_PY) {
-        const double l2 = rec[s].lr * rec[s].lr;
-#pragma unroll
-        for (int z = 0; z < Z; ++z) {
-          st[0][z] += rec[s].x * p[z];
-          st[1][z] += rec[s].nx * p[z];
-          st[2][z] += rec[s].lr * p[z];
-          st[3][z] += rec[s].lb * p[z];
-          st[4][z] += p[z];
-          st[5][z] += l2 * p[z];
-        }
-      } else if (A.loggamma != nullptr && active) {
-#pragma unroll
-        for (int z = 0; z < Z; ++z) A.loggamma[(size_t)t * K + lane + z * U] = log(p[z]);
-      }
-      const bool first = (t == c.cs);
-      if (WRITE_POST || first) {
-        double rz[Z];
-#pragma unroll
-        for (int z = 0; z < Z; ++z) rz[z] = warp_sum(p[z]);
-        if (WRITE_POST && A.rhoG != nullptr) {
-          if (active) A.rhoG[(size_t)t * U + lane] = gsum;
-#pragma unroll
-          for (int z = 0; z < Z; ++z)
-            if (lane == z) A.rhoZ[(size_t)t * Z + z] = rz[z];
-        }
-        if (first && A.rhoG0 != nullptr) {
-          if (active) A.rhoG0[(size_t)c.chr * U + lane] = gsum;
-#pragma unroll
-          for (int z = 0; z < Z; ++z)
-            if (lane == z) A.rhoZ0[(size_t)c.chr * Z + z] = rz[z];
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) F->bconsumed = k + 1;
-  }
-  if (!FROM_PY && active) {
-    double *dst = A.part + (size_t)chunk * 6 * K;
-#pragma unroll
-    for (int qq = 0; qq < 6; ++qq)
-#pragma unroll
-      for (int z = 0; z < Z; ++z) dst[qq * K + lane + z * U] = st[qq][z];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Deterministic reduction of the per-chunk partial sums and log-likelihood pieces.
-// Fixed two-level order (slices of chunks, then slices in order) => bitwise reproducible.
+// Deterministic reduction of the per-chunk partial sums and log-likelihood pieces, one launch.
+// Blocks [0, ceil(width/32)): 32 columns x 8 chunk slices per block, every thread adds its slice in chunk order,
+// thread (col, 0) adds the eight slice sums in order.  Last block: one thread per chromosome adds the chunk
+// log-likelihood pieces of its own chunk range.  Fixed order => bitwise reproducible.
 // out layout: [6*K stats | nChr loglik]
 // ------------------------------------------------------------------------------------------
-__global__ void reduce_slices_kernel(const double *__restrict__ part, int nChunks, int width, int slice,
-                                     double *__restrict__ tmp) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = blockIdx.y;
-  if (k >= width) return;
-  const int c0 = s * slice, c1 = min(c0 + slice, nChunks);
-  double acc = 0.0;
-  for (int c = c0; c < c1; ++c) acc += part[(size_t)c * width + k];
-  tmp[(size_t)s * width + k] = acc;
-}
-
-__global__ void reduce_final_kernel(const double *__restrict__ tmp, int nSlices, int width,
-                                    const double *__restrict__ chunk_ll, const Chunk *__restrict__ chunks,
-                                    int nChunks, int nChr, double *__restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < width) {
+__global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ part, int nChunks, int width,
+                                                     const double *__restrict__ chunk_ll, const int *__restrict__ chr_chunk0,
+                                                     int nChr, double *__restrict__ out) {
+  __shared__ double sm[8][33];
+  const int nColBlocks = (width + 31) / 32;
+  if ((int)blockIdx.x < nColBlocks) {
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + col;
+    const int per = (nChunks + 7) / 8;
+    const int c0 = sl * per, c1 = min(c0 + per, nChunks);
     double acc = 0.0;
-    for (int s = 0; s < nSlices; ++s) acc += tmp[(size_t)s * width + k];
-    out[k] = acc;
-  } else if (k < width + nChr) {
-    const int chr = k - width;
-    double acc = 0.0;
-    for (int c = 0; c < nChunks; ++c)
-      if (chunks[c].chr == chr) acc += chunk_ll[c];
-    out[k] = acc;
+    if (k < width)
+      for (int c = c0; c < c1; ++c) acc += part[(size_t)c * width + k];
+    sm[sl][col] = acc;
+    __syncthreads();
+    if (sl == 0 && k < width) {
+      double tot = sm[0][col];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) tot += sm[q][col];
+      out[k] = tot;
+    }
+  } else {
+    for (int chr = threadIdx.x; chr < nChr; chr += blockDim.x) {
+      double acc = 0.0;
+      for (int c = chr_chunk0[chr]; c < chr_chunk0[chr + 1]; ++c) acc += chunk_ll[c];
+      out[width + chr] = acc;
+    }
   }
 }
 
@@ -1083,15 +53,10 @@ __global__ void txn_coeff_kernel(const double *__restrict__ rhoG, const double *
   const double q = rZ + (double)(Z - 1) * nz;
   const double rs_non = rG * q + oG * ((double)(h * Z) * rZ + (double)(U - 1 - h) * q);
   const double rs_het = rG * (double)Z * rZ + oG * ((double)((h - 1) * Z) * rZ + (double)(U - h) * q);
+  const double k0 = oG * nz, k1 = oG * (rZ - nz), k2 = (rG - oG) * nz, k3 = (rG - oG) * (rZ - nz), cB = oG * rZ, k4 = (rG - oG) * rZ;
   TxnRec r;
-  r.k0 = oG * nz;
-  r.k1 = oG * (rZ - nz);
-  r.k2 = (rG - oG) * nz;
-  r.k3 = (rG - oG) * (rZ - nz);
-  r.cB = oG * rZ;
-  r.k4 = (rG - oG) * rZ;
-  r.irn = 1.0 / rs_non;
-  r.irh = (h > 0) ? 1.0 / rs_het : 0.0;
+  r.h[0] = TxnHalf{1.0 / rs_non, k0, k2, k1, k3, k0, cB, k1};
+  r.h[1] = TxnHalf{(h > 0) ? 1.0 / rs_het : 0.0, cB, k4, 0.0, 0.0, k0, cB, k1};
   out[t] = r;
 }
 
