@@ -506,3 +506,27 @@ def test_readme_flow_from_allele_count_file(tmp_path):
     assert text[0].startswith("Normal contamination estimate:\t") and text[-1].startswith("S_Dbw validity index (Both):\t")
     assert np.isfinite(fit["S_Dbw"]) and int(np.sum(segs["Length.snp."])) == data["posn"].size
     assert "Corrected_Copy_Number" in corr["segs"] and len(corr["cn"]["Corrected_Call"]) == data["posn"].size
+
+
+def test_estep_is_bitwise_reproducible_at_scale():
+    """The E-step is a fixed-order computation (no floating-point atomics): repeated calls with the same
+    parameters return bit-identical statistics, with and without the N-sized posterior outputs, on a grid large
+    enough that several CTAs share every SM.  Any difference is a race (this caught shared memory being reused
+    over live mbarrier words)."""
+    N, Z = 400000, 3
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=20261020)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=Z)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    sol = T.Solver(data, g, Z, 1e15, 1.0)
+    args = (0.45, sP["s_0"], 2.04, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    for chunk in (1024, 512):
+        sol.configure(chunk, 192, 1e-8)
+        ref = None
+        for r in range(6):
+            out = sol.estep(*args, posteriors=(r % 2 == 0))
+            key = np.concatenate([out["stats"][k].ravel() for k in "abcdeg"] + [out["loglik_chr"], out["rhoG0"].ravel()])
+            assert np.isfinite(key).all()
+            if ref is None:
+                ref = key
+            assert np.array_equal(ref, key), (chunk, r)
+    sol.close()

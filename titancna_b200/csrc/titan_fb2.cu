@@ -54,67 +54,176 @@ constexpr int kWPC = 4;  // warps per CTA: a warp's SM sub-partition is its inde
                          // would crowd a single scheduler.  Round kernels: four independent chunks; final pass: the
                          // four quarters of one chunk.
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void bulk_s2g(void *gdst, unsigned ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // Per-warp ring of per-SNP row tiles.  A tile is TS consecutive SNP rows of up to four arrays; lane 0 issues the
 // copies, every lane waits on the slot's mbarrier before reading.  `fin` adds the alpha rows and the records.
-// The cursor walks the stream one position at a time: position i of the stream is SNP first + dir*i, tiles are
-// fetched kNS - 1 ahead.
+// The cursor walks the stream one position at a time (position i of the stream is SNP first + dir*i); tiles are
+// fetched kNS - 1 ahead.  Everything the inner loop touches is a 32-bit shared-space address that is bumped, not
+// recomputed: brow / trow (/ arow / srow) address the rows of the current position.
 struct Ring {
-  char *base;
-  unsigned long long *bar;
-  const Fb2Args *A;
-  int TS, Kp, dir, k, s, ntiles;
-  long long first;
-  unsigned rowB, slot_bytes, offT, offA, offS;
-  bool fin;
+  unsigned sbase, sbar, slot_bytes, rowB, offT, offA, offS;
+  unsigned cur, brow, trow;    // current slot, its B row and its transition record
+  int rstep, tstep, sstep;     // signed byte steps of the B / alpha rows, the transition records and the SNP records
+  int TS, s, k, ntiles, slot_i;
+  unsigned phase;
+  const char *gB, *gT, *gA, *gS;             // global source of the next tile to fetch
+  long long dB, dT, dS;                      // signed byte strides between consecutive tiles
+  bool fin, up;
   int lane;
 
-  __device__ __forceinline__ void issue(int kk) {
-    const int sl = kk % kNS;
-    char *slot = base + (size_t)sl * slot_bytes;
-    // ascending streams: tile kk holds SNP rows first + kk*TS ..; descending ones: rows first - (kk+1)*TS + 1 .. first - kk*TS
-    const long long rowBT = dir > 0 ? first + (long long)kk * TS : first - (long long)(kk + 1) * TS + 1;
+  __device__ __forceinline__ void issue(int sl) {      // lane 0: fetch the next tile into slot sl
+    const unsigned slot = sbase + (unsigned)sl * slot_bytes, bar = sbar + 8u * (unsigned)sl;
     fence_async_smem();          // the slot was read through the generic proxy until the __syncwarp before this call
-    mbar_expect_tx(bar + sl, slot_bytes);
-    bulk_g2s(slot, A->Bm + rowBT * Kp, (unsigned)TS * rowB, bar + sl);
-    bulk_g2s(slot + offT, A->txn + rowBT, (unsigned)TS * (unsigned)sizeof(TxnRec), bar + sl);
-    if (fin) {                   // posteriors are formed one SNP below the emission row of the same stream position
-      bulk_g2s(slot + offA, A->alpha + (rowBT - 1) * Kp, (unsigned)TS * rowB, bar + sl);
-      bulk_g2s(slot + offS, A->snp + (rowBT - 1), (unsigned)TS * 32u, bar + sl);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot), "l"(gB),
+                 "r"((unsigned)TS * rowB), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot + offT), "l"(gT),
+                 "r"((unsigned)TS * (unsigned)sizeof(TxnRec)), "r"(bar)
+                 : "memory");
+    if (fin) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot + offA), "l"(gA),
+                   "r"((unsigned)TS * rowB), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot + offS), "l"(gS),
+                   "r"((unsigned)TS * 32u), "r"(bar)
+                   : "memory");
+      gA += dB;
+      gS += dS;
     }
+    gB += dB;
+    gT += dT;
   }
-  __device__ __forceinline__ void start(const Fb2Args &A_, char *smem, int TS_, bool fin_, int lane_, int dir_, long long first_,
+  __device__ __forceinline__ void wait_slot(int sl, unsigned ph) {
+    const unsigned bar = sbar + 8u * (unsigned)sl;
+    unsigned ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(ph)
+          : "memory");
+    } while (!ok);
+  }
+  __device__ __forceinline__ void enter_slot() {
+    cur = sbase + (unsigned)slot_i * slot_bytes;
+    brow = cur + (up ? 0u : (unsigned)(TS - 1) * rowB);
+    trow = cur + offT + (up ? 0u : (unsigned)(TS - 1) * (unsigned)sizeof(TxnRec));
+  }
+  __device__ __forceinline__ void start(const Fb2Args &A, char *smem, int TS_, bool fin_, int lane_, int dir, long long first,
                                         int npos) {
-    A = &A_; TS = TS_; Kp = A_.Kp; fin = fin_; lane = lane_; dir = dir_; first = first_;
-    rowB = (unsigned)Kp * 8u;
+    TS = TS_; fin = fin_; lane = lane_; up = dir > 0;
+    rowB = (unsigned)A.Kp * 8u;
     offT = (unsigned)TS * rowB;
     offA = offT + (unsigned)TS * (unsigned)sizeof(TxnRec);
     offS = offA + (fin ? (unsigned)TS * rowB : 0u);
     slot_bytes = offS + (fin ? (unsigned)TS * 32u : 0u);
-    base = smem;
-    bar = reinterpret_cast<unsigned long long *>(smem + (size_t)kNS * slot_bytes);
+    sbase = smem_u32(smem);
+    sbar = sbase + (unsigned)kNS * slot_bytes;
+    rstep = up ? (int)rowB : -(int)rowB;
+    tstep = up ? (int)sizeof(TxnRec) : -(int)sizeof(TxnRec);
+    sstep = up ? 32 : -32;
     ntiles = (npos + TS - 1) / TS;
-    k = 0;
-    s = 0;
+    // ascending streams: tile kk holds SNP rows first + kk*TS ..; descending ones: rows first - (kk+1)*TS + 1 .. first - kk*TS;
+    // posteriors are formed one SNP below the emission row of the same stream position
+    const long long row0 = up ? first : first - (long long)TS + 1;
+    gB = reinterpret_cast<const char *>(A.Bm + row0 * A.Kp);
+    gT = reinterpret_cast<const char *>(A.txn + row0);
+    gA = reinterpret_cast<const char *>(A.alpha + (row0 - 1) * A.Kp);
+    gS = reinterpret_cast<const char *>(A.snp + (row0 - 1));
+    const long long sgn = up ? 1 : -1;
+    dB = sgn * (long long)TS * rowB;
+    dT = sgn * (long long)TS * (long long)sizeof(TxnRec);
+    dS = sgn * (long long)TS * 32;
+    k = 0; s = 0; slot_i = 0; phase = 0u;
     if (lane == 0) {
-      for (int i = 0; i < kNS; ++i) mbar_init(bar + i, 1);
+      for (int i = 0; i < kNS; ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sbar + 8u * (unsigned)i), "r"(1) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       fence_async_smem();
       for (int i = 0; i < kNS && i < ntiles; ++i) issue(i);
     }
     __syncwarp();
-    if (ntiles > 0) mbar_wait(bar, 0u);
+    enter_slot();
+    if (ntiles > 0) wait_slot(0, 0u);
   }
-  // row of the current stream position inside its tile (tiles ascend in SNP index whatever the direction)
-  __device__ __forceinline__ int row() const { return dir > 0 ? s : TS - 1 - s; }
-  __device__ __forceinline__ const char *slot() const { return base + (size_t)(k % kNS) * slot_bytes; }
+  // before the ring's shared memory is used for anything else: an mbarrier word must be invalidated first
+  __device__ __forceinline__ void retire() {
+    __syncwarp();
+    if (lane == 0)
+      for (int i = 0; i < kNS; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sbar + 8u * (unsigned)i) : "memory");
+    __syncwarp();
+  }
+  __device__ __forceinline__ unsigned arow() const { return brow + offA; }                       // alpha row of this position (fin)
+  __device__ __forceinline__ unsigned srow() const { return cur + offS + (unsigned)(up ? s : TS - 1 - s) * 32u; }
   __device__ __forceinline__ void advance() {
+    brow += rstep;
+    trow += tstep;
     if (++s == TS) {
       __syncwarp();
-      if (lane == 0 && k + kNS < ntiles) issue(k + kNS);
+      if (lane == 0 && k + kNS < ntiles) issue(slot_i);
       ++k;
       s = 0;
-      if (k < ntiles) mbar_wait(bar + (k % kNS), (unsigned)((k / kNS) & 1));
+      if (++slot_i == kNS) { slot_i = 0; phase ^= 1u; }
+      enter_slot();
+      if (k < ntiles) wait_slot(slot_i, phase);
     }
+  }
+};
+
+// Alpha rows leave through shared memory: the owned steps of a forward chunk park their rows in one of two tile
+// buffers and lane 0 sends every full tile to HBM with one bulk store (cp.async.bulk.global.shared).
+struct AlphaOut {
+  unsigned sbuf[2], rowB, wr;   // wr: shared address of the next row to fill
+  char *gdst;
+  int TS, filled, which, lane;
+  __device__ __forceinline__ void start(unsigned smem_addr, int TS_, unsigned rowB_, double *dst, int lane_) {
+    TS = TS_; rowB = rowB_; lane = lane_;
+    sbuf[0] = smem_addr;
+    sbuf[1] = smem_addr + (unsigned)TS * rowB;
+    gdst = reinterpret_cast<char *>(dst);
+    filled = 0; which = 0; wr = sbuf[0];
+  }
+  __device__ __forceinline__ void flush() {
+    if (filled == 0) return;
+    fence_async_smem();                         // every lane: its rows were written through the generic proxy
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(gdst, sbuf[which], (unsigned)filled * rowB);
+      bulk_commit();
+      bulk_wait_read<1>();                      // the other buffer's store has finished reading it
+    }
+    __syncwarp();
+    gdst += (size_t)filled * rowB;
+    which ^= 1;
+    wr = sbuf[which];
+    filled = 0;
+  }
+  __device__ __forceinline__ void row_done() {
+    wr += rowB;
+    if (++filled == TS) flush();
+  }
+  __device__ __forceinline__ void finish() {
+    flush();
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the rows have landed, not just left shared memory
+    __syncwarp();
   }
 };
 
@@ -149,22 +258,23 @@ __device__ __forceinline__ void lane_info(LaneInfo<Z, GS> &L, int U, int lane, c
 
 // forward: a <- (A_t^T applied to a) .* (B * 2^-e);  the lane's coefficient half does the HET / non-HET selection
 template <int Z, int GS>
-__device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[GS][Z], const char *trow, const LaneInfo<Z, GS> &L,
+__device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[GS][Z], unsigned trow, const LaneInfo<Z, GS> &L,
                                           int &e) {
   double w[GS][Z], Wz[Z], Wg[GS];
   double2 c01[GS], c23[GS];
   double c4[GS];
 #pragma unroll
-  for (int z = 0; z < Z; ++z) Wz[z] = 0.0;
-#pragma unroll
   for (int s = 0; s < GS; ++s) {
-    const char *cf = trow + L.hoff[s];
-    c01[s] = *reinterpret_cast<const double2 *>(cf);          // irs, cW
-    c23[s] = *reinterpret_cast<const double2 *>(cf + 16);     // cG, cZ
-    c4[s] = *reinterpret_cast<const double *>(cf + 32);       // cw
-    Wg[s] = 0.0;
+    const unsigned cf = trow + L.hoff[s];
+    c01[s] = lds_v2f64(cf);          // irs, cW
+    c23[s] = lds_v2f64(cf + 16);     // cG, cZ
+    c4[s] = lds_f64(cf + 32);        // cw
 #pragma unroll
-    for (int z = 0; z < Z; ++z) { w[s][z] = a[s][z] * c01[s].x; Wz[z] += w[s][z]; Wg[s] += w[s][z]; }
+    for (int z = 0; z < Z; ++z) {
+      w[s][z] = a[s][z] * c01[s].x;
+      Wz[z] = (s == 0) ? w[s][z] : Wz[z] + w[s][z];
+      Wg[s] = (z == 0) ? w[s][z] : Wg[s] + w[s][z];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)      // Z interleaved butterflies: Z independent shuffles per stage
@@ -185,19 +295,17 @@ __device__ __forceinline__ void fwd_step2(double (&a)[GS][Z], const double (&B)[
 // backward: b <- A_{t+1} applied to (b .* B_{t+1}), rescaled by a power of two.  The table holds at most one
 // diploid-HET genotype, so the HET mass is a broadcast from its lane instead of a butterfly.
 template <int Z, int GS>
-__device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[GS][Z], const char *trow, const LaneInfo<Z, GS> &L,
+__device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[GS][Z], unsigned trow, const LaneInfo<Z, GS> &L,
                                           int &e) {
   double bb[GS][Z], loc[GS], red[Z];
 #pragma unroll
-  for (int z = 0; z < Z; ++z) red[z] = 0.0;
-#pragma unroll
   for (int s = 0; s < GS; ++s) {
-    loc[s] = 0.0;
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       bb[s][z] = b[s][z] * B[s][z];
-      loc[s] += bb[s][z];
-      red[z] += L.het[s] ? 0.0 : bb[s][z];
+      loc[s] = (z == 0) ? bb[s][z] : loc[s] + bb[s][z];
+      const double nh = L.het[s] ? 0.0 : bb[s][z];
+      red[z] = (s == 0) ? nh : red[z] + nh;
     }
   }
   double H = 0.0;
@@ -217,11 +325,13 @@ __device__ __forceinline__ void bwd_step2(double (&b)[GS][Z], const double (&B)[
   const double sc = pow2_rescale(Wn + H, e);
 #pragma unroll
   for (int s = 0; s < GS; ++s) {
-    const TxnHalf c = *reinterpret_cast<const TxnHalf *>(trow + L.hoff[s]);
-    const double irs = L.act[s] ? c.irs * sc : 0.0;
-    const double base = c.k0 * Wn + c.cB * H + c.cG * loc[s];
+    const unsigned cf = trow + L.hoff[s];
+    const double2 c01 = lds_v2f64(cf), c23 = lds_v2f64(cf + 16), c45 = lds_v2f64(cf + 32), c67 = lds_v2f64(cf + 48);
+    // TxnHalf: irs, cW | cG, cZ | cw, k0 | cB, k1
+    const double irs = L.act[s] ? c01.x * sc : 0.0;
+    const double base = c45.y * Wn + c67.x * H + c23.x * loc[s];
 #pragma unroll
-    for (int z = 0; z < Z; ++z) b[s][z] = (base + c.k1 * red[z] + c.cw * bb[s][z]) * irs;
+    for (int z = 0; z < Z; ++z) b[s][z] = (base + c67.y * red[z] + c45.x * bb[s][z]) * irs;
   }
 }
 
@@ -231,6 +341,23 @@ __device__ __forceinline__ void load_row(double (&v)[GS][Z], const void *row, co
   for (int s = 0; s < GS; ++s)
 #pragma unroll
     for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? *reinterpret_cast<const double *>(static_cast<const char *>(row) + L.off[s][z]) : 0.0;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void load_row_s(double (&v)[GS][Z], unsigned srow, const LaneInfo<Z, GS> &L) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? lds_f64(srow + L.off[s][z]) : 0.0;
+}
+
+template <int Z, int GS>
+__device__ __forceinline__ void store_row_s(unsigned srow, const double (&v)[GS][Z], const LaneInfo<Z, GS> &L) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+    if (L.act[s])
+#pragma unroll
+      for (int z = 0; z < Z; ++z) sts_f64(srow + L.off[s][z], v[s][z]);
 }
 
 template <int Z, int GS>
@@ -301,22 +428,19 @@ __device__ __forceinline__ void copy_vec(double *dst, const double *src, const L
   store_row<Z, GS>(dst, v, L);
 }
 
-// one forward step at the cursor's position; OWNED steps store alpha~ and account for the log-likelihood
+// one forward step at the cursor's position; OWNED steps park alpha~ for the bulk store and account for the log-likelihood
 template <int Z, int GS, bool OWNED>
-__device__ __forceinline__ void fwd_one(double (&a)[GS][Z], Ring &ring, const LaneInfo<Z, GS> &L, int K, double &acc_m, int &acc_e,
-                                        char *&arow) {
-  const char *slot = ring.slot();
-  const int r = ring.row();
-  const char *brow = slot + (size_t)r * ring.rowB;
+__device__ __forceinline__ void fwd_one(double (&a)[GS][Z], Ring &ring, const LaneInfo<Z, GS> &L, unsigned mOff, double &acc_m,
+                                        int &acc_e, AlphaOut &out) {
   double B[GS][Z];
-  load_row<Z, GS>(B, brow, L);
+  load_row_s<Z, GS>(B, ring.brow, L);
   int e;
-  fwd_step2<Z, GS>(a, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+  fwd_step2<Z, GS>(a, B, ring.trow, L, e);
   if (OWNED) {
-    acc_m += reinterpret_cast<const double *>(brow)[K];
+    acc_m += lds_f64(ring.brow + mOff);
     acc_e += e;
-    store_row<Z, GS>(arow, a, L);
-    arow += ring.rowB;
+    store_row_s<Z, GS>(out.wr, a, L);
+    out.row_done();
   }
   ring.advance();
 }
@@ -361,17 +485,18 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
   const int q0 = ch.t0 - tb;
   Ring ring;
   ring.start(A, smem, TS, false, lane, +1, tb, n_own + (has_ext ? 1 : 0));
+  AlphaOut out;
+  out.start(ring.sbar + 8u * kNS + 8u, TS, ring.rowB, A.alpha + (size_t)ch.t0 * A.Kp, lane);
+  const unsigned mOff = 8u * (unsigned)K;
 
   double acc_m = 0.0;        // sum of emission shifts over the owned range
   int acc_e = 0;             // sum of power-of-two rescale exponents over the owned range
   double s_start = 1.0;      // mass of the vector entering the owned range
-  char *arow = reinterpret_cast<char *>(A.alpha + (size_t)ch.t0 * A.Kp);
   int q = 0;
   if (!have_start) {
     // stream position 0 has no predecessor vector: chromosome start (pi) or a flat speculative start
-    const char *brow = ring.slot() + (size_t)ring.row() * ring.rowB;
     double B[GS][Z];
-    load_row<Z, GS>(B, brow, L);
+    load_row_s<Z, GS>(B, ring.brow, L);
     if (tb == ch.cs) {
       load_row<Z, GS>(a, A.pi, L);
 #pragma unroll
@@ -385,37 +510,36 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
         for (int z = 0; z < Z; ++z) a[g][z] = B[g][z];
     }
     if (q0 == 0) {           // only a chromosome-leading chunk owns its very first position
-      acc_m += reinterpret_cast<const double *>(brow)[K];
-      store_row<Z, GS>(arow, a, L);
-      arow += ring.rowB;
+      acc_m += lds_f64(ring.brow + mOff);
+      store_row_s<Z, GS>(out.wr, a, L);
+      out.row_done();
     }
     ring.advance();
     q = 1;
-    for (; q < q0; ++q) fwd_one<Z, GS, false>(a, ring, L, K, acc_m, acc_e, arow);      // warm-up: nothing stored
+    for (; q < q0; ++q) fwd_one<Z, GS, false>(a, ring, L, mOff, acc_m, acc_e, out);      // warm-up: nothing stored
   }
   if (ch.t0 != ch.cs) {      // entering the owned range: record / publish alpha~_{t0-1}
     s_start = vec_sum<Z, GS>(a);
     if (!have_start) { scale_vec<Z, GS>(a, 1.0 / s_start); s_start = 1.0; }
     store_row<Z, GS>(startv, a, L);
   }
-  for (; q < n_own; ++q) fwd_one<Z, GS, true>(a, ring, L, K, acc_m, acc_e, arow);
+  for (; q < n_own; ++q) fwd_one<Z, GS, true>(a, ring, L, mOff, acc_m, acc_e, out);
+  out.finish();
   const double s_end = vec_sum<Z, GS>(a);
   store_row<Z, GS>(A.endF + cur + (size_t)c * K, a, L, 1.0 / s_end);
   if (lane == 0) A.chunk_ll[c] = (log(s_end) - log(s_start)) + acc_m + (double)acc_e * 0.6931471805599453094;
   if (has_ext) {
-    fwd_one<Z, GS, false>(a, ring, L, K, acc_m, acc_e, arow);
+    fwd_one<Z, GS, false>(a, ring, L, mOff, acc_m, acc_e, out);
     store_row<Z, GS>(A.extF + cur + (size_t)c * K, a, L, 1.0 / vec_sum<Z, GS>(a));
   }
 }
 
 template <int Z, int GS>
 __device__ __forceinline__ void bwd_one(double (&b)[GS][Z], Ring &ring, const LaneInfo<Z, GS> &L) {
-  const char *slot = ring.slot();
-  const int r = ring.row();
   double B[GS][Z];
-  load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
+  load_row_s<Z, GS>(B, ring.brow, L);
   int e;
-  bwd_step2<Z, GS>(b, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+  bwd_step2<Z, GS>(b, B, ring.trow, L, e);
   ring.advance();
 }
 
@@ -493,7 +617,7 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
 
 // one launch per round: warps [0, nChunks) run forward chunks, [nChunks, 2 nChunks) backward chunks
 template <int Z, int GS>
-__global__ void __launch_bounds__(32 * kWPC) fb2_round_kernel(Fb2Args A, int TS, int ring_stride) {
+__global__ void __launch_bounds__(32 * kWPC, 3) fb2_round_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem[];
   if (A.use_solved) {
     if (A.round > 0 && A.rerun[A.round] == 0) return;        // probe mode: this cycle's boundary test found nothing to re-run
@@ -617,13 +741,11 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
   Ring ring;
   ring.start(A, smem, TS, false, lane, backward ? -1 : +1, backward ? ch.t1 : ch.t0, n);
   for (int q = 0; q < n; ++q) {
-    const char *slot = ring.slot();
-    const int r = ring.row();
     double B[GS][Z];
-    load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
+    load_row_s<Z, GS>(B, ring.brow, L);
     int e;
-    if (backward) bwd_step2<Z, GS>(v, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
-    else fwd_step2<Z, GS>(v, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+    if (backward) bwd_step2<Z, GS>(v, B, ring.trow, L, e);
+    else fwd_step2<Z, GS>(v, B, ring.trow, L, e);
     E += e;
     ring.advance();
   }
@@ -633,7 +755,7 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
 
 // warp id -> (direction, chunk, probe); clean chunks cost one boundary test
 template <int Z, int GS>
-__global__ void __launch_bounds__(32 * kWPC) fb2_probe_kernel(Fb2Args A, int TS, int ring_stride) {
+__global__ void __launch_bounds__(32 * kWPC, 3) fb2_probe_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem[];
   if (A.round > 1 && A.rerun[A.round - 1] == 0) return;      // the previous test already found every boundary clean
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -741,7 +863,7 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
 // reference: src/fwd_backC_clonalCN.c:148-192; R/hmmClonal.R:230-234; R/paramEstimation.R:34-40
 // ------------------------------------------------------------------------------------------
 template <int Z, int GS, bool WRITE_POST, bool FROM_PY>
-__global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS, int ring_stride) {
+__global__ void __launch_bounds__(32 * kWPC, 3) fb2_final_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
   const Chunk ch = A.chunks[c];
@@ -770,17 +892,15 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
     Ring ring;
     ring.start(A, fb2_smem_all + (size_t)warp * ring_stride, TS, true, lane, -1, tn, n);
     for (int j = 0; j < n; ++j) {
-      const char *slot = ring.slot();
-      const int r = ring.row();
       const int t = tn - j - 1;                 // the SNP whose posterior this step forms
       if (tn - j < ch.ce) {
         double B[GS][Z];
-        load_row<Z, GS>(B, slot + (size_t)r * ring.rowB, L);
+        load_row_s<Z, GS>(B, ring.brow, L);
         int e;
-        bwd_step2<Z, GS>(b, B, slot + ring.offT + sizeof(TxnRec) * r, L, e);
+        bwd_step2<Z, GS>(b, B, ring.trow, L, e);
       }
       double p[GS][Z];
-      load_row<Z, GS>(p, slot + ring.offA + (size_t)r * ring.rowB, L);
+      load_row_s<Z, GS>(p, ring.arow(), L);
       double loc = 0.0;
 #pragma unroll
       for (int g = 0; g < GS; ++g)
@@ -789,7 +909,10 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
       const double inv = 1.0 / warp_sum(loc);
       scale_vec<Z, GS>(p, inv);
       if (!FROM_PY) {
-        const SnpRec rec = *reinterpret_cast<const SnpRec *>(slot + ring.offS + 32 * r);
+        const unsigned sr = ring.srow();
+        const double2 r01 = lds_v2f64(sr), r23 = lds_v2f64(sr + 16);
+        SnpRec rec;
+        rec.x = r01.x; rec.nx = r01.y; rec.lr = r23.x; rec.lb = r23.y;
         const double l2 = rec.lr * rec.lr;
 #pragma unroll
         for (int g = 0; g < GS; ++g)
@@ -844,11 +967,12 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_final_kernel(Fb2Args A, int TS,
       }
       ring.advance();
     }
+    ring.retire();
   }
   if (!FROM_PY) {
     // combine the four quarters in a fixed order: quarter sums to shared memory, warp 0 adds them up
-    __syncthreads();                              // every ring of the CTA has been drained
-    double *sm = reinterpret_cast<double *>(fb2_smem_all);
+    __syncthreads();                              // every ring of the CTA has been drained and its mbarriers invalidated
+    double *sm = reinterpret_cast<double *>(fb2_smem_all + (size_t)kWPC * ring_stride);
     double *mine = sm + (size_t)warp * 6 * K;
 #pragma unroll
     for (int qq = 0; qq < 6; ++qq) store_row<Z, GS>(mine + qq * K, st[qq], L);
@@ -949,16 +1073,19 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
 // ------------------------------------------------------------------------------------------
 bool fb2_supported(int U, int Z) { return U >= 1 && U <= 64 && Z >= 1 && Z <= 8; }
 
+// a warp's shared memory: kNS input slots, the mbarriers, and (round kernels) two alpha tiles on their way out
 static size_t ring_bytes(int TS, int Kp, bool fin) {
   size_t slot = (size_t)TS * Kp * 8 + (size_t)TS * sizeof(TxnRec);
   if (fin) slot += (size_t)TS * Kp * 8 + (size_t)TS * 32;
-  return ((kNS * slot + kNS * 8 + 127) / 128) * 128;
+  size_t bytes = kNS * slot + kNS * 8 + 8;
+  if (!fin) bytes += 2 * (size_t)TS * Kp * 8;
+  return ((bytes + 127) / 128) * 128;
 }
 // Steps per tile: the largest power of two that keeps a warp's ring near 10 KB, so that six 4-warp CTAs fit an SM
 // and every chunk of a 1 M-SNP genome is resident in a single wave.
 static int tile_steps(int Kp, bool fin) {
   for (int ts = 8; ts > 1; ts >>= 1)
-    if (ring_bytes(ts, Kp, fin) <= 10240) return ts;
+    if (ring_bytes(ts, Kp, fin) <= (fin ? 10240 : 14336)) return ts;
   return 1;
 }
 
@@ -1035,7 +1162,7 @@ cudaError_t fb2_launch_final(const Fb2Args &A, int Z, bool write_post, bool from
   const int GS = A.U > 32 ? 2 : 1;
   const int TS = tile_steps(A.Kp, true);
   const size_t ring = ring_bytes(TS, A.Kp, true);
-  const size_t smem = std::max(kWPC * ring, (size_t)kWPC * 6 * A.K * sizeof(double));     // rings, then the quarter sums
+  const size_t smem = kWPC * ring + (size_t)kWPC * 6 * A.K * sizeof(double);     // rings, then the quarter sums behind them
   const unsigned blocks = (unsigned)A.nChunks;
   cudaError_t e = cudaSuccess;
   if (from_py) {
