@@ -15,7 +15,7 @@
  *                                in R around the .Call (R/hmmClonal.R:141-171,191-234,261-291,449-484;
  *                                R/paramEstimation.R:27-44,75-283,533-547)
  * The R-side glue that binds these (same .Call names/arity as src/register.c:8-13) is
- * titancna_b200/csrc/r_glue.c; see INTEGRATION.md.
+ * titancna_b200/csrc/r_glue.c (reference-compatible routines) + r_glue_fused.c (solver routines); see INTEGRATION.md.
  */
 #ifndef TITANCNA_B200_H
 #define TITANCNA_B200_H
@@ -97,6 +97,9 @@ typedef struct titan_data_desc {
  * partitions chromosomes into position chunks and allocates all device scratch. */
 int titan_solver_create(const titan_data_desc *desc, titan_solver **out);
 void titan_solver_destroy(titan_solver *s);
+
+/* Shape of the data set a solver holds (any pointer may be NULL). */
+int titan_solver_shape(const titan_solver *s, int64_t *N, int32_t *nChr, int32_t *U, int32_t *Z);
 
 /* Tuning knobs (defaults in DESIGN.md).  chunk_len <= 0: one chunk per chromosome (plain
  * sequential recursion).  Otherwise chromosomes are cut into chunks of chunk_len SNPs that run
@@ -210,6 +213,33 @@ int titan_solver_timing(const titan_solver *s, titan_timing *t);
  * creates one solver per solution; cudaMalloc/cudaFree of such blocks cost more than an E-step).  This
  * returns the cached memory to the driver.  No counterpart in the reference (R frees through its GC). */
 int titan_release_cached_memory(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. One solution over several GPUs: chromosomes sharded across ranks (one process per GPU), ONE
+ *    all-reduce(sum, fp64) of [a,b,c,d,e,g | loglik per chromosome | rhoG, rhoZ at chrPos_0] per E-step
+ *    on the device, M-step replicated on every rank.  Replaces the sum over the reference's
+ *    foreach(c = 1:numChrs) %dopar% workers (R/hmmClonal.R:203-234) when the workers are GPUs.
+ *    NCCL is bound at run time (libnccl.so.2); without it these calls fail with TITAN_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------- */
+#define TITAN_COMM_ID_BYTES 128
+typedef struct titan_comm titan_comm;
+/* rank 0 draws an id and ships the 128 bytes to the other ranks by any means the host has
+ * (R: parallel / Rmpi / a file; Python: torch.distributed.broadcast_object_list) */
+int titan_comm_unique_id(char *id_out /* [TITAN_COMM_ID_BYTES] */);
+/* collective over all `world` ranks, on the calling thread's current device (titan_set_device) */
+int titan_comm_create(const char *id, int rank, int world, titan_comm **out);
+void titan_comm_destroy(titan_comm *c);
+int titan_comm_info(const titan_comm *c, int *rank, int *world, int *nccl_version);
+/* The solver holds chromosomes chr_global[0..nChr) (ascending) of a data set with nChr_total chromosomes.
+ * From here on titan_estep / titan_em_run return whole-genome quantities on every rank: stats summed
+ * over ranks, loglik_chr[nChr_total], rhoG0[U x nChr_total], rhoZ0[Z x nChr_total]; the N-sized outputs
+ * (rhoG, rhoZ, Viterbi path) stay per shard.  comm == NULL detaches. */
+int titan_solver_set_comm(titan_solver *s, titan_comm *comm, int nChr_total, const int32_t *chr_global);
+
+/* FP64 roofline denominator, measured: DFMA throughput (TFLOP/s, 2 flop per DFMA) of the current device with every
+ * SM busy, best of five launches; ms_out (optional) = duration of that launch.  SURVEY.md 8(d) asks for it because
+ * MEASURED_PEAKS.json has no fp64 figure.  No counterpart in the reference. */
+int titan_measure_fp64_peak(double *tflops_out, double *ms_out);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ import ctypes as C
 import os
 import numpy as np
 
-INTSXP, REALSXP, STRSXP, VECSXP = 13, 14, 16, 19
+INTSXP, REALSXP, STRSXP, VECSXP, EXTPTRSXP = 13, 14, 16, 19, 22
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libtitanref.so")
@@ -60,6 +60,12 @@ class ShimLibrary:
         L.shim_lookup.restype = C.c_void_p
         L.shim_lookup.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
         L.shim_free_all.restype = None
+        if hasattr(L, "shim_calln"):      # glue builds carry the generic trampoline + external pointers
+            L.shim_calln.restype = SEXP
+            L.shim_calln.argtypes = [C.c_void_p, C.c_int, C.POINTER(SEXP)]
+            L.shim_named_list.restype = SEXP
+            L.shim_named_list.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(SEXP)]
+            L.shim_run_finalizers.restype = C.c_int
         L.R_init_TitanCNA.restype = None
         L.R_init_TitanCNA.argtypes = [C.c_void_p]
         L.R_init_TitanCNA(None)  # library.dynam -> R_init_<pkg>
@@ -78,9 +84,51 @@ class ShimLibrary:
             raise KeyError(f"{name} is not a registered .Call routine of {self.path}")
         return fn, n.value
 
-    def registered(self):
+    # -- generic .Call (any registered routine; arguments are SEXPs built by _real / named_list) ----
+    def call(self, name, *args):
+        fn, nargs = self.routine(name)
+        if nargs != len(args):
+            raise TypeError(f".Call({name!r}) takes {nargs} arguments, got {len(args)}")
+        arr = (SEXP * len(args))(*args)
+        out = self.lib.shim_calln(fn, len(args), arr)
+        if not out:
+            msg = self.lib.shim_last_error().decode(errors="replace")
+            self.lib.shim_free_all()
+            raise RError(msg)
+        return out
+
+    def named_list(self, items, keep):
+        """dict name -> numeric vector/scalar  ->  VECSXP with a names attribute"""
+        names = (C.c_char_p * len(items))(*[k.encode() for k in items])
+        elts = (SEXP * len(items))(*[self._real(np.atleast_1d(v), keep) for v in items.values()])
+        keep.append((names, elts))
+        return self.lib.shim_named_list(len(items), names, elts)
+
+    @staticmethod
+    def list_to_dict(out):
+        """named VECSXP of REALSXPs -> dict of numpy arrays (matrices in R's column-major shape)"""
+        o = out.contents
+        assert o.type == VECSXP
+        elts = C.cast(o.data, C.POINTER(SEXP))
+        names = C.cast(o.names.contents.data, C.POINTER(SEXP))
+        res = {}
+        for i in range(o.length):
+            nm = C.cast(names[i].contents.data, C.c_char_p).value.decode()
+            e = elts[i].contents
+            a = np.ctypeslib.as_array(C.cast(e.data, C.POINTER(C.c_double)), shape=(e.length,)).copy()
+            if e.dim:
+                d = C.cast(e.dim.contents.data, C.POINTER(C.c_int))
+                a = a.reshape((int(d[0]), int(d[1])), order="F")
+            res[nm] = a
+        return res
+
+    def gc(self):
+        """run the finalizers of every external pointer made so far (R's garbage collection of dropped solvers)"""
+        return self.lib.shim_run_finalizers()
+
+    def registered(self, names=("getPositionOverlapC", "fwd_backC_clonalCN", "viterbiC_clonalCN")):
         out = {}
-        for nm in ("getPositionOverlapC", "fwd_backC_clonalCN", "viterbiC_clonalCN"):
+        for nm in names:
             try:
                 out[nm] = self.routine(nm)[1]
             except KeyError:

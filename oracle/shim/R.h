@@ -1,5 +1,5 @@
 /* Minimal stand-in for the R C API, used ONLY to compile the reference's own
- * src/*.c (and this repo's R glue) in a container that has no R installation.
+ * src/ C files (and this repo's R glue) in a container that has no R installation.
  * TEST INFRASTRUCTURE: nothing in the product path includes this header.
  *
  * It models an SEXP as a small tagged heap record.  Only the entry points the
@@ -18,6 +18,11 @@ extern "C" {
 #define STRSXP  16
 #define VECSXP  19
 #define CHARSXP  9
+#define EXTPTRSXP 22
+#define LGLSXP  10
+#define TRUE  1
+#define FALSE 0
+typedef int Rboolean;
 
 typedef struct shim_sexp {
   int type;                 /* INTSXP / REALSXP / STRSXP / VECSXP / CHARSXP */
@@ -37,6 +42,19 @@ SEXP shim_alloc_matrix(int type, int nr, int nc);
 SEXP shim_mkchar(const char *s);
 void shim_error(const char *fmt, ...) __attribute__((noreturn));
 int  R_registerRoutines(DllInfo *, const void *, const R_CallMethodDef *, const void *, const void *);
+
+/* external pointers + finalizers (used by the fused glue): the shim keeps a registry and runs the finalizers when
+ * the test harness asks for a "garbage collection" (shim_run_finalizers) */
+typedef void (*R_CFinalizer_t)(struct shim_sexp *);
+struct shim_sexp *R_MakeExternalPtr(void *p, struct shim_sexp *tag, struct shim_sexp *prot);
+void *R_ExternalPtrAddr(struct shim_sexp *s);
+void R_ClearExternalPtr(struct shim_sexp *s);
+void R_RegisterCFinalizerEx(struct shim_sexp *s, R_CFinalizer_t fun, Rboolean onexit);
+int shim_run_finalizers(void);
+double asReal(struct shim_sexp *x);
+int asInteger(struct shim_sexp *x);
+char *R_alloc(size_t n, int size);
+struct shim_sexp *shim_list_get(struct shim_sexp *list, const char *name);
 
 extern SEXP R_NamesSymbol;
 extern SEXP R_NilValue;
@@ -59,6 +77,11 @@ extern SEXP R_NilValue;
 #define SET_VECTOR_ELT(x,i,v) (((SEXP *)((x)->data))[i] = (v))
 #define VECTOR_ELT(x,i)       (((SEXP *)((x)->data))[i])
 #define setAttrib(x, sym, v)  ((x)->names = (v))
+#define getAttrib(x, sym)     ((x)->names ? (x)->names : R_NilValue)
+#define STRING_ELT(x,i)       (((SEXP *)((x)->data))[i])
+#define CHAR(x)               ((const char *)((x)->data))
+#define TYPEOF(x)             ((x)->type)
+#define isNull(x)             ((x) == R_NilValue || (x) == NULL)
 #define error                 shim_error
 #define Rf_error              shim_error
 

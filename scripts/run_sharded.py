@@ -25,7 +25,10 @@ if rank == 0:
     t_1 = time.perf_counter() - t0
     err = {k: float(np.abs(np.asarray(cp[k]) - np.asarray(ref[k])).max()) for k in ("n", "phi", "s", "var", "piG", "piZ")}
     llerr = float(np.abs(cp["loglik"][1:] - ref["loglik"][1:]).max() / np.abs(ref["loglik"][1:]).max())
-    print({"world": world, "iters": int(cp["n"].size - 1), "sharded_s": t_sh, "single_gpu_s": t_1, "max_abs_err": err, "loglik_rel_err": llerr,
+    comm = T.Comm(T.Comm.unique_id(), 0, 1)
+    ver = comm.nccl_version()
+    comm.close()
+    print({"world": world, "nccl_version": ver, "iters": int(cp["n"].size - 1), "sharded_s": t_sh, "single_gpu_s": t_1, "max_abs_err": err, "loglik_rel_err": llerr,
            "shard_sizes": [int(x) for x in T.shard_chromosomes(data, world)[2]]})
     assert max(err.values()) < 1e-8 and llerr < 1e-11
 dist.barrier()

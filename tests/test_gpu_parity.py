@@ -530,3 +530,56 @@ def test_estep_is_bitwise_reproducible_at_scale():
                 ref = key
             assert np.array_equal(ref, key), (chunk, r)
     sol.close()
+
+
+@pytest.mark.gpu
+def test_fused_r_glue_returns_the_runEMclonalCN_list_and_an_int_path():
+    """Level 2 of the drop-in: csrc/r_glue_fused.c through the .Call emulation -- titan_solver_create_R (external
+    pointer + finalizer), titan_em_run_R (the named list of R/hmmClonal.R:344-357, iteration axis trimmed to 1:i) and
+    titan_viterbi_R (INTSXP[N]) -- against the host mirror runEMclonalCN / viterbiClonalCN on the same data."""
+    import ctypes as C
+    from oracle import refshim
+    from titancna_b200 import build as B
+    glue = refshim.ShimLibrary(B.GLUE)
+    data, _ = synth.make_data(6000, Z=2, maxCN=5, n_chr=3, seed=11, mean_seg=300)
+    p = T.loadDefaultParameters(copyNumber=5, numberClonalClusters=2, data=data)
+    g, nP, pP, sP = p["genotypeParams"], p["normalParams"], p["ploidyParams"], p["cellPrevParams"]
+    want = T.runEMclonalCN(data, p, txnExpLen=1e9, txnZstrength=1.0, maxiter=4, verbose=False)
+    wpath = T.viterbiClonalCN(data, want)
+    keep = []
+    R = lambda v: glue._real(np.atleast_1d(np.asarray(v, float)), keep)
+    off = T.chromosome_offsets(data["chr"]).astype(float)
+    solver = glue.call("titan_solver_create_R", R(off), R(data["posn"]), R(data["ref"]), R(data["tumDepth"]), R(data["logR"]),
+                       R(1e9), R(1.0), R(g["ZS"]), R(2))
+    assert solver.contents.type == refshim.EXTPTRSXP and solver.contents.data
+    hyper = {k: g[k] for k in ("rt", "ct", "ZS", "rn", "var_0", "alphaKHyper", "betaKHyper", "kappaGHyper", "piG_0")}
+    hyper.update({k: sP[k] for k in ("s_0", "alphaSHyper", "betaSHyper", "kappaZHyper", "piZ_0")})
+    hyper.update({k: nP[k] for k in ("n_0", "alphaNHyper", "betaNHyper")})
+    hyper.update({k: pP[k] for k in ("phi_0", "alphaPHyper", "betaPHyper")})
+    out = glue.call("titan_em_run_R", solver, glue.named_list(hyper, keep), R(4), R(1500), R(1), R(1), R(1), R(0.001))
+    fit = glue.list_to_dict(out)
+    assert list(fit) == ["n", "s", "var", "phi", "piG", "piZ", "muR", "muC", "loglik", "rhoG", "rhoZ"]
+    U, Z, N, I = len(g["rt"]), 2, data["posn"].size, want["n"].size
+    assert fit["n"].shape == (I,) and fit["s"].shape == (Z, I) and fit["var"].shape == (U, I) and fit["muR"].shape == (U * Z, I)
+    assert fit["rhoG"].shape == (U, N) and fit["rhoZ"].shape == (Z, N)
+    for k in ("n", "phi", "loglik", "s", "var", "piG", "piZ"):
+        assert np.array_equal(fit[k], want[k]), k
+    assert np.array_equal(fit["muR"].reshape((U, Z, I), order="F"), want["muR"])
+    assert np.array_equal(fit["rhoG"], want["rhoG"]) and np.array_equal(fit["rhoZ"], want["rhoZ"])
+    i = I - 1
+    vp = glue.call("titan_viterbi_R", solver, R(fit["n"][i]), R(fit["s"][:, i]), R(fit["phi"][i]), R(fit["var"][:, i]),
+                   R(fit["piG"][:, i - 1]), R(fit["piZ"][:, i - 1]), R(g["rt"]), R(g["ct"]), R(g["rn"]))
+    o = vp.contents
+    assert o.type == refshim.INTSXP and o.length == N
+    path = np.ctypeslib.as_array(C.cast(o.data, C.POINTER(C.c_int)), shape=(N,)).copy()
+    assert np.array_equal(path, wpath)
+    with pytest.raises(refshim.RError, match="must be a numeric vector"):
+        bad = dict(hyper)
+        del bad["kappaGHyper"]
+        glue.call("titan_em_run_R", solver, glue.named_list(bad, keep), R(4), R(1500), R(1), R(1), R(1), R(0.001))
+    glue.lib.shim_free_all()
+    assert glue.gc() >= 1                                   # the finalizer destroys the solver ...
+    with pytest.raises(refshim.RError, match="not a live titan solver"):      # ... a stale handle is refused
+        stale = glue.lib.shim_wrap(refshim.EXTPTRSXP, 1, None, -1, -1)
+        glue.call("titan_viterbi_R", stale, *[R(0.0) for _ in range(9)])
+    glue.lib.shim_free_all()

@@ -145,6 +145,17 @@ def test_r_glue_registers_the_reference_call_table():
     assert glue.registered() == {"getPositionOverlapC": 3, "fwd_backC_clonalCN": 9, "viterbiC_clonalCN": 9}
     if refshim.have_reference():
         assert glue.registered() == refshim.reference().registered()
+    # Level 2 (r_glue_fused.c): the solver routines ride in the same table
+    assert glue.registered(("titan_solver_create_R", "titan_em_run_R", "titan_viterbi_R")) == {
+        "titan_solver_create_R": 9, "titan_em_run_R": 8, "titan_viterbi_R": 10}
+    keep = []
+    with pytest.raises(refshim.RError, match="not a live titan solver"):
+        glue.call("titan_viterbi_R", *[glue._real([0.0], keep) for _ in range(10)])
+    with pytest.raises(refshim.RError, match="equal length"):
+        glue.call("titan_solver_create_R", glue._real([0, 3], keep), glue._real([1, 2, 3], keep), glue._real([1, 2], keep),
+                  glue._real([1, 2, 3], keep), glue._real([1, 2, 3], keep), glue._real([1e15], keep), glue._real([1.0], keep),
+                  glue._real([0, 1], keep), glue._real([1], keep))
+    glue.lib.shim_free_all()
     with pytest.raises(refshim.RError, match="The obslik must be 4-by-5 dimension"):
         glue.fwd_back(np.zeros(4), np.zeros((3, 5)), np.zeros(2), np.arange(2.0), 2, np.arange(5.0), 1e15, 1e15)
     with pytest.raises(refshim.RError, match="The obslik must be 4-by-5 dimension"):

@@ -84,7 +84,8 @@ EXPORTS = [
     "titan_fwd_back_clonalCN", "titan_viterbi_clonalCN", "titan_get_position_overlap",
     "titan_solver_create", "titan_solver_destroy", "titan_solver_configure", "titan_solver_set_stream",
     "titan_estep", "titan_viterbi", "titan_em_run", "titan_mstep", "titan_solver_timing",
-    "titan_release_cached_memory",
+    "titan_release_cached_memory", "titan_measure_fp64_peak",
+    "titan_solver_shape", "titan_comm_unique_id", "titan_comm_create", "titan_comm_destroy", "titan_comm_info", "titan_solver_set_comm",
 ]
 
 _lib = None
@@ -121,11 +122,17 @@ def lib():
                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                               c_double_p, c_int_p, c_double_p]
     L.titan_solver_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.titan_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
+    L.titan_solver_shape.argtypes = [C.c_void_p, c_i64_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.titan_comm_unique_id.argtypes = [C.c_char_p]
+    L.titan_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.titan_comm_destroy.argtypes = [C.c_void_p]
+    L.titan_comm_destroy.restype = None
+    L.titan_comm_info.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
+    L.titan_solver_set_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
     for name in EXPORTS:
-        if getattr(L, name).restype is C.c_int or name not in ("titan_last_error", "titan_version",
-                                                               "titan_solver_destroy"):
-            if name not in ("titan_last_error", "titan_version", "titan_solver_destroy"):
-                getattr(L, name).restype = C.c_int
+        if name not in ("titan_last_error", "titan_version", "titan_solver_destroy", "titan_comm_destroy"):
+            getattr(L, name).restype = C.c_int
     _lib = L
     return L
 
@@ -145,3 +152,41 @@ def device_count() -> int:
     n = C.c_int(0)
     rc = lib().titan_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def measure_fp64_peak():
+    """DFMA throughput of the current device in TFLOP/s (titan_measure_fp64_peak) and the launch's milliseconds."""
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(lib().titan_measure_fp64_peak(C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+class Comm:
+    """One NCCL communicator over the ranks that share a chromosome-sharded solution (include/titancna_b200.h section 3)."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        check(lib().titan_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, world: int):
+        if len(unique_id) != Comm.ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of Comm.unique_id() drawn on rank 0")
+        h = C.c_void_p()
+        check(lib().titan_comm_create(C.create_string_buffer(unique_id, Comm.ID_BYTES), int(rank), int(world), C.byref(h)))
+        self._h, self.rank, self.world = h, int(rank), int(world)
+
+    def nccl_version(self) -> int:
+        v = C.c_int(0)
+        check(lib().titan_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().titan_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close

@@ -43,7 +43,7 @@ def _stale(target, sources):
 def build(force=False, verbose=False):
     """Every .cu is its own translation unit (compiled in parallel, nvcc cross-compiles without a GPU), linked into one
     shared object."""
-    units = ["titan_api.cu", "titan_fb2.cu"]
+    units = ["titan_api.cu", "titan_fb2.cu", "titan_util.cu"]
     headers = [os.path.join(CSRC, f) for f in ("titan_kernels.cuh", "titan_common.cuh", "titan_fb2.h", "titan_host.hpp")]
     headers.append(os.path.join(ROOT, "include", "titancna_b200.h"))
     objdir = os.path.join(CSRC, "build")
@@ -66,12 +66,13 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    glue_src = os.path.join(CSRC, "r_glue.c")
+    glue_src = [os.path.join(CSRC, "r_glue.c"), os.path.join(CSRC, "r_glue_fused.c")]
     shim = os.path.join(ROOT, "oracle", "shim")
-    if os.path.exists(glue_src) and os.path.isdir(shim) and (force or _stale(GLUE, [glue_src, LIB])):
+    shim_src = [os.path.join(shim, f) for f in ("shim.c", "R.h")]
+    if all(os.path.exists(g) for g in glue_src) and os.path.isdir(shim) and (force or _stale(GLUE, glue_src + shim_src + [LIB])):
         cc = shutil.which("gcc") or "gcc"
-        cmd = [cc, "-O2", "-fPIC", "-shared", "-I", shim, "-I", os.path.join(ROOT, "include"), "-o", GLUE,
-               glue_src, os.path.join(shim, "shim.c"), "-L", CSRC, "-ltitancna_b200", "-Wl,-rpath,$ORIGIN"]
+        cmd = [cc, "-O2", "-Wall", "-fPIC", "-shared", "-I", shim, "-I", os.path.join(ROOT, "include"), "-o", GLUE,
+               *glue_src, os.path.join(shim, "shim.c"), "-L", CSRC, "-ltitancna_b200", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

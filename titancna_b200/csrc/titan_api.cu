@@ -17,6 +17,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "titan_comm.h"
 #include "titan_fb2.h"
 #include "titan_host.hpp"
 #include "titan_kernels.cuh"
@@ -55,6 +56,10 @@ struct CudaFail {
   } while (0)
 
 extern "C" const char *titan_last_error(void) { return g_err.c_str(); }
+int titan::set_error(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
 extern "C" const char *titan_version(void) { return "titancna_b200 0.1 (sm_100a)"; }
 
 extern "C" int titan_device_count(int *count) {
@@ -193,6 +198,14 @@ struct titan_solver {
   std::thread vit_builder;          // builds the Viterbi log-transition tables on the host while the EM runs
   std::vector<double> vit_tab;      // [nDistinct][K][4]
   bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
+
+  // chromosome-sharded solution (titan_solver_set_comm): this solver holds chromosomes chr_global[] of nChrTotal
+  titan_comm *comm = nullptr;
+  int nChrTotal = 0;
+  std::vector<int> chr_global;
+  DevBuf<int> chr_global_d;
+  DevBuf<double> gvec;             // [6K | nChrTotal loglik | U x nChrTotal | Z x nChrTotal], all-reduced in place
+  int nChrOut() const { return comm ? nChrTotal : nChr; }
 
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   titan_timing tm{};
@@ -512,6 +525,15 @@ extern "C" void titan_solver_destroy(titan_solver *s) {
   delete s;
 }
 
+extern "C" int titan_solver_shape(const titan_solver *s, int64_t *N, int32_t *nChr, int32_t *U, int32_t *Z) {
+  if (!s) return fail(TITAN_ERR_ARG, "titan_solver_shape: NULL solver");
+  if (N) *N = s->N;
+  if (nChr) *nChr = s->nChr;
+  if (U) *U = s->U;
+  if (Z) *Z = s->Z;
+  return TITAN_OK;
+}
+
 extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup_len, double rel_tol, int max_rounds) {
   if (!s) return fail(TITAN_ERR_ARG, "solver is NULL");
   try {
@@ -559,6 +581,53 @@ extern "C" int titan_release_cached_memory(void) {
 extern "C" int titan_solver_timing(const titan_solver *s, titan_timing *t) {
   if (!s || !t) return fail(TITAN_ERR_ARG, "NULL argument");
   *t = s->tm;
+  return TITAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// chromosome shards: whole-genome layout of the per-E-step outputs, all-reduced over the ranks of one solution
+// ---------------------------------------------------------------------------------------------
+__global__ void shard_gather_kernel(const double *__restrict__ out, const double *__restrict__ rhoG0,
+                                    const double *__restrict__ rhoZ0, const int *__restrict__ chr_global, int nChr, int nT,
+                                    int width, int U, int Z, double *__restrict__ g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < width) { g[i] = out[i]; return; }
+  int j = i - width;
+  if (j < nChr) { g[width + chr_global[j]] = out[width + j]; return; }
+  j -= nChr;
+  if (j < nChr * U) { g[width + nT + chr_global[j / U] * U + j % U] = rhoG0[j]; return; }
+  j -= nChr * U;
+  if (j < nChr * Z) g[width + nT + nT * U + chr_global[j / Z] * Z + j % Z] = rhoZ0[j];
+}
+
+extern "C" int titan_solver_set_comm(titan_solver *s, titan_comm *comm, int nChr_total, const int32_t *chr_global) {
+  if (!s) return fail(TITAN_ERR_ARG, "titan_solver_set_comm: NULL solver");
+  if (s->legacy_py) return fail(TITAN_ERR_ARG, "titan_solver_set_comm: solver was created for materialised emissions");
+  try {
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->state_valid = false;
+    if (!comm) {
+      s->comm = nullptr;
+      s->out_h.alloc(6 * (size_t)s->K + s->nChr + (size_t)s->nChr * (s->U + s->Z));
+      return TITAN_OK;
+    }
+    if (!chr_global || nChr_total < s->nChr) return fail(TITAN_ERR_ARG, "titan_solver_set_comm: chr_global[nChr] and nChr_total >= nChr are required");
+    if (comm->device != s->device) return fail(TITAN_ERR_ARG, "titan_solver_set_comm: communicator and solver live on different devices");
+    for (int c = 0; c < s->nChr; ++c)
+      if (chr_global[c] < 0 || chr_global[c] >= nChr_total || (c > 0 && chr_global[c] <= chr_global[c - 1]))
+        return fail(TITAN_ERR_ARG, "titan_solver_set_comm: chr_global must be ascending indices below nChr_total");
+    s->chr_global.assign(chr_global, chr_global + s->nChr);
+    s->nChrTotal = nChr_total;
+    s->chr_global_d.alloc(std::max(1, s->nChr));
+    CK(cudaMemcpy(s->chr_global_d.p, s->chr_global.data(), sizeof(int) * s->nChr, cudaMemcpyHostToDevice));
+    const size_t len = 6 * (size_t)s->K + (size_t)nChr_total * (1 + s->U + s->Z);
+    s->gvec.alloc(len);
+    s->out_h.alloc(len);
+    s->comm = comm;
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
   return TITAN_OK;
 }
 
@@ -732,7 +801,8 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
 // the N-sized marginals (what runEMclonalCN returns as rhoG / rhoZ of its last E-step).
 static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o, bool want_post, double *loggamma_out,
                       bool posterior_only = false) {
-  const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
+  const int U = s->U, Z = s->Z, K = s->K;
+  int nChr = s->nChr;
   const int64_t N = s->N;
   CK(cudaSetDevice(s->device));
   int rc = TITAN_OK;
@@ -766,10 +836,27 @@ static int estep_impl(titan_solver *s, const titan_params *p, titan_estep_out *o
   }
   CK(cudaEventRecord(s->ev[3], s->stream));
   double *oh = s->out_h.p;
-  CK(cudaMemcpyAsync(oh, s->out.p, sizeof(double) * (width + nChr), cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaMemcpyAsync(oh + width + nChr, s->rhoG0.p, sizeof(double) * (size_t)nChr * U, cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaMemcpyAsync(oh + width + nChr + (size_t)nChr * U, s->rhoZ0.p, sizeof(double) * (size_t)nChr * Z,
-                     cudaMemcpyDeviceToHost, s->stream));
+  if (s->comm) {
+    // whole-genome layout, zero where another rank holds the chromosome, summed over the ranks on the device
+    const int nT = s->nChrTotal;
+    const size_t len = (size_t)width + (size_t)nT * (1 + U + Z);
+    const int items = width + nChr * (1 + U + Z);
+    CK(cudaMemsetAsync(s->gvec.p, 0, sizeof(double) * len, s->stream));
+    shard_gather_kernel<<<(items + 255) / 256, 256, 0, s->stream>>>(s->out.p, s->rhoG0.p, s->rhoZ0.p, s->chr_global_d.p, nChr, nT,
+                                                                    width, U, Z, s->gvec.p);
+    CK(cudaGetLastError());
+    s->tm.kernel_launches += 1;
+    std::string err;
+    if (!comm_allreduce_sum_f64(s->comm, s->gvec.p, len, s->stream, err)) return fail(TITAN_ERR_CUDA, "%s", err.c_str());
+    CK(cudaEventRecord(s->ev[3], s->stream));      // the collective is part of a sharded E-step's device time
+    CK(cudaMemcpyAsync(oh, s->gvec.p, sizeof(double) * len, cudaMemcpyDeviceToHost, s->stream));
+    nChr = nT;                      // the outputs below are whole-genome sized
+  } else {
+    CK(cudaMemcpyAsync(oh, s->out.p, sizeof(double) * (width + nChr), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(oh + width + nChr, s->rhoG0.p, sizeof(double) * (size_t)nChr * U, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(oh + width + nChr + (size_t)nChr * U, s->rhoZ0.p, sizeof(double) * (size_t)nChr * Z,
+                       cudaMemcpyDeviceToHost, s->stream));
+  }
   CK(cudaStreamSynchronize(s->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1])); s->tm.last_fwd_ms = ms;
@@ -1329,7 +1416,7 @@ extern "C" int titan_mstep(const titan_hyper *h, int U, int Z, int nChr, int max
 extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_em_opts *o, titan_em_out *out) {
   if (!s || !h || !o || !out) return fail(TITAN_ERR_ARG, "titan_em_run: NULL argument");
   if (s->legacy_py) return fail(TITAN_ERR_ARG, "titan_em_run: solver was created for materialised emissions");
-  const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChr;
+  const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChrOut();      // whole genome when the solution is sharded
   th::Hyper H;
   int rc = hyper_from_c(h, U, Z, &H);
   if (rc != TITAN_OK) return rc;

@@ -45,6 +45,13 @@ class Solver:
         self.U = int(np.asarray(genotypeParams["rt"]).size)
         self.Z = int(Z)
         self.K = self.U * self.Z
+        # the C ABI takes bare pointers: every column must really have N entries, every per-genotype vector U
+        for k in ("chr", "ref", "tumDepth", "logR"):
+            if np.asarray(data[k]).size != self.N:
+                raise ValueError(f"data${k} has {np.asarray(data[k]).size} entries, data$posn has {self.N}")
+        for k in ("ct", "ZS"):
+            if np.asarray(genotypeParams[k]).size < self.U:
+                raise ValueError(f"genotypeParams${k} has fewer entries than genotypeParams$rt ({self.U})")
         keep = []
         d = DataDesc()
         d.N, d.nChr = self.N, self.nChr
@@ -59,6 +66,7 @@ class Solver:
         h = C.c_void_p()
         check(L.titan_solver_create(C.byref(d), C.byref(h)))
         self._h = h
+        self.nChrOut = self.nChr          # whole-genome chromosome count once set_comm() shards the solution
 
     def close(self):
         if getattr(self, "_h", None):
@@ -72,6 +80,21 @@ class Solver:
 
     def set_stream(self, cuda_stream_ptr):
         check(lib().titan_solver_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_comm(self, comm, nChr_total, chr_global):
+        """This solver holds chromosomes `chr_global` (ascending indices) of an `nChr_total`-chromosome data set whose
+        other chromosomes live on the other ranks of `comm` (a _lib.Comm): estep() / runEMclonalCN then return
+        whole-genome statistics on every rank (one NCCL all-reduce per E-step inside the library)."""
+        if comm is None:
+            check(lib().titan_solver_set_comm(self._h, None, 0, None))
+            self.nChrOut = self.nChr
+            return
+        idx = np.ascontiguousarray(chr_global, dtype=np.int32)
+        if idx.size != self.nChr:
+            raise ValueError("chr_global must name every chromosome this solver holds")
+        check(lib().titan_solver_set_comm(self._h, comm._h, int(nChr_total), idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        self.nChrOut = int(nChr_total)
+        self._comm = comm                 # keep the communicator alive as long as the solver uses it
 
     def timing(self):
         t = Timing()
@@ -91,7 +114,7 @@ class Solver:
         """One E-step -> dict(loglik_chr, stats{a,b,c,d,e,g}[U,Z], rhoG0, rhoZ0, [rhoG, rhoZ], muR, muC)."""
         keep = []
         p = self._params(n, s, phi, var, piG, piZ, genotypeParams, keep)
-        U, Z, K, nChr, N = self.U, self.Z, self.K, self.nChr, self.N
+        U, Z, K, nChr, N = self.U, self.Z, self.K, self.nChrOut, self.N
         ll = np.zeros(nChr); st = np.zeros(6 * K); g0 = np.zeros(nChr * U); z0 = np.zeros(nChr * Z)
         muR = np.zeros(K); muC = np.zeros(K)
         o = EstepOut()

@@ -70,6 +70,16 @@ def _all_reduce_sum(vec, group=None):
     return t.cpu().numpy()
 
 
+def make_comm(rank, world, group=None):
+    """A library communicator (NCCL inside libtitancna_b200) over the ranks of a torch.distributed group: rank 0 draws
+    the 128-byte id, torch.distributed ships it (plumbing only), every rank joins on its current CUDA device."""
+    import torch.distributed as dist
+    ids = [_lib.Comm.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0, group=group)
+    return _lib.Comm(ids[0], rank, world)
+
+
 def host_mstep(params, U, Z, nChr, maxiterUpdate, normalEstimateMethod, estimateS, estimatePloidy, stats_flat, rhoG0,
                rhoZ0, prev):
     """titan_mstep (host C++ coordinate descent + priors) -> dict(n, s, var, phi, piG, piZ, sweeps, prior)."""
@@ -92,11 +102,17 @@ def host_mstep(params, U, Z, nChr, maxiterUpdate, normalEstimateMethod, estimate
 
 def runEMclonalCN_sharded(data, params, rank, world, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, maxiterUpdate=1500,
                           normalEstimateMethod="map", estimateS=True, estimatePloidy=True, likChangeThreshold=0.001,
-                          group=None, estep_fn=None, device=None, verbose=False):
+                          group=None, estep_fn=None, device=None, verbose=False, comm=None, solver=None,
+                          return_timing=False):
     """runEMclonalCN with one solution's chromosomes sharded over `world` ranks.
 
+    On GPUs (default) every rank builds a Solver over its own chromosomes, attaches a library communicator
+    (titan_solver_set_comm) and runs the ordinary in-library EM loop: the ONE collective of an iteration is an
+    ncclAllReduce of the statistics vector on the device, inside titan_estep; the M-step is replicated.
+    The N-sized outputs (rhoG, rhoZ) cover this rank's chromosomes (`shard`, `shard_index`).
+
     `estep_fn(sub_data, n, s, phi, var, piG, piZ, genotypeParams) -> dict(loglik, stats_flat, rhoG0, rhoZ0)` lets the CPU
-    tests stand in for the GPU E-step; by default each rank builds a Solver over its own chromosomes."""
+    tests stand in for the GPU E-step; that path keeps the loop and the all-reduce on the host (torch.distributed)."""
     _check_params(params)
     g, pP, nP, sP = (params[k] for k in ("genotypeParams", "ploidyParams", "normalParams", "cellPrevParams"))
     U, Z = len(g["rt"]), len(sP["s_0"])
@@ -104,17 +120,31 @@ def runEMclonalCN_sharded(data, params, rank, world, txnExpLen=1e15, txnZstrengt
     shards, off, _ = shard_chromosomes(data, world)
     nChr = off.size - 1
     mine = shards[rank]
-    sub, _ = subset_data(data, off, mine)
-    solver = None
+    sub, sub_idx = subset_data(data, off, mine)
     if estep_fn is None:
-        solver = Solver(sub, g, Z, txnExpLen, txnZstrength, device=device) if len(mine) else None
-
-        def estep_fn(_sub, n, s, phi, var, piG, piZ, gp):
-            if solver is None:
-                return {"loglik": 0.0, "stats_flat": np.zeros(6 * K), "rhoG0": np.zeros((U, 0)), "rhoZ0": np.zeros((Z, 0))}
-            o = solver.estep(n, s, phi, var, piG, piZ, gp)
-            return {"loglik": o["loglik"], "stats_flat": o["stats_flat"], "rhoG0": o["rhoG0"], "rhoZ0": o["rhoZ0"]}
-
+        if len(mine) == 0:
+            raise ValueError("more ranks than chromosomes: every rank of a sharded solution needs at least one chromosome")
+        own_solver, own_comm = solver is None, comm is None
+        if own_solver:
+            solver = Solver(sub, g, Z, txnExpLen, txnZstrength, device=device)
+        if own_comm:
+            comm = make_comm(rank, world, group)
+        try:
+            solver.set_comm(comm, nChr, mine)
+            cp = runEMclonalCN(sub, params, txnExpLen=txnExpLen, txnZstrength=txnZstrength, maxiter=maxiter,
+                               maxiterUpdate=maxiterUpdate, normalEstimateMethod=normalEstimateMethod, estimateS=estimateS,
+                               estimatePloidy=estimatePloidy, likChangeThreshold=likChangeThreshold, verbose=verbose and rank == 0,
+                               solver=solver, return_timing=return_timing)
+        finally:
+            if own_solver:
+                solver.close()
+            else:
+                solver.set_comm(None, 0, None)
+            if own_comm:
+                comm.close()
+        cp["shard"], cp["shard_index"] = mine, sub_idx
+        return cp
+    solver = None            # host-side loop below: stand-in E-step, all-reduce through torch.distributed (CPU tests)
     M = int(maxiter) + 1
     cur = {"n": float(nP["n_0"]), "s": np.array(sP["s_0"], float), "var": np.array(g["var_0"], float),
            "phi": float(pP["phi_0"]), "piG": np.array(g["piG_0"], float), "piZ": np.array(sP["piZ_0"], float)}
