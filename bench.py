@@ -184,7 +184,7 @@ def cpu_estep(sample, Z, threads):
     return step, engine
 
 
-def run_reference_arm(a, rank, world):
+def run_reference_arm(a, rank, world, emit):
     """The reference's own C (one chromosome per worker, its only parallel mode) on the host cores.  One step of the
     full configuration costs ~280 core-seconds (O(N K^2)) and its longest chromosome ~22 s on one thread, so the arm
     runs every step on the LARGEST per-chromosome prefix sample that keeps steps + warm-up inside --ref-budget-s
@@ -226,7 +226,7 @@ def run_reference_arm(a, rank, world):
                              "sample": sample_txt, "whole_workload": bool(whole)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -241,15 +241,22 @@ def em_trajectory(T, data, p, sol, maxiter=20):
 
 
 def main():
+    # stdout carries the one JSON line and nothing else: native libraries (NCCL's version banner) write to file
+    # descriptor 1 directly, so the descriptor itself is pointed at stderr until the line is printed
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
-        run_reference_arm(a, rank, world)
+        run_reference_arm(a, rank, world, emit)
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line, nothing else
     import torch
     import torch.distributed as dist
     import titancna_b200 as T
@@ -460,7 +467,7 @@ def main():
                                     "kind": "reference" if engine == "reference" else "port",
                                     "sample": f"one E-step over the first {per_chr} SNPs of each chromosome "
                                               f"({sample['posn'].size} SNPs, K={K}), {dt:.1f} s on one host core"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

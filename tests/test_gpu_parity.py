@@ -583,3 +583,46 @@ def test_fused_r_glue_returns_the_runEMclonalCN_list_and_an_int_path():
         stale = glue.lib.shim_wrap(refshim.EXTPTRSXP, 1, None, -1, -1)
         glue.call("titan_viterbi_R", stale, *[R(0.0) for _ in range(9)])
     glue.lib.shim_free_all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk,warm", [(400, 128), (0, 1)])
+def test_config4_as_named_36_genotype_states_k180(chunk, warm):
+    """BASELINE configs[3] as written: maxCN = 10 -> the 36-state genotype table (two genotypes per lane in the
+    forward-backward kernels), numClusters = 5, K = 180.  The reference's C is generic in K, so its port referees the
+    E-step (log-likelihoods, posteriors, the six sums) and the Viterbi path bit for bit."""
+    N, Z = 2400, 5
+    data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=2, seed=41, mean_seg=200)
+    p = T.loadDefaultParameters(copyNumber=10, numberClonalClusters=Z, extendedTable=True)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    assert g["rt"].size == 36 and g["ct"][-1] == 10 and np.count_nonzero(g["ZS"] == -1) == 1
+    n, phi, s = 0.35, 2.1, np.array(synth.S_TRUE[:Z]) * 0.9 + 0.02
+    var = g["var_0"] * np.linspace(0.5, 1.5, g["var_0"].size)
+    es = _oracle_estep(data, p, n, s, phi, var, g["piG_0"], sP["piZ_0"], 1e15, 1.0)
+    sol = T.Solver(data, g, Z, 1e15, 1.0)
+    sol.configure(chunk, warm, 1e-10)
+    out = sol.estep(n, s, phi, var, g["piG_0"], sP["piZ_0"], g, posteriors=True)
+    got = sol.viterbi(n, s, phi, var, g["piG_0"], sP["piZ_0"], g)
+    sol.close()
+    assert np.allclose(out["loglik_chr"], es["loglik_chr"], rtol=LL_RTOL, atol=0)
+    assert np.abs(out["rhoG"] - es["rhoG"]).max() < 1e-9 and np.abs(out["rhoZ"] - es["rhoZ"]).max() < 1e-9
+    for k in "abcdeg":
+        ref = es["stats"][k]
+        assert np.abs(out["stats"][k] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), k
+    lp = np.vectorize(math.log)(np.outer(g["piG_0"], sP["piZ_0"]).reshape(-1, order="F"))
+    want = np.empty(N, dtype=np.int32)
+    for idx in O.chromosome_slices(data["chr"]):
+        want[idx] = O.viterbi(lp, es["py"][:, idx], g["ZS"], Z, data["posn"][idx], 1e15, 1e15, engine="port")
+    assert got.max() <= 180 and np.array_equal(got, want), f"first mismatch at {np.flatnonzero(got != want)[:5]}"
+
+
+@pytest.mark.gpu
+def test_config4_as_named_em_matches_oracle_em():
+    """runEMclonalCN on the 36-state table (K = 108 at three clusters) against the oracle's EM restatement."""
+    data, _ = synth.make_data(3000, Z=3, maxCN=8, n_chr=2, seed=43, mean_seg=250)
+    p = T.loadDefaultParameters(copyNumber=10, numberClonalClusters=3, data=data, extendedTable=True)
+    got = T.runEMclonalCN(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=3, verbose=False)
+    want = O.run_em_clonal_cn(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=3, engine="port", threads=8)
+    for k in ("n", "phi", "s", "var"):
+        assert np.allclose(got[k], want[k], rtol=0, atol=1e-6), k
+    assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=1e-9)

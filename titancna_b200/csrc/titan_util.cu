@@ -145,6 +145,20 @@ extern "C" int titan_comm_create(const char *id, int rank, int world, titan_comm
   if (rc != 0) return comm_fail(TITAN_ERR_CUDA, nccl_msg(api, "ncclCommInitRank", rc));
   titan_comm *c = new titan_comm;
   c->nccl = comm; c->rank = rank; c->world = world; c->device = dev;
+  // NCCL connects its channels lazily inside the first collective (hundreds of milliseconds): do that here, once,
+  // so that the first E-step of a sharded solution costs what every other one costs
+  double *warm = nullptr;
+  if (cudaMalloc(&warm, sizeof(double) * 2048) == cudaSuccess) {
+    cudaMemset(warm, 0, sizeof(double) * 2048);
+    const int rc2 = api.AllReduce(warm, warm, 2048, kNcclFloat64, kNcclSum, comm, (cudaStream_t)0);
+    const cudaError_t ce = cudaStreamSynchronize((cudaStream_t)0);
+    cudaFree(warm);
+    if (rc2 != 0 || ce != cudaSuccess) {
+      api.CommDestroy(comm);
+      delete c;
+      return comm_fail(TITAN_ERR_CUDA, rc2 != 0 ? nccl_msg(api, "ncclAllReduce (warm-up)", rc2) : std::string("warm-up all-reduce failed: ") + cudaGetErrorString(ce));
+    }
+  }
   *out = c;
   return TITAN_OK;
 }

@@ -24,11 +24,12 @@ def setupClonalParameters(Z, sPriorStrength=2):
             "kappaZHyper": np.ones(Z) + 1}
 
 
-def _symmetric_table(rn):
-    """rt / ct of the symmetric genotype table for total copies 0..8 (R/utils.R:24-26,42-43):
-    for c copies the major-allele fractions c/c, (c-1)/c, ... down to 1/2."""
+def _symmetric_table(rn, max_copies=8):
+    """rt / ct of the symmetric genotype table for total copies 0..max_copies (R/utils.R:24-26,42-43 list 0..8):
+    for c copies the major-allele fractions c/c, (c-1)/c, ... down to 1/2.  The same rule continued to 9 and 10
+    copies gives the 36-state table of BASELINE configs[3] (ct 9: 1, 8/9 .. 5/9; ct 10: 1, .9 .. .5)."""
     rt, ct, balanced = [rn, 1.0], [0, 1], []
-    for c in range(2, 9):
+    for c in range(2, max_copies + 1):
         for major in range(c, (c + 1) // 2 - 1, -1):
             rt.append(major / c)
             ct.append(c)
@@ -38,15 +39,16 @@ def _symmetric_table(rn):
 
 
 def loadDefaultParameters(copyNumber=5, numberClonalClusters=1, skew=0, hetBaselineSkew=None,
-                          alleleEmissionModel="binomial", symmetric=True, data=None):
-    """R/utils.R:7-148.  `data` (optional) is a dict with ref, tumDepth, logR."""
-    if copyNumber < 3 or copyNumber > 8:
+                          alleleEmissionModel="binomial", symmetric=True, data=None, extendedTable=False):
+    """R/utils.R:7-148.  `data` (optional) is a dict with ref, tumDepth, logR.
+    `extendedTable=True` (no R counterpart) lifts the reference's limit of 8 copies to 10: 36 genotype states."""
+    if copyNumber < 3 or copyNumber > (10 if extendedTable else 8):
         raise ValueError("loadDefaultParameters: Fewer than 3 or more than 8 copies are \n             "
                          "being specified. Please use minimum 3 or maximum 8 'copyNumber'.")
     if alleleEmissionModel not in ("binomial", "Gaussian"):
         raise ValueError('loadDefaultParameters: alleleEmissionModel must be either "binomial" or "Gaussian".')
     rn = 0.5
-    rt, ct, hetState = _symmetric_table(rn)     # hetState = c(4, 9, 16, 25)
+    rt, ct, hetState = _symmetric_table(rn, 10 if extendedTable else 8)     # hetState = c(4, 9, 16, 25[, 36])
     rt = rt + skew
     rt[rt > 1] = 1
     rt[rt < (rn + skew)] = rn + skew
