@@ -111,7 +111,7 @@ def test_fused_estep_matches_oracle(N, Z, maxCN, n_chr, txn, zfac, chunk, warm):
     assert tm["n_chunks"] >= n_chr
 
 
-@pytest.mark.parametrize("vit_mode", ["-1", "0", "2", "3"])
+@pytest.mark.parametrize("vit_mode", ["-1", "0", "2", "3", "4"])
 @pytest.mark.parametrize("N,Z,maxCN,n_chr,txn,zfac", [
     (6000, 3, 8, 3, 1e15, 1.0), (5000, 1, 8, 2, 1e15, 5e5), (4000, 5, 8, 2, 1e9, 1e9), (3000, 2, 5, 4, 1e5, 1.0),
     (2000, 8, 4, 2, 1e15, 1.0), (1500, 8, 8, 2, 1e15, 1.0), (1500, 6, 8, 1, 1e12, 3.0)])

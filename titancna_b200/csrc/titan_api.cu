@@ -159,7 +159,7 @@ struct titan_solver {
   int engine = 2;                  // titan_fb2: materialised emissions, posterior-weighted boundary test, probe-accelerated rounds
   int Kp = 0;                      // row stride of the per-SNP K-vectors in HBM: K states + the emission shift, padded to 16 bytes
   double tol = 1e-8;               // posterior-weighted boundary tolerance of the fb2 engine
-  int vit_mode = -1;               // 3: cluster-sliced scan, 2: register-sliced dense scan, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
+  int vit_mode = -1;               // 4: warp-reduction scan, 3: cluster-sliced scan, 2: register-sliced dense scan, 0: shared-memory dense scan, -1: by K (TITAN_VIT_MODE)
 
   // device data
   DevBuf<SnpRec> snp;
@@ -195,6 +195,7 @@ struct titan_solver {
   DevBuf<double> ltab;
   DevBuf<unsigned char> psi, bt_comp, bt_entry;
   bool vit_ready = false;
+  bool vit_monotone = false;        // every table row has logA(class 2) >= logA(class 0) and logA(class 3) >= logA(class 1)
   std::thread vit_builder;          // builds the Viterbi log-transition tables on the host while the EM runs
   std::vector<double> vit_tab;      // [nDistinct][K][4]
   bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
@@ -949,6 +950,10 @@ static int viterbi_prepare(titan_solver *s) {
   if (s->vit_tab.empty()) build_viterbi_tables(s);
   const std::vector<double> &tab = s->vit_tab;
   const std::vector<int> &id = s->pair_id;
+  // the warp-reduction kernel relies on: same-genotype classes never below the other-genotype classes of the same row
+  s->vit_monotone = true;
+  for (size_t r = 0; r + 3 < tab.size() && s->vit_monotone; r += 4)
+    s->vit_monotone = tab[r + 2] >= tab[r] && tab[r + 3] >= tab[r + 1];
   s->txn_id.alloc(N);
   CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
   s->ltab.alloc(tab.size());
@@ -1033,6 +1038,26 @@ static void launch_vit_cluster(const VitArgs &A, int nChr, cudaStream_t st) {
   }
 }
 
+template <int Z>
+static void launch_vit_redux_z(const VitArgs &A, int nChr, cudaStream_t st) {
+  const size_t smem = 16 * (size_t)(2 * 2 * Z * 32) + sizeof(double) * (size_t)(A.K + 2) + VitRing::bytes(A.K);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_redux_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  viterbi_redux_kernel<Z><<<nChr, 32 * (Z + 1), smem, st>>>(A);
+}
+
+static void launch_vit_redux(const VitArgs &A, int nChr, cudaStream_t st) {
+  switch (A.Z) {
+    case 1: launch_vit_redux_z<1>(A, nChr, st); break;
+    case 2: launch_vit_redux_z<2>(A, nChr, st); break;
+    case 3: launch_vit_redux_z<3>(A, nChr, st); break;
+    case 4: launch_vit_redux_z<4>(A, nChr, st); break;
+    case 5: launch_vit_redux_z<5>(A, nChr, st); break;
+    case 6: launch_vit_redux_z<6>(A, nChr, st); break;
+    case 7: launch_vit_redux_z<7>(A, nChr, st); break;
+    default: launch_vit_redux_z<8>(A, nChr, st); break;
+  }
+}
+
 static void launch_vit_dense(const VitArgs &A, int nChr, int K, bool from_py, cudaStream_t st) {
   int P = 4;                                   // threads per destination state (power of two)
   while (P > 1 && K * P > 1024) P >>= 1;
@@ -1069,14 +1094,17 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   CK(cudaEventRecord(s->ev[4], s->stream));
   int fP = 0, fPER = 0;
   const bool fast_ok = vit_fast_cfg(K, fP, fPER);
-  // 3: cluster-sliced scan, 2: register-sliced dense scan (both one barrier per SNP, emissions materialised first),
-  // 0: shared-memory dense scan (any K <= 256, any class matrix)
+  // 4: warp-reduction scan, 3: cluster-sliced scan, 2: register-sliced dense scan (all one barrier per SNP, emissions
+  // materialised first), 0: shared-memory dense scan (any K <= 256, any class matrix)
   const bool cluster_ok = s->U <= 32 && s->Z <= 8;
+  const bool redux_ok = cluster_ok && s->vit_monotone;
   int mode = s->vit_mode;
-  if (mode < 0) {   // measured on B200 (1 M SNPs, 23 chromosomes): cluster-sliced wins for Z <= 4 and wherever the dense scan has no instance
-    if (cluster_ok && (s->Z <= kVitClusterAutoMaxZ || !fast_ok)) mode = 3;
+  if (mode < 0) {   // measured on B200 (1 M SNPs, 23 chromosomes)
+    if (redux_ok) mode = 4;
+    else if (cluster_ok && (s->Z <= kVitClusterAutoMaxZ || !fast_ok)) mode = 3;
     else mode = fast_ok ? 2 : 0;
   }
+  if (mode == 4 && !redux_ok) mode = 3;
   if (mode == 3 && !cluster_ok) mode = 2;
   if (mode == 2 && !fast_ok) mode = 0;
   if (mode >= 2) {
@@ -1089,7 +1117,8 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
       s->state_valid = false;
       A.py = s->alpha.p;
     }
-    if (mode == 3) launch_vit_cluster(A, s->nChr, s->stream);
+    if (mode == 4) launch_vit_redux(A, s->nChr, s->stream);
+    else if (mode == 3) launch_vit_cluster(A, s->nChr, s->stream);
     else launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
   } else {
     launch_vit_dense(A, s->nChr, K, s->legacy_py, s->stream);

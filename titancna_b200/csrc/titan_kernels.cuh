@@ -707,6 +707,183 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-reduction Viterbi step (default for U <= 32): the slice scan of viterbi_cluster_kernel without the scan.
+//
+// Warp z' holds cluster z' with lane = SOURCE genotype g': every lane keeps the four class values of its own state
+// in registers.  What a destination of genotype g can take from warp z' is
+//   X_g = max over g' of (g' == g ? v2[g'] : v0[g'])      destination in another cluster
+//   Y_g = max over g' of (g' == g ? v3[g'] : v1[g'])      destination in cluster z' / diploid-HET destination
+// and because the same-genotype class never loses to the other-genotype class of the same source (rhoG >= oG, so
+// v2 >= v0 and v3 >= v1 in every row of the host-built table; checked on the host when the table is built), the
+// own-genotype substitution cannot evict a maximum it does not replace: X_g is the better of v2[g] (index g) and the
+// warp-wide first-index maximum (M0, a0) of v0 -- for g == a0 the rule still holds, v2[a0] >= M0.  The warp-wide
+// maximum of an fp64 value is two REDUX.MAX on an order-preserving 64-bit integer key (high word, then low word among
+// the lanes that hold the high maximum), the first index a ballot + find-first-set: exact, ties to the lowest source.
+// One CTA barrier per step publishes the Z per-warp (X, Y) rows; a dedicated warp keeps the input ring filled.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f64_key(double v, unsigned &hi, unsigned &lo) {
+  const int h = __double2hiint(v);
+  const unsigned m = (unsigned)(h >> 31);            // all ones for negative values
+  hi = (unsigned)h ^ (m | 0x80000000u);
+  lo = (unsigned)__double2loint(v) ^ m;
+}
+__device__ __forceinline__ double f64_unkey(unsigned hi, unsigned lo) {
+  const unsigned m = ~(unsigned)((int)hi >> 31);     // key's top bit set <=> value was non-negative
+  return __hiloint2double((int)(hi ^ (m | 0x80000000u)), (int)(lo ^ m));
+}
+// first-index arg-max over the warp of the values whose keys are (hi, lo)
+__device__ __forceinline__ void warp_argmax_key(unsigned hi, unsigned lo, double &mv, int &arg) {
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const bool p = hi == mh;
+  const unsigned ml = __reduce_max_sync(0xffffffffu, p ? lo : 0u);
+  const unsigned who = __ballot_sync(0xffffffffu, p && lo == ml);
+  arg = __ffs((int)who) - 1;
+  mv = f64_unkey(mh, ml);
+}
+
+template <int Z>
+__global__ void __launch_bounds__(32 * (Z + 1)) viterbi_redux_kernel(VitArgs A) {
+  extern __shared__ __align__(16) unsigned char vr_sm[];
+  constexpr int D = 4;                      // unroll of the step loop; even: the exchange parity of a step is static
+  VCand *xch = reinterpret_cast<VCand *>(vr_sm);                             // [2 parity][2 X/Y][Z][32]
+  double *dfin = reinterpret_cast<double *>(xch + 2 * 2 * Z * 32);           // [K]
+  VitRing ring;
+  ring.carve(dfin + ((A.K + 1) & ~1), A.K);
+  const int K = A.K, U = A.U, K4 = 4 * A.K;
+  const int chr = blockIdx.x;
+  const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
+  if (cs >= ce) return;
+  const int warp = threadIdx.x >> 5, g = threadIdx.x & 31;
+  const int last = ce - 1;
+  if (warp == Z) {
+    // ---- feeder warp: keeps the ring DV steps ahead for every state (lane l serves states l, l+32, ...) ----
+    for (int u = 0; u < DV; ++u) {
+      const int s = cs + 1 + u;
+      const int rid = A.txn_id[min(s + 1, last)];
+      for (int j = g; j < K; j += 32) {
+        const int sc = min(s, last);
+        cp_async<8>(ring.e + u * K + j, A.py + (size_t)sc * K + j);
+        const double *row = A.ltab + (size_t)rid * 4 * K + (size_t)j * 4;
+        cp_async<16>(ring.L + ((size_t)u * K + j) * 4, row);
+        cp_async<16>(ring.L + ((size_t)u * K + j) * 4 + 2, row + 2);
+      }
+      cp_async_commit();
+    }
+    int rid_next = A.txn_id[min(cs + DV + 2, last)];     // table of the group issued next (step cs + DV + 1)
+    cp_async_wait<DV - 1>();                             // group of step cs+1 has landed
+    __syncthreads();                                     // publishes the t = cs state and group cs+1
+    for (int tt = cs + 1; tt < ce; ++tt) {
+      // group tt+DV goes into the slot of step tt-2, which every consumer left before the previous barrier
+      const int s = tt + DV, slot = (s - cs - 1) & (RV - 1);
+      const int rid = rid_next;
+      rid_next = A.txn_id[min(s + 2, last)];
+      for (int j = g; j < K; j += 32) {
+        const int sc = min(s, last);
+        cp_async<8>(ring.e + slot * K + j, A.py + (size_t)sc * K + j);
+        const double *row = A.ltab + (size_t)rid * 4 * K + (size_t)j * 4;
+        cp_async<16>(ring.L + ((size_t)slot * K + j) * 4, row);
+        cp_async<16>(ring.L + ((size_t)slot * K + j) * 4 + 2, row + 2);
+      }
+      cp_async_commit();
+      cp_async_wait<DV - 1>();                           // group of step tt+1 has landed: the next barrier publishes it
+      __syncthreads();
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                     // the consumers' closing barrier
+    return;
+  }
+  const int zs = warp;
+  const bool on = g < U;
+  const int j = on ? g + zs * U : 0;        // this lane's state: source (g, zs) and destination (g, zs)
+  const bool het = on && A.het[g];
+  const int ibase = zs * U;
+  // gather addresses: row (z') of X or Y that applies to destination cluster zs
+  unsigned gadr[Z];
+  {
+    const unsigned xbase = (unsigned)__cvta_generic_to_shared(xch);
+#pragma unroll
+    for (int w = 0; w < Z; ++w) {
+      const int sel = (w == zs || het) ? 1 : 0;
+      gadr[w] = xbase + 16u * (unsigned)((sel * Z + w) * 32 + g);
+    }
+  }
+  constexpr unsigned XPAR = 16u * 2 * Z * 32;     // bytes between the two exchange parities
+  VCand *xmine = xch + zs * 32 + g;               // parity 0, X; Y sits Z*32 entries further
+  double v0, v1, v2, v3;
+  // ---- t = cs ----
+  {
+    double d0 = -CUDART_INF;
+    double2 a = make_double2(0, 0), b = make_double2(0, 0);
+    if (on) {
+      d0 = __dadd_rn(A.M.logpi[j], A.py[(size_t)cs * K + j]);
+      if (cs + 1 < ce) {
+        const double2 *row = reinterpret_cast<const double2 *>(A.ltab + (size_t)j * 4 + (size_t)A.txn_id[cs + 1] * K4);
+        a = row[0]; b = row[1];
+      }
+      A.psi[(size_t)cs * K + j] = 0;
+      dfin[j] = d0;
+    }
+    v0 = __dadd_rn(d0, a.x); v1 = __dadd_rn(d0, a.y); v2 = __dadd_rn(d0, b.x); v3 = __dadd_rn(d0, b.y);
+  }
+  __syncthreads();
+  for (int t = cs + 1; t < ce; t += D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      const int tt = t + u;
+      if (tt >= ce) break;
+      // ---- warp-wide first-index maxima of the two other-genotype classes ----
+      unsigned h0, l0, h1, l1;
+      f64_key(v0, h0, l0);
+      f64_key(v1, h1, l1);
+      if (!on) { h0 = l0 = h1 = l1 = 0u; }
+      double m0, m1;
+      int a0, a1;
+      warp_argmax_key(h0, l0, m0, a0);
+      warp_argmax_key(h1, l1, m1, a1);
+      // own-genotype substitution: v2 / v3 at index g against the maximum at index a
+      const bool tx = (v2 > m0) || (v2 == m0 && g < a0);
+      const bool ty = (v3 > m1) || (v3 == m1 && g < a1);
+      VCand cx, cy;
+      cx.v = tx ? v2 : m0; cx.i = ibase + (tx ? g : a0); cx.pad = 0;
+      cy.v = ty ? v3 : m1; cy.i = ibase + (ty ? g : a1); cy.pad = 0;
+      VCand *xo = xmine + ((u & 1) ? 2 * Z * 32 : 0);
+      xo[0] = cx;
+      xo[Z * 32] = cy;
+      __syncthreads();
+      // ---- gather over the Z clusters, in source order ----
+      double gv[Z];
+      int gi[Z];
+#pragma unroll
+      for (int w = 0; w < Z; ++w) {
+        double ip;
+        lds_v2f64(gadr[w] + ((u & 1) ? XPAR : 0u), gv[w], ip);
+        gi[w] = __double2loint(ip);
+      }
+      const int slot = (tt - cs - 1) & (RV - 1);
+      const double e_u = ring.e[slot * K + j];
+      const double2 *rl = reinterpret_cast<const double2 *>(ring.L + ((size_t)slot * K + j) * 4);
+      const double2 la_u = rl[0], lb_u = rl[1];
+      double best;
+      int arg;
+      PairTree<0, Z>::run(gv, gi, best, arg);
+      const double d = on ? __dadd_rn(best, e_u) : -CUDART_INF;
+      v0 = __dadd_rn(d, la_u.x); v1 = __dadd_rn(d, la_u.y); v2 = __dadd_rn(d, lb_u.x); v3 = __dadd_rn(d, lb_u.y);
+      if (on) {
+        A.psi[(size_t)tt * K + j] = (unsigned char)arg;
+        if (tt == last) dfin[j] = d;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // first-index arg-max of the last delta (viterbiC_clonalCN.c:118)
+    int arg = 0;
+    for (int i = 1; i < K; ++i)
+      if (dfin[arg] < dfin[i]) arg = i;
+    A.path[ce - 1] = arg;            // 0-based for now; the back-trace adds 1
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Back-trace (src/viterbiC_clonalCN.c:119-126: path[t-1] = psi[t][path[t]]), parallel in position.
 // Row t of psi is a map state -> state, and maps compose associatively, so the pointer chase over a
 // chromosome splits into tiles of R rows (tile k of a chromosome covers rows hi = ce-1-k*R down to
