@@ -350,8 +350,8 @@ def main():
     achieved = N * K * b_alg / (my_ms * 1e-3) / 1e9
     mean = {k: float(np.mean(v)) for k, v in phases.items()}
     Kp = K + 1 + (K + 1) % 2
-    r0_bytes = N * (2 * 8 * Kp + 8 * Kp + 2 * 64)      # scaled emissions read by both directions, alpha written, records twice
-    fin_bytes = N * (2 * 8 * Kp + 64 + 32)             # scaled emissions + alpha read, both records
+    r0_bytes = N * (2 * 8 * Kp + 8 * Kp + 2 * 128)     # scaled emissions read by both directions, alpha written, records twice
+    fin_bytes = N * (2 * 8 * Kp + 128 + 32)            # scaled emissions + alpha read, both records
     em_bytes = N * (8 * Kp + 32)
     roofline = {"bound": "hbm", "kernel": "fb2_round_kernel (round 0 + re-runs: largest share of the E-step; frac is the WHOLE E-step)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
