@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -88,16 +89,29 @@ extern "C" int titan_set_device(int device) {
 // sporadically cost 50-500 ms each (unmap / remap), several times the E-step.  Ordering contract: every API
 // entry leaves its streams synchronised and ~titan_solver synchronises before its members are released, so
 // a block is never returned to the pool while work on it is in flight.
-static void pool_prepare() {
-  static thread_local int prepared_dev = -1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev == prepared_dev) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+// The pool is the library's OWN (one per device, created on first use): the device's default pool, which a host
+// application may share, keeps its release threshold.
+static cudaMemPool_t titan_pool(int dev) {
+  static std::mutex mu;
+  static std::unordered_map<int, cudaMemPool_t> pools;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = pools.find(dev);
+  if (it != pools.end()) return it->second;
+  cudaMemPoolProps props{};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  cudaMemPool_t pool = nullptr;
+  if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+    cudaGetLastError();
+    pool = nullptr;                                   // fall back to the default pool, threshold untouched
+  } else {
     unsigned long long keep = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  prepared_dev = dev;
+  pools[dev] = pool;
+  return pool;
 }
 
 template <class T>
@@ -107,8 +121,11 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    pool_prepare();
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), cudaStreamPerThread));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    cudaMemPool_t pool = titan_pool(dev);
+    if (pool) CK(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&p), count * sizeof(T), pool, cudaStreamPerThread));
+    else CK(cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), cudaStreamPerThread));
     CK(cudaStreamSynchronize(cudaStreamPerThread));     // usable from any stream from here on
     n = count;
   }
@@ -553,6 +570,8 @@ extern "C" int titan_solver_configure(titan_solver *s, int chunk_len, int warmup
 
 extern "C" int titan_solver_set_stream(titan_solver *s, void *cuda_stream) {
   if (!s) return fail(TITAN_ERR_ARG, "solver is NULL");
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);      // nothing of this solver may still be in flight on the old stream
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   if (cuda_stream) {
     s->stream = (cudaStream_t)cuda_stream;
@@ -569,9 +588,8 @@ extern "C" int titan_release_cached_memory(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
-  cudaMemPool_t pool;
-  e = cudaDeviceGetDefaultMemPool(&pool, dev);
-  if (e == cudaSuccess) {
+  cudaMemPool_t pool = titan_pool(dev);
+  if (pool) {
     cudaDeviceSynchronize();
     e = cudaMemPoolTrimTo(pool, 0);
   }
