@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--no-em", action="store_true", help="skip the whole-solution record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 15-solution sweep record")
     ap.add_argument("--no-sharded", action="store_true", help="skip the chromosome-sharded configs[3] record")
+    ap.add_argument("--sweep-concurrent", type=int, default=1, help="solutions in flight per GPU in the sweep record")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: CPU seconds for all its steps")
     return ap.parse_args()
 
@@ -424,7 +425,8 @@ def main():
             return {"iters": int(c["n"].size - 1), "loglik": float(c["loglik"][-1]), "segments": int(1 + np.count_nonzero(np.diff(pth))),
                     "seconds": time.perf_counter() - t1}
 
-        res, info = T.run_sweep(data, rank, world, device=local, maxiter=20, run_one=run_one, make_params=lambda pl, z: production_params(
+        res, info = T.run_sweep(data, rank, world, device=local, maxiter=20, run_one=run_one, concurrent=a.sweep_concurrent,
+                                make_params=lambda pl, z: production_params(
             T.loadDefaultParameters, data, z, pl), **EM_KW)
         barrier()
         sw = time.perf_counter() - t0
@@ -432,7 +434,7 @@ def main():
             work = float(sum(N * 25.0 * r["numClusters"] * r["iters"] for r in res))
             line["sweep"] = {"solutions": len(res), "wall_s": sw, "value": work / sw, "unit": UNIT, "scaling": "strong",
                              "em_iterations_total": int(sum(r["iters"] for r in res)), "lpt_load_K": [float(x) for x in info["load"]],
-                             "solution_seconds": [round(r["seconds"], 4) for r in res],
+                             "solution_seconds": [round(r["seconds"], 4) for r in res], "solutions_in_flight_per_gpu": a.sweep_concurrent,
                              "note": "ploidy_0 {2,3,4} x numClusters {1..5}: solver creation from host columns, production EM and Viterbi "
                                      "decode per solution (wall clock, barrier to barrier); CUDA context and input generation outside"}
     if not a.no_sharded:
