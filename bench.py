@@ -19,8 +19,8 @@ steps share parameters.
           columns are resident state, uploaded once by titan_solver_create: config.engine.upload_ms and e2e_cold.)
   roofline.frac     : whole-E-step algorithmic bytes (B_alg) / time / measured HBM peak
   roofline.fp64_frac: whole-E-step algorithmic flops (F_alg = 4K + 40) / time / MEASURED DFMA peak
-With N>1 GPUs every rank runs its own solution of the snakemake grid (ploidy_0 in {2,3,4} at numClusters=3) on its own copy
-of the data -- the path's natural shard, no data-path collective: weak scaling.  Two more records ride on the same line:
+With N>1 GPUs every rank runs the same solution shape on its own tumour sample (same generator, seed + 100 rank): independent
+solutions, the path's natural shard, no data-path collective: weak scaling.  Two more records ride on the same line:
   sweep   : the 15-solution ploidy x numClusters sweep strong-scaled over the N ranks (LPT), EM + Viterbi per solution
   sharded : BASELINE configs[3] (2 M SNPs, K = 125) with its chromosomes sharded over the N ranks, the statistics
             all-reduced by NCCL inside the library once per E-step
@@ -76,7 +76,7 @@ def workload_config(a, n_gpus):
                         f"(U=25, K={K}), txnExpLen=1e15, txnZstrength=1 [BASELINE.json configs[1]]",
             "snps": a.snps, "clusters": a.clusters, "K": K, "seed": SEED,
             "step": "one E-step; step i uses the parameters of iteration i mod I of a production EM run on this data",
-            "parallelism": "1 solution per GPU (solution-grid shard)" if n_gpus > 1 else "single solution",
+            "parallelism": "1 solution per GPU (one tumour sample of this shape per rank, seed + 100 rank)" if n_gpus > 1 else "single solution",
             "l2": "working set (alpha + scaled emissions, K x N fp64 each = %.0f MB, streamed) exceeds the 126 MB L2" % (
                 2 * a.snps * K * 8 / 1e6)}
 
@@ -271,10 +271,11 @@ def main():
     T.lib().titan_set_device(local)
 
     Z, K = a.clusters, 25 * a.clusters
-    data, _ = synth.make_data(a.snps, Z=Z, maxCN=8, n_chr=23, seed=SEED)
+    # rank 0 = the named workload; rank r > 0 = another tumour sample of the same shape (same generator, seed + 100 r):
+    # independent solutions, fixed work per GPU, no data-path collective
+    data, _ = synth.make_data(a.snps, Z=Z, maxCN=8, n_chr=23, seed=SEED + 100 * rank)
     N = data["posn"].size
-    # rank r = solution (ploidy_0 = 2, 3, 4, 2, ...; numClusters) of the snakemake grid on its own copy of the data
-    ploidy = PLOIDIES[rank % len(PLOIDIES)]
+    ploidy = 2
     p = production_params(T.loadDefaultParameters, data, Z, ploidy)
     g = p["genotypeParams"]
 
@@ -410,6 +411,8 @@ def main():
     sol.close()
 
     # ---- the two real shards, every N: strong scaling of fixed total work ----
+    if world > 1 and rank > 0 and not a.no_sweep:
+        data, _ = synth.make_data(a.snps, Z=Z, maxCN=8, n_chr=23, seed=SEED)      # the sweep runs on ONE data set: rank 0's
     if not a.no_sweep:
         barrier()
         t0 = time.perf_counter()
@@ -450,14 +453,15 @@ def main():
         ver = comm.nccl_version()
         comm.close()
         its4 = int(cp4["n"].size - 1)
-        est = torch.tensor([cp4["timing"]["estep_ms"]], dtype=torch.float64, device="cuda")
+        est = torch.tensor([cp4["timing"]["estep_ms"], cp4["timing"]["estep_ms"] - cp4["timing"]["reduce_ms"]], dtype=torch.float64,
+                           device="cuda")
         if world > 1:
             dist.all_reduce(est, op=dist.ReduceOp.MAX)
         if rank == 0:
             N4 = data4["posn"].size
             line["sharded"] = {"workload": f"{N4} SNPs, numClusters=5 (K=125), chromosomes LPT-sharded over {world} rank(s), "
                                            f"{its4} EM iterations [BASELINE.json configs[3], U=25 variant]",
-                               "wall_s": sh, "estep_device_ms_max_rank": float(est[0]), "value": N4 * 125.0 * its4 / (float(est[0]) * 1e-3),
+                               "wall_s": sh, "estep_device_ms_max_rank": float(est[0]), "estep_compute_ms_max_rank": float(est[1]), "value": N4 * 125.0 * its4 / (float(est[0]) * 1e-3),
                                "unit": UNIT, "scaling": "strong", "collective": "ncclAllReduce(sum, f64) of %d doubles per E-step, inside titan_estep" % (
                                    6 * 125 + 23 * (1 + 25 + Z4)), "nccl_version": ver, "n": float(cp4["n"][-1]), "loglik": float(cp4["loglik"][-1])}
 

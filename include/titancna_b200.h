@@ -176,6 +176,8 @@ typedef struct titan_em_out {
   int32_t *cd_sweeps;         /* optional [maxiter+1]: coordinate-descent sweeps of each M-step      */
   double estep_ms;            /* OUT: device time spent in E-step kernels (CUDA events)              */
   double mstep_ms;            /* OUT: host time spent in the M-step                                  */
+  double reduce_ms;           /* OUT: part of estep_ms spent in the final reduction and, for a sharded solution, in
+                                 the all-reduce (which includes waiting for the slowest rank)         */
 } titan_em_out;
 
 /* The whole runEMclonalCN loop (binomial allele model, no outlier state): E-steps on the device,

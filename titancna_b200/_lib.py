@@ -66,7 +66,8 @@ class EmOut(C.Structure):
     _fields_ = [("iters", C.c_int32), ("n", c_double_p), ("phi", c_double_p), ("loglik", c_double_p),
                 ("s", c_double_p), ("piZ", c_double_p), ("var", c_double_p), ("piG", c_double_p),
                 ("muR", c_double_p), ("muC", c_double_p), ("rhoG", c_double_p), ("rhoZ", c_double_p),
-                ("cd_sweeps", C.POINTER(C.c_int32)), ("estep_ms", C.c_double), ("mstep_ms", C.c_double)]
+                ("cd_sweeps", C.POINTER(C.c_int32)), ("estep_ms", C.c_double), ("mstep_ms", C.c_double),
+                ("reduce_ms", C.c_double)]
 
 
 class Timing(C.Structure):

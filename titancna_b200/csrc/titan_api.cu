@@ -1502,6 +1502,7 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
   bool converged = false;
   out->estep_ms = 0;
   out->mstep_ms = 0;
+  out->reduce_ms = 0;
   titan_params last_p{};
   bool have_last = false;
   try {
@@ -1518,6 +1519,7 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
       last_p = p;
       have_last = true;
       out->estep_ms += s->tm.last_estep_ms;
+      out->reduce_ms += s->tm.last_reduce_ms;
       double ll = 0;
       for (int c = 0; c < nChr; ++c) ll += llc[c];        // :218 sum over chromosomes
       if (!std::isfinite(ll)) return fail(TITAN_ERR_NUMERIC, "non-finite log-likelihood in EM iteration %d", i);

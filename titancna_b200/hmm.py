@@ -226,7 +226,7 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
                "genotypeParams": g, "ploidyParams": pP, "normalParams": nP, "cellPrevParams": sP,
                "symmetric": g.get("symmetric", True), "cd_sweeps": sweeps[:i].copy()}
         if return_timing:
-            res["timing"] = dict(solver.timing(), estep_ms=out.estep_ms, mstep_ms=out.mstep_ms)
+            res["timing"] = dict(solver.timing(), estep_ms=out.estep_ms, mstep_ms=out.mstep_ms, reduce_ms=out.reduce_ms)
         return res
     finally:
         if own:
