@@ -1,0 +1,22 @@
+"""Cycles per E-step of the 2 M-SNP K = 125 workload (BASELINE configs[3], U = 25 variant): TITAN_TRACE=2 on stderr."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("TITAN_TRACE", "2")
+import numpy as np
+import titancna_b200 as T
+from tests import synth
+import bench
+Z = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
+data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=bench.SEED + 2)
+p = bench.production_params(T.loadDefaultParameters, data, Z, 2.0)
+sol = T.Solver(data, p["genotypeParams"], Z, 1e15, 1.0)
+cp = T.runEMclonalCN(data, p, maxiter=4, verbose=False, solver=sol, return_timing=True, **bench.EM_KW)
+print("estep_ms", cp["timing"]["estep_ms"], "iters", cp["n"].size - 1)
+g = p["genotypeParams"]
+for i in range(cp["n"].size - 1):
+    sol.estep(cp["n"][i], cp["s"][:, i], cp["phi"][i], cp["var"][:, i], cp["piG"][:, i], cp["piZ"][:, i], g)
+    tm = sol.timing()
+    print(i, "estep %.2f = emission %.2f + round0 %.2f + verification %.2f + final %.2f  cycles %d" % (
+        tm["last_estep_ms"], tm["last_emission_ms"], tm["last_fwd_r0_ms"], tm["last_rounds_ms"], tm["last_bwd_r0_ms"], tm["last_fwd_rounds"]))
+sol.close()

@@ -1031,6 +1031,13 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
       i2v[s] = E.M.i2v[gg];
     }
   }
+  // the run's per-SNP records: one coalesced load per warp, then broadcast reads from shared memory (the dependent
+  // global load at the top of every iteration was the kernel's largest stall)
+  __shared__ SnpRec srec[4][kEmRun];
+  if (!FROM_PY) {
+    if (ta + lane < te) srec[threadIdx.x >> 5][lane] = E.snp[ta + lane];
+    __syncwarp();
+  }
 #pragma unroll 2
   for (long long t = ta; t < te; ++t) {
     double v[GS][Z];
@@ -1045,7 +1052,7 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
           mx = fmax(mx, v[s][z]);
         }
     } else {
-      const SnpRec r = E.snp[t];
+      const SnpRec r = srec[threadIdx.x >> 5][(int)(t - ta)];
 #pragma unroll
       for (int s = 0; s < GS; ++s)
 #pragma unroll
