@@ -11,6 +11,8 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
 data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=23, seed=bench.SEED + 2)
 p = bench.production_params(T.loadDefaultParameters, data, Z, 2.0)
 sol = T.Solver(data, p["genotypeParams"], Z, 1e15, 1.0)
+if os.environ.get("CHUNK"):
+    sol.configure(int(os.environ["CHUNK"]), int(os.environ.get("WARM", 192)), 1e-8)
 cp = T.runEMclonalCN(data, p, maxiter=4, verbose=False, solver=sol, return_timing=True, **bench.EM_KW)
 print("estep_ms", cp["timing"]["estep_ms"], "iters", cp["n"].size - 1)
 g = p["genotypeParams"]
