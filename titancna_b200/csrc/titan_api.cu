@@ -162,6 +162,10 @@ struct titan_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t stream2 = nullptr;   // speculative final pass (created on first use)
+  cudaEvent_t ev_spec[2] = {nullptr, nullptr};
+  int spec_final = 1;               // TITAN_SPEC_FINAL
+  DevBuf<unsigned int> ver;         // [2][nChunks] run counters / counters seen by the last final pass
   int64_t N = 0;
   int nChr = 0, U = 0, Z = 0, K = 0, h = 0;
   bool legacy_py = false;          // emissions come from a materialised py matrix
@@ -233,6 +237,9 @@ struct titan_solver {
     if (stream) cudaStreamSynchronize(stream);          // members (device buffers) go back to the pool after this body
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
+    if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+    for (auto &e : ev_spec)
+      if (e) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -270,6 +277,7 @@ static void build_chunks(titan_solver *s) {
   s->extb.alloc(2 * nc * K);
   s->subb.alloc(3 * nc * K);
   s->pflags.alloc(6 * nc);
+  s->ver.alloc(2 * nc);
   s->pints.alloc(10 * nc);
   s->pvec.alloc(8 * nc * K);
   CK(cudaMemset(s->pflags.p, 0, 6 * nc));
@@ -355,6 +363,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
   if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
   if (const char *e = getenv("TITAN_PROBES")) s->probes = atoi(e);
+  if (const char *e = getenv("TITAN_SPEC_FINAL")) s->spec_final = atoi(e);
   if (const char *e = getenv("TITAN_PROBE_WINDOW")) s->probe_window = std::max(0, atoi(e));
   try {
     CK(cudaGetDevice(&s->device));
@@ -746,6 +755,8 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
     A.use_solved = 0;
   }
   A.part = s->part.p;
+  A.final_mode = 0;
+  A.ver = s->ver.p; A.fin_ver = s->ver.p + s->nChunks;
   A.rhoG0 = s->rhoG0.p; A.rhoZ0 = s->rhoZ0.p;
   A.rhoG = (post && !s->legacy_py) ? s->rhoG.p : nullptr;
   A.rhoZ = (post && !s->legacy_py) ? s->rhoZ.p : nullptr;
@@ -753,6 +764,7 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
   cudaStream_t st = s->stream;
   int rounds = 1;
   int64_t runs = 0;
+  bool spec = false, spec_launched_any = false;
   if (!posterior_only) {
     EmArgs E{};
     E.snp = s->snp_p();
@@ -773,6 +785,19 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
     int round = 0;
     unsigned int *ctr_h = s->rerun_h.p;
     const bool probes = s->probes != 0 && K >= 3;
+    // Speculative final pass: the cycles after round 0 are latency-bound (one recursion warp per dirty chunk, most SMs
+    // idle), the final pass is throughput work.  Once the first cycle has decided which chunks it re-runs, every other
+    // chunk gets its final pass on a second stream; a chunk that runs again later bumps its counter and is redone by
+    // the closing pass.  Results are identical: a chunk's final pass depends only on that chunk's own verified inputs.
+    spec = probes && !done && s->spec_final != 0 && !s->legacy_py;
+    if (spec) {
+      if (!s->stream2) CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+      for (auto &e : s->ev_spec)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CK(cudaMemsetAsync(s->ver.p, 0, sizeof(unsigned int) * (size_t)s->nChunks, st));
+      CK(cudaMemsetAsync(s->ver.p + s->nChunks, 0xff, sizeof(unsigned int) * (size_t)s->nChunks, st));
+    }
+    bool &spec_launched = spec_launched_any;
     while (!done) {
       // probe mode: a cycle is boundary test + probe runs, chain solve, one re-run of the dirty chunks (3 launches)
       const int queued = std::max(1, std::min(probes ? std::max(1, s->round_batch / 2) : s->round_batch, hard_cap - round));
@@ -784,6 +809,16 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
           CK(fb2_launch_probe(A, s->Z, st));
           CK(fb2_launch_solve(A, s->Z, st));
           s->tm.kernel_launches += 2;
+          if (spec) {     // this cycle has its re-run set: every other chunk without a valid final pass goes to the second stream
+            CK(cudaEventRecord(s->ev_spec[0], st));
+            CK(cudaStreamWaitEvent(s->stream2, s->ev_spec[0], 0));
+            Fb2Args F = A;
+            F.final_mode = 1;
+            CK(fb2_launch_final(F, s->Z, post, false, s->stream2));
+            CK(cudaEventRecord(s->ev_spec[1], s->stream2));
+            s->tm.kernel_launches++;
+            spec_launched = true;
+          }
         }
         CK(fb2_launch_round(A, s->Z, st));
         s->tm.kernel_launches++;
@@ -809,6 +844,10 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
     CK(cudaEventRecord(s->ev[7], st));
   }
   CK(cudaEventRecord(s->ev[1], st));
+  if (spec_launched_any) {
+    CK(cudaStreamWaitEvent(st, s->ev_spec[1], 0));
+    A.final_mode = 2;                               // closing pass: chunks that ran again since their speculative pass
+  }
   CK(cudaEventRecord(s->ev[8], st));
   CK(fb2_launch_final(A, s->Z, post && !s->legacy_py, s->legacy_py, st));
   CK(cudaEventRecord(s->ev[9], st));

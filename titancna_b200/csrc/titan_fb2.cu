@@ -479,6 +479,7 @@ __device__ __forceinline__ void fb2_forward(const Fb2Args &A, int c, int lane, c
     have_start = false;
   }
   if (lane == 0 && !(A.use_solved && A.round > 0)) atomicAdd(A.rerun + A.round, 1u);
+  if (lane == 0 && A.round > 0) atomicAdd(A.ver + c, 1u);      // a final pass of this chunk started earlier is stale now
 
   const int n_own = ch.t1 - tb;                 // stream positions q < n_own are SNPs tb + q of this chunk
   const bool has_ext = ch.t1 < ch.ce;           // one more step: alpha^ at the first SNP of the next chunk
@@ -586,6 +587,7 @@ __device__ __forceinline__ void fb2_backward(const Fb2Args &A, int c, int lane, 
       for (int z = 0; z < Z; ++z) b[s][z] = L.act[s] ? 1.0 : 0.0;
   }
   if (lane == 0 && !(A.use_solved && A.round > 0)) atomicAdd(A.rerun + A.round, 1u);
+  if (lane == 0 && A.round > 0) atomicAdd(A.ver + c, 1u);
 
   const int n_main = tn - ch.t0;                // steps j < n_main produce beta~ at SNPs tn-1 .. t0
   const bool has_ext = ch.t0 > ch.cs;           // one more step: beta~ at the last SNP of the previous chunk
@@ -866,6 +868,12 @@ template <int Z, int GS, bool WRITE_POST, bool FROM_PY>
 __global__ void __launch_bounds__(32 * kWPC, 3) fb2_final_kernel(Fb2Args A, int TS, int ring_stride) {
   extern __shared__ __align__(128) char fb2_smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
+  unsigned int ver0 = 0;
+  if (A.final_mode != 0) {                    // uniform per CTA
+    ver0 = A.ver[c];
+    if (A.fin_ver[c] == ver0) return;                                                              // an earlier pass is still valid
+    if (A.final_mode == 1 && A.rerun[A.round] != 0 && (A.solvedF[c] | A.solvedB[c])) return;     // re-run in flight right now
+  }
   const Chunk ch = A.chunks[c];
   const int U = A.U, K = A.K;
   LaneInfo<Z, GS> L;
@@ -993,6 +1001,7 @@ __global__ void __launch_bounds__(32 * kWPC, 3) fb2_final_kernel(Fb2Args A, int 
         }
         store_row<Z, GS>(dst + qq * K, acc, L);
       }
+      if (A.final_mode != 0 && lane == 0) A.fin_ver[c] = ver0;
     }
   }
 }

@@ -47,6 +47,12 @@ struct Fb2Args {
   const int *chr_chunk0;       // [nChr+1] first chunk of every chromosome
   int nChr;
   // final pass
+  // final_mode 0: every chunk.  1 (speculative, on a second stream while the verification cycles still run, once per
+  // cycle): every chunk without a valid pass that the current cycle does not re-run; a pass records the chunk's run
+  // counter it started from.  2 (closing): the chunks that ran again since their last pass (or never had one).
+  int final_mode;
+  unsigned int *ver;           // [nChunks] += 1 whenever the chunk runs (either direction) in a round >= 1
+  unsigned int *fin_ver;       // [nChunks] value of ver[c] the last final pass of chunk c started from
   double *part;                // [nChunks][6][K]
   double *rhoG0, *rhoZ0;       // [nChr][U], [nChr][Z]
   double *rhoG, *rhoZ;         // optional [N][U], [N][Z]
