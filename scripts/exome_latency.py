@@ -25,6 +25,13 @@ for mode, N in (("exome", 50000), ("haplotype", 200000)):
     print(f"{mode} N={N}: create {t_create*1e3:.1f} ms; E-step wall {wall*1e3:.3f} ms, device {tm['last_estep_ms']:.3f} ms "
           f"(fwd r0 {tm['last_fwd_r0_ms']:.3f}, bwd r0 {tm['last_bwd_r0_ms']:.3f}, rounds {tm['last_fwd_rounds']}/{tm['last_bwd_rounds']}, "
           f"chunks {tm['n_chunks']}, launches/step {0})", flush=True)
+    for chunk in (512, 256, 128):      # small-N regime: shorter chunks shorten every latency-bound pass
+        sol.configure(chunk, min(192, chunk), 1e-8)
+        for _ in range(3):
+            sol.estep(*args)
+        tm = sol.timing()
+        print(f"   chunk {chunk}: E-step device {tm['last_estep_ms']:.3f} ms, cycles {tm['last_fwd_rounds']}, chunks {tm['n_chunks']}", flush=True)
+    sol.configure(1024, 192, 1e-8)
     t0 = time.perf_counter()
     cp = T.runEMclonalCN(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=20, verbose=False, solver=sol)
     t_em = time.perf_counter() - t0

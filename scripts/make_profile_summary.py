@@ -1,12 +1,12 @@
 """profiles/ summaries from the GPU captures (read here, no GPU):
-  python scripts/make_profile_summary.py <tag> <estep_full.ncu-rep> <launches.csv>
-writes profiles/<tag>_ncu_estep_raw.csv (ncu --page raw of the whole-E-step capture), profiles/<tag>_ncu_summary.json
+  python scripts/make_profile_summary.py <tag> <estep_full.ncu-rep> <launches.csv> [outdir = profiles/]
+writes <outdir>/<tag>_ncu_estep_raw.csv (ncu --page raw of the whole-E-step capture), profiles/<tag>_ncu_summary.json
 (per launch + whole E-step: time, DRAM bytes, pipe / issue / stall counters) and profiles/<tag>_launch_summary.json."""
 import collections, csv, json, os, re, subprocess, sys
 
 tag, rep, launches = sys.argv[1], sys.argv[2], sys.argv[3]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-P = os.path.join(ROOT, "profiles")
+P = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "profiles")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 open(os.path.join(P, f"{tag}_ncu_estep_raw.csv"), "w").write(raw)
 dig = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_digest.py"), rep], capture_output=True, text=True).stdout
@@ -43,7 +43,6 @@ for a in agg.values():
     a["share"] = a["us"] / tot
 json.dump({"total_us": tot, "kernels": collections.OrderedDict(sorted(agg.items(), key=lambda kv: -kv[1]["us"]))},
           open(os.path.join(P, f"{tag}_launch_summary.json"), "w"), indent=1)
-os.replace(launches, launches) if False else None
 print("estep under ncu: %.1f us, %.1f MB DRAM" % (tot_us, tot_b / 1e6))
 for n, a in per.items():
     print(f"  {n:40s} x{a['launches']:2d} {a['us']:8.1f} us {100 * a['share_of_estep']:5.1f} %  {a['dram_bytes'] / 1e6:8.1f} MB")

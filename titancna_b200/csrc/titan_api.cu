@@ -360,6 +360,16 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   // forgetting of the start vector; a longer flat warm-up then saves whole verification cycles (measured at 1 M / 2 M
   // SNPs: Z = 4: 512 beats 192 by 15-20 %, Z = 5: 1024 by 15-25 %; Z <= 3: 192 is best).  titan_solver_configure overrides.
   s->warm = in.Z >= 5 ? 1024 : in.Z == 4 ? 512 : 192;
+  // Chunk length: 1024 SNPs once the genome fills the GPU; below ~300 k SNPs every pass is latency-bound whatever the
+  // chunk count, so shorter chunks shorten every pass (measured: 50 k-SNP exome 1.25 -> 0.58 ms per E-step at 128,
+  // 200 k-SNP haplotype bins 1.40 -> 0.88 ms at 512; 1 M SNPs: 512 and 1024 equal).
+  {
+    const int64_t target = in.N / 300;              // aim for >= 300 chunks
+    int len = 1024;
+    while (len > 128 && len > target) len >>= 1;
+    s->chunk_len = len;
+    s->warm = std::min(s->warm, std::max(192, len));
+  }
   if (const char *e = getenv("TITAN_VIT_MODE")) s->vit_mode = atoi(e);
   if (const char *e = getenv("TITAN_ROUND_BATCH")) s->round_batch = std::max(1, atoi(e));
   if (const char *e = getenv("TITAN_PROBES")) s->probes = atoi(e);
