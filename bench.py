@@ -81,9 +81,9 @@ def workload_config(a, n_gpus):
                 2 * a.snps * K * 8 / 1e6)}
 
 
-def production_params(mod_load, data, Z, ploidy=2.0):
+def production_params(mod_load, data, Z, ploidy=2.0, moments=None):
     """scripts/R_scripts/titanCNA.R:235-247"""
-    p = mod_load(8, Z, data=data)
+    p = mod_load(8, Z, data=data) if moments is None else mod_load(8, Z, data=data, moments=moments)
     K = p["genotypeParams"]["rt"].size
     p["genotypeParams"]["alphaKHyper"] = np.full(K, 10000.0)
     p["genotypeParams"]["betaKHyper"] = np.full(K, 25.0)
@@ -428,9 +428,9 @@ def main():
             return {"iters": int(c["n"].size - 1), "loglik": float(c["loglik"][-1]), "segments": int(1 + np.count_nonzero(np.diff(pth))),
                     "seconds": time.perf_counter() - t1}
 
+        mom = T.dataMoments(data)                  # inside the timed region: computed once per sweep, not once per solution
         res, info = T.run_sweep(data, rank, world, device=local, maxiter=20, run_one=run_one, concurrent=a.sweep_concurrent,
-                                make_params=lambda pl, z: production_params(
-            T.loadDefaultParameters, data, z, pl), **EM_KW)
+                                make_params=lambda pl, z: production_params(T.loadDefaultParameters, data, z, pl, mom), **EM_KW)
         barrier()
         sw = time.perf_counter() - t0
         if rank == 0:

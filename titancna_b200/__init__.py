@@ -4,7 +4,7 @@ Host-side mirror of the reference's R API for the path (same function names):
     loadDefaultParameters, setupClonalParameters, runEMclonalCN, viterbiClonalCN
 over the C ABI in include/titancna_b200.h (titancna_b200/csrc/libtitancna_b200.so).
 """
-from .params import loadDefaultParameters, setupClonalParameters, estimateDirichletParamsMap  # noqa: F401
+from .params import loadDefaultParameters, setupClonalParameters, estimateDirichletParamsMap, dataMoments  # noqa: F401
 from .hmm import (Solver, runEMclonalCN, viterbiClonalCN, fwd_back_clonalCN, viterbi_clonalCN,  # noqa: F401
                   chromosome_offsets)
 from .sweep import runEMclonalCN_sharded, run_sweep, lpt_assign, shard_chromosomes, solution_grid, make_comm  # noqa: F401

@@ -137,22 +137,72 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+// Pinned host staging buffers are a few KB per solver, but cudaMallocHost / cudaFreeHost sporadically take 80-500 ms
+// (page pinning / unpinning; measured in a 15-solution sweep, TITAN_TRACE=1): blocks are recycled through a
+// process-wide cache of power-of-two size classes and only given back at process exit.
+struct PinnedCache {
+  std::mutex mu;
+  std::unordered_map<size_t, std::vector<void *>> free_blocks;      // bytes (power of two >= 4 KB) -> blocks
+  static size_t size_class(size_t bytes) {
+    size_t c = 4096;
+    while (c < bytes) c <<= 1;
+    return c;
+  }
+  void *get(size_t bytes, size_t *cls_out) {
+    const size_t cls = size_class(bytes);
+    *cls_out = cls;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto &v = free_blocks[cls];
+      if (!v.empty()) {
+        void *p = v.back();
+        v.pop_back();
+        return p;
+      }
+    }
+    void *p = nullptr;
+    CK(cudaMallocHost(&p, cls));
+    return p;
+  }
+  void put(void *p, size_t cls) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_blocks[cls].push_back(p);
+  }
+};
+static PinnedCache &pinned_cache() {
+  static PinnedCache *c = new PinnedCache();      // never destroyed: the blocks must outlive every solver
+  return *c;
+}
+
 template <class T>
 struct PinBuf {
   T *p = nullptr;
-  size_t n = 0;
+  size_t n = 0, cls = 0;
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    CK(cudaMallocHost(&p, count * sizeof(T)));
+    p = static_cast<T *>(pinned_cache().get(count * sizeof(T), &cls));
     n = count;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p) pinned_cache().put(p, cls);
     p = nullptr;
     n = 0;
   }
   ~PinBuf() { release(); }
+};
+
+// TITAN_TRACE=1: wall-clock phases of solver creation and destruction on stderr
+struct PhaseTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTrace() : on(getenv("TITAN_TRACE") && atoi(getenv("TITAN_TRACE"))), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[titan trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
 };
 
 static const int kMaxZ = 8;
@@ -233,14 +283,21 @@ struct titan_solver {
   titan_timing tm{};
 
   ~titan_solver() {
+    PhaseTrace tr;
     if (vit_builder.joinable()) vit_builder.join();
+    tr.mark("destroy: join table builder");
     if (stream) cudaStreamSynchronize(stream);          // members (device buffers) go back to the pool after this body
+    if (stream2) cudaStreamSynchronize(stream2);
+    tr.mark("destroy: stream sync");
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
-    if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
     for (auto &e : ev_spec)
       if (e) cudaEventDestroy(e);
+    if (stream2) cudaStreamDestroy(stream2);
     if (own_stream && stream) cudaStreamDestroy(stream);
+    tr.mark("destroy: events + streams");
+    model_h.release(); out_h.release(); rerun_h.release();
+    tr.mark("destroy: pinned host buffers");
   }
 };
 
@@ -306,18 +363,6 @@ struct SolverInit {
   int nZS;
 };
 
-// TITAN_TRACE=1: wall-clock phases of solver creation on stderr
-struct PhaseTrace {
-  bool on;
-  std::chrono::steady_clock::time_point t0;
-  PhaseTrace() : on(getenv("TITAN_TRACE") && atoi(getenv("TITAN_TRACE"))), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char *what) {
-    if (!on) return;
-    const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[titan trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
 
 static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   PhaseTrace trace;
@@ -561,9 +606,11 @@ extern "C" int titan_solver_create(const titan_data_desc *d, titan_solver **out)
 }
 
 extern "C" void titan_solver_destroy(titan_solver *s) {
+  PhaseTrace tr_all;
   if (!s) return;
   cudaSetDevice(s->device);
   delete s;
+  tr_all.mark("destroy: total (device buffers last)");
 }
 
 extern "C" int titan_solver_shape(const titan_solver *s, int64_t *N, int32_t *nChr, int32_t *U, int32_t *Z) {

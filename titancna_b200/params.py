@@ -38,10 +38,24 @@ def _symmetric_table(rn, max_copies=8):
     return np.array(rt, dtype=np.float64), np.array(ct, dtype=np.float64), np.array(balanced)
 
 
+def dataMoments(data):
+    """The data-dependent numbers loadDefaultParameters derives (R/utils.R:32-40,80-95): median and variance of the allelic
+    ratio, variance of logR, their correlation.  O(N) with a sort: a sweep over (ploidy, numClusters) computes them once
+    and hands them to every loadDefaultParameters(..., moments=) call instead of 15 times."""
+    ref, depth, logR = (np.asarray(data[k], float) for k in ("ref", "tumDepth", "logR"))
+    ar = ref / depth
+    return {"hetARshift": float(np.nanmedian(ar)),
+            "corRho_0": float(np.corrcoef(ar, logR)[0, 1]) if ref.size > 0 and logR.size > 0 else None,
+            "var_logR": float(np.var(logR, ddof=1)), "var_ar": float(np.nanvar(ar, ddof=1))}
+
+
 def loadDefaultParameters(copyNumber=5, numberClonalClusters=1, skew=0, hetBaselineSkew=None,
-                          alleleEmissionModel="binomial", symmetric=True, data=None, extendedTable=False):
+                          alleleEmissionModel="binomial", symmetric=True, data=None, extendedTable=False, moments=None):
     """R/utils.R:7-148.  `data` (optional) is a dict with ref, tumDepth, logR.
-    `extendedTable=True` (no R counterpart) lifts the reference's limit of 8 copies to 10: 36 genotype states."""
+    `extendedTable=True` (no R counterpart) lifts the reference's limit of 8 copies to 10: 36 genotype states.
+    `moments=dataMoments(data)` (no R counterpart) reuses the data-dependent numbers across calls."""
+    if data is not None and moments is None:
+        moments = dataMoments(data)
     if copyNumber < 3 or copyNumber > (10 if extendedTable else 8):
         raise ValueError("loadDefaultParameters: Fewer than 3 or more than 8 copies are \n             "
                          "being specified. Please use minimum 3 or maximum 8 'copyNumber'.")
@@ -55,7 +69,7 @@ def loadDefaultParameters(copyNumber=5, numberClonalClusters=1, skew=0, hetBasel
     if hetBaselineSkew is not None:
         hetARshift = hetBaselineSkew + 0.5
     elif data is not None:
-        hetARshift = float(np.nanmedian(np.asarray(data["ref"], float) / np.asarray(data["tumDepth"], float)))
+        hetARshift = moments["hetARshift"]
     else:
         hetARshift = 0.55
     rt[hetState - 1] = hetARshift
@@ -70,13 +84,12 @@ def loadDefaultParameters(copyNumber=5, numberClonalClusters=1, skew=0, hetBasel
     corRho_0 = None
     have_data = data is not None
     if have_data and len(data.get("ref", ())) > 0 and len(data.get("logR", ())) > 0:
-        ar = np.asarray(data["ref"], float) / np.asarray(data["tumDepth"], float)
-        corRho_0 = float(np.corrcoef(ar, np.asarray(data["logR"], float))[0, 1])
+        corRho_0 = moments["corRho_0"]
     if have_data:
         betaK = 25.0
-        alphaK = betaK / float(np.var(np.asarray(data["logR"], float), ddof=1))
+        alphaK = betaK / moments["var_logR"]
         betaR = 25.0
-        alphaR = betaR / float(np.nanvar(np.asarray(data["ref"], float) / np.asarray(data["tumDepth"], float), ddof=1))
+        alphaR = betaR / moments["var_ar"]
     else:
         alphaK, betaK, alphaR, betaR = 10000.0, 25.0, 10000.0, 25.0
     genotypeParams = {

@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 from ._lib import c_double_p, check, lib
 from .hmm import Solver, _check_params, _hyper, chromosome_offsets, runEMclonalCN, viterbiClonalCN
-from .params import loadDefaultParameters
+from .params import dataMoments, loadDefaultParameters
 from .results import correctIntegerCN, outputTitanResults, outputTitanSegments
 from .selection import outputModelParameters, selectSolution
 
@@ -206,8 +206,10 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
     where, load = lpt_assign(costs, world)
     mine = [grid[i] for i in range(len(grid)) if where[i] == rank]
     if make_params is None:
+        moments = dataMoments(data)          # the data-dependent defaults once, not once per solution
+
         def make_params(ploidy, Z):
-            p = loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z, data=data)
+            p = loadDefaultParameters(copyNumber=maxCN, numberClonalClusters=Z, data=data, moments=moments)
             p["ploidyParams"]["phi_0"] = float(ploidy)
             return p
     if run_one is None:
