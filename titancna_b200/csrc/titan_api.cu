@@ -208,6 +208,52 @@ struct PhaseTrace {
 static const int kMaxZ = 8;
 static const int kRoundSlots = 4096;
 
+// Host-exact, parameter-independent transition terms of one data set (positions + txnExpLen + zStrength).  A sweep
+// creates one solver per (ploidy, numClusters) on the SAME positions, and hashing a million gap lengths costs more
+// than everything else in solver creation (27 of ~45 ms): the tables of the most recent data sets are kept and
+// shared, keyed on a 64-bit hash of the position column.
+struct GapTables {
+  std::vector<double> rhoG_h, rhoZ_h;   // [N] host-exact transition terms between t-1 and t
+  std::vector<double> pairG, pairZ;     // the distinct (rhoG, rhoZ) pairs of this data set
+  std::vector<int> pair_id;             // [N] which pair sits between SNP t-1 and t
+};
+struct GapKey {
+  int64_t N = 0;
+  int nChr = 0;
+  double txn = 0, zs = 0;
+  uint64_t hpos = 0, hchr = 0;
+  bool operator==(const GapKey &o) const {
+    return N == o.N && nChr == o.nChr && txn == o.txn && zs == o.zs && hpos == o.hpos && hchr == o.hchr;
+  }
+};
+static uint64_t hash_words(const void *p, size_t n_words, uint64_t h) {
+  const uint64_t *w = static_cast<const uint64_t *>(p);
+  for (size_t i = 0; i < n_words; ++i) {
+    h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+  }
+  return h;
+}
+struct GapCache {
+  std::mutex mu;
+  std::vector<std::pair<GapKey, std::shared_ptr<const GapTables>>> recent;     // newest last, at most 4
+  std::shared_ptr<const GapTables> find(const GapKey &k) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : recent)
+      if (e.first == k) return e.second;
+    return nullptr;
+  }
+  void put(const GapKey &k, std::shared_ptr<const GapTables> v) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (recent.size() >= 4) recent.erase(recent.begin());
+    recent.emplace_back(k, std::move(v));
+  }
+};
+static GapCache &gap_cache() {
+  static GapCache *c = new GapCache();
+  return *c;
+}
+
 struct titan_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -221,9 +267,7 @@ struct titan_solver {
   bool legacy_py = false;          // emissions come from a materialised py matrix
   std::vector<int64_t> chr_start;
   std::vector<unsigned char> het;
-  std::vector<double> rhoG_h, rhoZ_h;   // host-exact transition terms between t-1 and t
-  std::vector<double> pairG, pairZ;     // the distinct (rhoG, rhoZ) pairs of this data set
-  std::vector<int> pair_id;             // [N] which pair sits between SNP t-1 and t
+  std::shared_ptr<const GapTables> gaps;   // host-exact transition terms of this data set (shared between solvers)
 
   // configuration
   int chunk_len = 1024, warm = 192, max_rounds = 0;   // max_rounds 0: bounded by the chunk count (titan_solver_configure)
@@ -477,10 +521,17 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     // host-exact transition terms (parameter independent).  exp() is evaluated once per DISTINCT gap
     // length (an open-addressing table keyed on the gap's bit pattern), then gaps that round to the
     // same (rhoG, rhoZ) pair are merged: the Viterbi tables are built per distinct pair.
-    s->rhoG_h.assign(N, 1.0);
-    s->rhoZ_h.assign(N, 1.0);
-    s->pair_id.assign(N, 0);
-    {
+    GapKey gkey;
+    gkey.N = N; gkey.nChr = in.nChr; gkey.txn = in.txnExpLen; gkey.zs = in.zStrength;
+    gkey.hpos = hash_words(in.posn, (size_t)N, 1);
+    gkey.hchr = hash_words(in.chr_start, (size_t)in.nChr + 1, 2);
+    s->gaps = gap_cache().find(gkey);
+    if (!s->gaps) {
+      std::shared_ptr<GapTables> G = std::make_shared<GapTables>();
+      G->rhoG_h.assign(N, 1.0);
+      G->rhoZ_h.assign(N, 1.0);
+      G->pair_id.assign(N, 0);
+      {
       size_t cap = 1;
       int lg = 0;
       while (cap < (size_t)std::max<int64_t>(1024, N / 4)) { cap <<= 1; ++lg; }
@@ -514,9 +565,9 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
             auto pk = std::make_pair(th::bits_of(rG), th::bits_of(rZ));
             auto it = pairs.find(pk);
             if (it == pairs.end()) {
-              it = pairs.emplace(pk, (int)s->pairG.size()).first;
-              s->pairG.push_back(rG);
-              s->pairZ.push_back(rZ);
+              it = pairs.emplace(pk, (int)G->pairG.size()).first;
+              G->pairG.push_back(rG);
+              G->pairZ.push_back(rZ);
             }
             keys[h] = key; vals[h] = it->second;
             if (++used * 2 > cap) {
@@ -526,18 +577,21 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
             }
           }
           const int id = vals[h];
-          s->pair_id[t] = id;
-          s->rhoG_h[t] = s->pairG[id];
-          s->rhoZ_h[t] = s->pairZ[id];
+          G->pair_id[t] = id;
+          G->rhoG_h[t] = G->pairG[id];
+          G->rhoZ_h[t] = G->pairZ[id];
         }
+    }
+      s->gaps = G;
+      gap_cache().put(gkey, s->gaps);
     }
     trace.mark("distinct gaps (host exp)");
     {
       DevBuf<double> dG, dZ;
       dG.alloc(N); dZ.alloc(N);
       trace.mark("  rho alloc");
-      CK(cudaMemcpy(dG.p, s->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(dZ.p, s->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dG.p, s->gaps->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dZ.p, s->gaps->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       trace.mark("  rho memcpy");
       s->txn.alloc(N + 2 * kFbPadRows);
       CK(cudaMemsetAsync(s->txn.p, 0, sizeof(TxnRec) * (N + 2 * kFbPadRows), s->stream));
@@ -1043,14 +1097,14 @@ static void launch_backtrace(const VitArgs &A, int nTiles, cudaStream_t st) {
 // the background at solver creation and joined by the first decode.
 static void build_viterbi_tables(titan_solver *s) {
   const int K = s->K;
-  const size_t np = std::max<size_t>(1, s->pairG.size());
+  const size_t np = std::max<size_t>(1, s->gaps->pairG.size());
   s->vit_tab.assign(np * 4 * (size_t)K, 0.0);
-  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->pairG.size() + 255) / 256)));
+  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->gaps->pairG.size() + 255) / 256)));
   std::vector<std::thread> pool;
   for (unsigned w = 0; w < nt; ++w)
     pool.emplace_back([s, w, nt, K]() {
-      for (size_t q = w; q < s->pairG.size(); q += nt)
-        th::viterbi_log_table(K, s->U, s->het.data(), s->pairG[q], s->pairZ[q], s->vit_tab.data() + q * 4 * (size_t)K);
+      for (size_t q = w; q < s->gaps->pairG.size(); q += nt)
+        th::viterbi_log_table(K, s->U, s->het.data(), s->gaps->pairG[q], s->gaps->pairZ[q], s->vit_tab.data() + q * 4 * (size_t)K);
     });
   for (auto &t : pool) t.join();
 }
@@ -1067,7 +1121,7 @@ static int viterbi_prepare(titan_solver *s) {
   if (s->vit_builder.joinable()) s->vit_builder.join();
   if (s->vit_tab.empty()) build_viterbi_tables(s);
   const std::vector<double> &tab = s->vit_tab;
-  const std::vector<int> &id = s->pair_id;
+  const std::vector<int> &id = s->gaps->pair_id;
   // the warp-reduction kernel relies on: same-genotype classes never below the other-genotype classes of the same row
   s->vit_monotone = true;
   for (size_t r = 0; r + 3 < tab.size() && s->vit_monotone; r += 4)
