@@ -342,6 +342,12 @@ def main():
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, wall_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    rank_ms = [dev_ms / a.steps if world == 1 else None]
+    if world > 1:      # every rank's own device time per step: shows whether ranks slow each other down or merely differ
+        mine = torch.tensor([float(np.sum(phases["last_estep_ms"])) / a.steps], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [float(x[0]) for x in allr]
     units = float(N) * K * a.steps * world
     value = units / (dev_ms * 1e-3)
     e2e_value = units / (wall_ms * 1e-3)
@@ -375,7 +381,7 @@ def main():
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
             "engine": {"upload_ms": upload_ms, "chunks": sol.timing()["n_chunks"], "em_iterations": I,
-                       "cycles_per_step": [int(x) for x in phases["last_fwd_rounds"]], "ploidy_0": ploidy,
+                       "cycles_per_step": [int(x) for x in phases["last_fwd_rounds"]], "rank_ms_per_step": rank_ms,
                        "parity_guard": {"loglik_rel": ll_rel, "sums_err_over_scale": st_rel, "against": "sequential recursion, same kernels, one chunk per chromosome"}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (5 * K + 3 * 25) * 8,
