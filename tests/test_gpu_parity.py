@@ -586,11 +586,12 @@ def test_fused_r_glue_returns_the_runEMclonalCN_list_and_an_int_path():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("chunk,warm", [(400, 128), (0, 1)])
-def test_config4_as_named_36_genotype_states_k180(chunk, warm):
+@pytest.mark.parametrize("chunk,warm,vit_mode", [(400, 128, "-1"), (0, 1, "0"), (400, 128, "4")])
+def test_config4_as_named_36_genotype_states_k180(chunk, warm, vit_mode, monkeypatch):
     """BASELINE configs[3] as written: maxCN = 10 -> the 36-state genotype table (two genotypes per lane in the
     forward-backward kernels), numClusters = 5, K = 180.  The reference's C is generic in K, so its port referees the
     E-step (log-likelihoods, posteriors, the six sums) and the Viterbi path bit for bit."""
+    monkeypatch.setenv("TITAN_VIT_MODE", vit_mode)      # auto = warp-reduction kernel with two genotypes per lane; 0 = dense scan
     N, Z = 2400, 5
     data, _ = synth.make_data(N, Z=Z, maxCN=8, n_chr=2, seed=41, mean_seg=200)
     p = T.loadDefaultParameters(copyNumber=10, numberClonalClusters=Z, extendedTable=True)

@@ -1210,11 +1210,16 @@ static void launch_vit_cluster(const VitArgs &A, int nChr, cudaStream_t st) {
   }
 }
 
+template <int Z, int GS>
+static void launch_vit_redux_zg(const VitArgs &A, int nChr, cudaStream_t st) {
+  const size_t smem = 16 * (size_t)(2 * 2 * Z * 32 * GS) + sizeof(double) * (size_t)(A.K + 2) + VitRing::bytes(A.K);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_redux_kernel<Z, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  viterbi_redux_kernel<Z, GS><<<nChr, 32 * (Z + 1), smem, st>>>(A);
+}
 template <int Z>
 static void launch_vit_redux_z(const VitArgs &A, int nChr, cudaStream_t st) {
-  const size_t smem = 16 * (size_t)(2 * 2 * Z * 32) + sizeof(double) * (size_t)(A.K + 2) + VitRing::bytes(A.K);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(viterbi_redux_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  viterbi_redux_kernel<Z><<<nChr, 32 * (Z + 1), smem, st>>>(A);
+  if (A.U > 32) launch_vit_redux_zg<Z, 2>(A, nChr, st);
+  else launch_vit_redux_zg<Z, 1>(A, nChr, st);
 }
 
 static void launch_vit_redux(const VitArgs &A, int nChr, cudaStream_t st) {
@@ -1269,14 +1274,14 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   // 4: warp-reduction scan, 3: cluster-sliced scan, 2: register-sliced dense scan (all one barrier per SNP, emissions
   // materialised first), 0: shared-memory dense scan (any K <= 256, any class matrix)
   const bool cluster_ok = s->U <= 32 && s->Z <= 8;
-  const bool redux_ok = cluster_ok && s->vit_monotone;
+  const bool redux_ok = s->U <= 64 && s->Z <= 8 && s->vit_monotone;
   int mode = s->vit_mode;
   if (mode < 0) {   // measured on B200 (1 M SNPs, 23 chromosomes)
     if (redux_ok) mode = 4;
     else if (cluster_ok && (s->Z <= kVitClusterAutoMaxZ || !fast_ok)) mode = 3;
     else mode = fast_ok ? 2 : 0;
   }
-  if (mode == 4 && !redux_ok) mode = 3;
+  if (mode == 4 && !redux_ok) mode = cluster_ok ? 3 : 2;
   if (mode == 3 && !cluster_ok) mode = 2;
   if (mode == 2 && !fast_ok) mode = 0;
   if (mode >= 2) {

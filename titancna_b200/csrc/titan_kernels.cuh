@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(32 * Z * H) viterbi_cluster_kernel(VitArgs A) 
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-reduction Viterbi step (default for U <= 32): the slice scan of viterbi_cluster_kernel without the scan.
+// Warp-reduction Viterbi step (default for U <= 64): the slice scan of viterbi_cluster_kernel without the scan.
 //
 // Warp z' holds cluster z' with lane = SOURCE genotype g': every lane keeps the four class values of its own state
 // in registers.  What a destination of genotype g can take from warp z' is
@@ -741,26 +741,29 @@ __device__ __forceinline__ void warp_argmax_key(unsigned hi, unsigned lo, double
   mv = f64_unkey(mh, ml);
 }
 
-template <int Z>
+// GS = 2 serves tables of 33..64 genotypes: lane l owns genotypes l and l + 32 of its cluster.  Source indices order as
+// (slot, lane), so a tie between candidates goes to slot 0 first, then to the lowest lane.
+template <int Z, int GS>
 __global__ void __launch_bounds__(32 * (Z + 1)) viterbi_redux_kernel(VitArgs A) {
   extern __shared__ __align__(16) unsigned char vr_sm[];
   constexpr int D = 4;                      // unroll of the step loop; even: the exchange parity of a step is static
-  VCand *xch = reinterpret_cast<VCand *>(vr_sm);                             // [2 parity][2 X/Y][Z][32]
-  double *dfin = reinterpret_cast<double *>(xch + 2 * 2 * Z * 32);           // [K]
+  constexpr int ROW = 32 * GS;              // entries per exchange row
+  VCand *xch = reinterpret_cast<VCand *>(vr_sm);                             // [2 parity][2 X/Y][Z][ROW]
+  double *dfin = reinterpret_cast<double *>(xch + 2 * 2 * Z * ROW);          // [K]
   VitRing ring;
   ring.carve(dfin + ((A.K + 1) & ~1), A.K);
   const int K = A.K, U = A.U, K4 = 4 * A.K;
   const int chr = blockIdx.x;
   const int cs = A.chr_start[chr], ce = A.chr_start[chr + 1];
   if (cs >= ce) return;
-  const int warp = threadIdx.x >> 5, g = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int last = ce - 1;
   if (warp == Z) {
     // ---- feeder warp: keeps the ring DV steps ahead for every state (lane l serves states l, l+32, ...) ----
     for (int u = 0; u < DV; ++u) {
       const int s = cs + 1 + u;
       const int rid = A.txn_id[min(s + 1, last)];
-      for (int j = g; j < K; j += 32) {
+      for (int j = lane; j < K; j += 32) {
         const int sc = min(s, last);
         cp_async<8>(ring.e + u * K + j, A.py + (size_t)sc * K + j);
         const double *row = A.ltab + (size_t)rid * 4 * K + (size_t)j * 4;
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(32 * (Z + 1)) viterbi_redux_kernel(VitArgs A) 
       const int s = tt + DV, slot = (s - cs - 1) & (RV - 1);
       const int rid = rid_next;
       rid_next = A.txn_id[min(s + 2, last)];
-      for (int j = g; j < K; j += 32) {
+      for (int j = lane; j < K; j += 32) {
         const int sc = min(s, last);
         cp_async<8>(ring.e + slot * K + j, A.py + (size_t)sc * K + j);
         const double *row = A.ltab + (size_t)rid * 4 * K + (size_t)j * 4;
@@ -793,37 +796,43 @@ __global__ void __launch_bounds__(32 * (Z + 1)) viterbi_redux_kernel(VitArgs A) 
     return;
   }
   const int zs = warp;
-  const bool on = g < U;
-  const int j = on ? g + zs * U : 0;        // this lane's state: source (g, zs) and destination (g, zs)
-  const bool het = on && A.het[g];
   const int ibase = zs * U;
-  // gather addresses: row (z') of X or Y that applies to destination cluster zs
-  unsigned gadr[Z];
+  bool on[GS], het[GS];
+  int g[GS], j[GS];
+  unsigned gadr[GS][Z];         // gather addresses: row (z') of X or Y that applies to destination (g, zs)
   {
     const unsigned xbase = (unsigned)__cvta_generic_to_shared(xch);
 #pragma unroll
-    for (int w = 0; w < Z; ++w) {
-      const int sel = (w == zs || het) ? 1 : 0;
-      gadr[w] = xbase + 16u * (unsigned)((sel * Z + w) * 32 + g);
+    for (int s = 0; s < GS; ++s) {
+      g[s] = lane + 32 * s;
+      on[s] = g[s] < U;
+      j[s] = on[s] ? g[s] + zs * U : 0;        // this slot's state: source (g, zs) and destination (g, zs)
+      het[s] = on[s] && A.het[g[s]];
+#pragma unroll
+      for (int w = 0; w < Z; ++w) {
+        const int sel = (w == zs || het[s]) ? 1 : 0;
+        gadr[s][w] = xbase + 16u * (unsigned)((sel * Z + w) * ROW + g[s]);
+      }
     }
   }
-  constexpr unsigned XPAR = 16u * 2 * Z * 32;     // bytes between the two exchange parities
-  VCand *xmine = xch + zs * 32 + g;               // parity 0, X; Y sits Z*32 entries further
-  double v0, v1, v2, v3;
+  constexpr unsigned XPAR = 16u * 2 * Z * ROW;    // bytes between the two exchange parities
+  VCand *xmine = xch + zs * ROW + lane;           // parity 0, X, slot 0; slot 1 sits 32 entries further, Y sits Z*ROW further
+  double v0[GS], v1[GS], v2[GS], v3[GS];
   // ---- t = cs ----
-  {
+#pragma unroll
+  for (int s = 0; s < GS; ++s) {
     double d0 = -CUDART_INF;
     double2 a = make_double2(0, 0), b = make_double2(0, 0);
-    if (on) {
-      d0 = __dadd_rn(A.M.logpi[j], A.py[(size_t)cs * K + j]);
+    if (on[s]) {
+      d0 = __dadd_rn(A.M.logpi[j[s]], A.py[(size_t)cs * K + j[s]]);
       if (cs + 1 < ce) {
-        const double2 *row = reinterpret_cast<const double2 *>(A.ltab + (size_t)j * 4 + (size_t)A.txn_id[cs + 1] * K4);
+        const double2 *row = reinterpret_cast<const double2 *>(A.ltab + (size_t)j[s] * 4 + (size_t)A.txn_id[cs + 1] * K4);
         a = row[0]; b = row[1];
       }
-      A.psi[(size_t)cs * K + j] = 0;
-      dfin[j] = d0;
+      A.psi[(size_t)cs * K + j[s]] = 0;
+      dfin[j[s]] = d0;
     }
-    v0 = __dadd_rn(d0, a.x); v1 = __dadd_rn(d0, a.y); v2 = __dadd_rn(d0, b.x); v3 = __dadd_rn(d0, b.y);
+    v0[s] = __dadd_rn(d0, a.x); v1[s] = __dadd_rn(d0, a.y); v2[s] = __dadd_rn(d0, b.x); v3[s] = __dadd_rn(d0, b.y);
   }
   __syncthreads();
   for (int t = cs + 1; t < ce; t += D) {
@@ -832,45 +841,78 @@ __global__ void __launch_bounds__(32 * (Z + 1)) viterbi_redux_kernel(VitArgs A) 
       const int tt = t + u;
       if (tt >= ce) break;
       // ---- warp-wide first-index maxima of the two other-genotype classes ----
-      unsigned h0, l0, h1, l1;
-      f64_key(v0, h0, l0);
-      f64_key(v1, h1, l1);
-      if (!on) { h0 = l0 = h1 = l1 = 0u; }
       double m0, m1;
       int a0, a1;
-      warp_argmax_key(h0, l0, m0, a0);
-      warp_argmax_key(h1, l1, m1, a1);
+      {
+        unsigned h0, l0, h1, l1;
+        f64_key(v0[0], h0, l0);
+        f64_key(v1[0], h1, l1);
+        if (!on[0]) { h0 = l0 = h1 = l1 = 0u; }
+        int s0 = 0, s1 = 0;                  // slot of this lane's best candidate (slot 0 wins ties: lower index)
+        if (GS > 1) {
+          unsigned h, l;
+          f64_key(v0[GS - 1], h, l);
+          if (on[GS - 1] && (h > h0 || (h == h0 && l > l0))) { h0 = h; l0 = l; s0 = 1; }
+          f64_key(v1[GS - 1], h, l);
+          if (on[GS - 1] && (h > h1 || (h == h1 && l > l1))) { h1 = h; l1 = l; s1 = 1; }
+        }
+        if (GS == 1) {
+          warp_argmax_key(h0, l0, m0, a0);
+          warp_argmax_key(h1, l1, m1, a1);
+        } else {
+          const unsigned mh0 = __reduce_max_sync(0xffffffffu, h0);
+          const bool p0 = h0 == mh0;
+          const unsigned ml0 = __reduce_max_sync(0xffffffffu, p0 ? l0 : 0u);
+          const bool q0 = p0 && l0 == ml0;
+          const unsigned w00 = __ballot_sync(0xffffffffu, q0 && s0 == 0), w01 = __ballot_sync(0xffffffffu, q0);
+          a0 = w00 ? __ffs((int)w00) - 1 : __ffs((int)w01) - 1 + 32;
+          m0 = f64_unkey(mh0, ml0);
+          const unsigned mh1 = __reduce_max_sync(0xffffffffu, h1);
+          const bool p1 = h1 == mh1;
+          const unsigned ml1 = __reduce_max_sync(0xffffffffu, p1 ? l1 : 0u);
+          const bool q1 = p1 && l1 == ml1;
+          const unsigned w10 = __ballot_sync(0xffffffffu, q1 && s1 == 0), w11 = __ballot_sync(0xffffffffu, q1);
+          a1 = w10 ? __ffs((int)w10) - 1 : __ffs((int)w11) - 1 + 32;
+          m1 = f64_unkey(mh1, ml1);
+        }
+      }
       // own-genotype substitution: v2 / v3 at index g against the maximum at index a
-      const bool tx = (v2 > m0) || (v2 == m0 && g < a0);
-      const bool ty = (v3 > m1) || (v3 == m1 && g < a1);
-      VCand cx, cy;
-      cx.v = tx ? v2 : m0; cx.i = ibase + (tx ? g : a0); cx.pad = 0;
-      cy.v = ty ? v3 : m1; cy.i = ibase + (ty ? g : a1); cy.pad = 0;
-      VCand *xo = xmine + ((u & 1) ? 2 * Z * 32 : 0);
-      xo[0] = cx;
-      xo[Z * 32] = cy;
+      VCand *xo = xmine + ((u & 1) ? 2 * Z * ROW : 0);
+#pragma unroll
+      for (int s = 0; s < GS; ++s) {
+        const bool tx = (v2[s] > m0) || (v2[s] == m0 && g[s] < a0);
+        const bool ty = (v3[s] > m1) || (v3[s] == m1 && g[s] < a1);
+        VCand cx, cy;
+        cx.v = tx ? v2[s] : m0; cx.i = ibase + (tx ? g[s] : a0); cx.pad = 0;
+        cy.v = ty ? v3[s] : m1; cy.i = ibase + (ty ? g[s] : a1); cy.pad = 0;
+        xo[32 * s] = cx;
+        xo[Z * ROW + 32 * s] = cy;
+      }
       __syncthreads();
       // ---- gather over the Z clusters, in source order ----
-      double gv[Z];
-      int gi[Z];
-#pragma unroll
-      for (int w = 0; w < Z; ++w) {
-        double ip;
-        lds_v2f64(gadr[w] + ((u & 1) ? XPAR : 0u), gv[w], ip);
-        gi[w] = __double2loint(ip);
-      }
       const int slot = (tt - cs - 1) & (RV - 1);
-      const double e_u = ring.e[slot * K + j];
-      const double2 *rl = reinterpret_cast<const double2 *>(ring.L + ((size_t)slot * K + j) * 4);
-      const double2 la_u = rl[0], lb_u = rl[1];
-      double best;
-      int arg;
-      PairTree<0, Z>::run(gv, gi, best, arg);
-      const double d = on ? __dadd_rn(best, e_u) : -CUDART_INF;
-      v0 = __dadd_rn(d, la_u.x); v1 = __dadd_rn(d, la_u.y); v2 = __dadd_rn(d, lb_u.x); v3 = __dadd_rn(d, lb_u.y);
-      if (on) {
-        A.psi[(size_t)tt * K + j] = (unsigned char)arg;
-        if (tt == last) dfin[j] = d;
+#pragma unroll
+      for (int s = 0; s < GS; ++s) {
+        double gv[Z];
+        int gi[Z];
+#pragma unroll
+        for (int w = 0; w < Z; ++w) {
+          double ip;
+          lds_v2f64(gadr[s][w] + ((u & 1) ? XPAR : 0u), gv[w], ip);
+          gi[w] = __double2loint(ip);
+        }
+        const double e_u = ring.e[slot * K + j[s]];
+        const double2 *rl = reinterpret_cast<const double2 *>(ring.L + ((size_t)slot * K + j[s]) * 4);
+        const double2 la_u = rl[0], lb_u = rl[1];
+        double best;
+        int arg;
+        PairTree<0, Z>::run(gv, gi, best, arg);
+        const double d = on[s] ? __dadd_rn(best, e_u) : -CUDART_INF;
+        v0[s] = __dadd_rn(d, la_u.x); v1[s] = __dadd_rn(d, la_u.y); v2[s] = __dadd_rn(d, lb_u.x); v3[s] = __dadd_rn(d, lb_u.y);
+        if (on[s]) {
+          A.psi[(size_t)tt * K + j[s]] = (unsigned char)arg;
+          if (tt == last) dfin[j[s]] = d;
+        }
       }
     }
   }
