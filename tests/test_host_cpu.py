@@ -164,3 +164,70 @@ def test_r_glue_registers_the_reference_call_table():
     if T.device_count() == 0:
         with pytest.raises(refshim.RError, match="CUDA"):
             glue.fwd_back(np.zeros(4), np.zeros((4, 5)), np.zeros(2), np.array([0.0, -1.0]), 2, np.arange(5.0), 1e15, 1e15)
+
+
+def test_data_moments_reuse_gives_identical_parameters():
+    """loadDefaultParameters(moments=dataMoments(data)) -- what the sweep does once per data set -- equals the
+    per-call computation (R/utils.R:32-40,80-95) bit for bit."""
+    rng = np.random.default_rng(3)
+    data = {"ref": rng.integers(10, 40, 500).astype(float), "tumDepth": np.full(500, 45.0), "logR": rng.normal(0, 0.2, 500)}
+    m = T.dataMoments(data)
+    for Z in (1, 4):
+        a = T.loadDefaultParameters(8, Z, data=data)
+        b = T.loadDefaultParameters(8, Z, data=data, moments=m)
+        for grp in a:
+            for k, v in a[grp].items():
+                assert np.array_equal(np.asarray(v, dtype=object), np.asarray(b[grp][k], dtype=object)), (grp, k)
+
+
+def test_extended_genotype_table_is_opt_in():
+    """BASELINE configs[3] as named needs maxCN = 10: the reference's limit (R/utils.R:9-12) stays the default."""
+    with pytest.raises(ValueError, match="more than 8 copies"):
+        T.loadDefaultParameters(copyNumber=10, numberClonalClusters=5)
+    g = T.loadDefaultParameters(copyNumber=10, numberClonalClusters=5, extendedTable=True)["genotypeParams"]
+    assert g["rt"].size == 36 and g["ct"].tolist().count(9) == 5 and g["ct"].tolist().count(10) == 6
+    assert np.allclose(g["rt"][25:30], [1, 8 / 9, 7 / 9, 6 / 9, 5 / 9]) and np.allclose(g["rt"][30:35], [1, .9, .8, .7, .6])
+    assert g["rt"][35] == g["rt"][3] and g["kappaGHyper"][35] == 500 and np.count_nonzero(g["ZS"] == -1) == 1
+    # the first 25 states are the reference's table
+    g8 = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=5)["genotypeParams"]
+    assert np.array_equal(g["rt"][:25], g8["rt"]) and np.array_equal(g["ct"][:25], g8["ct"])
+
+
+def test_solver_refuses_mismatched_column_lengths():
+    """The C ABI takes bare pointers: the host mirror checks every length before the call (no device needed)."""
+    p = T.loadDefaultParameters(5, 2)
+    data = {"chr": np.ones(4), "posn": np.arange(4.0), "ref": np.full(3, 9.0), "tumDepth": np.full(4, 12.0), "logR": np.zeros(4)}
+    with pytest.raises(ValueError, match=r"data\$ref has 3 entries"):
+        T.Solver(data, p["genotypeParams"], 2, 1e15, 1.0)
+    g = dict(p["genotypeParams"], ZS=p["genotypeParams"]["ZS"][:-1])
+    data["ref"] = np.full(4, 9.0)
+    with pytest.raises(ValueError, match="fewer entries"):
+        T.Solver(data, g, 2, 1e15, 1.0)
+
+
+def test_communicator_entry_points_fail_loudly_without_a_device_or_nccl():
+    if T.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(T.TitanError):
+        T.Comm(b"\0" * 128, 0, 1)
+    with pytest.raises(ValueError, match="128 bytes"):
+        T.Comm(b"short", 0, 1)
+
+
+def test_reference_arm_sample_fits_its_time_budget():
+    """bench.py --impl reference sizes its per-chromosome prefix sample from a calibration run so that steps + warm-up
+    stay inside --ref-budget-s, and says which fraction of the workload that is."""
+    import json
+    import subprocess
+    import sys
+    import time
+    t0 = time.time()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--snps", "60000", "--steps", "2",
+                          "--warmup", "1", "--ref-budget-s", "6"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                   # stdout carries the one JSON line and nothing else
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["steps"] == 2 and rec["warmup"] == 1 and rec["gpu_launches"] == 0
+    assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["e2e"]["h2d_bytes_per_step"] == 0
+    assert rec["value"] > 0 and time.time() - t0 < 120
