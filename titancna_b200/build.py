@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(ROOT, "include", "titancna_b200.h"))
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("TITAN_NVCC_DEFS", "").split()   # e.g. -DTITAN_PROBE_PIECES=4
     jobs, objs = [], []
     for u in units:
         src, obj = os.path.join(CSRC, u), os.path.join(objdir, u.replace(".cu", ".o"))

@@ -379,8 +379,8 @@ static void build_chunks(titan_solver *s) {
   s->subb.alloc(3 * nc * K);
   s->pflags.alloc(6 * nc);
   s->ver.alloc(2 * nc);
-  s->pints.alloc(10 * nc);
-  s->pvec.alloc(8 * nc * K);
+  s->pints.alloc((4 * kProbes - 2) * nc);
+  s->pvec.alloc((2 * kProbes + 2) * nc * K);
   CK(cudaMemset(s->pflags.p, 0, 6 * nc));
   // a chunk without a neighbour never writes its extended vector; the neighbour-less tests never read it either,
   // but keep the buffers defined
@@ -859,8 +859,10 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
     A.dirtyF = s->pflags.p; A.dirtyB = s->pflags.p + nc; A.solvedF = s->pflags.p + 2 * nc; A.solvedB = s->pflags.p + 3 * nc;
     A.probedF = s->pflags.p + 4 * nc; A.probedB = s->pflags.p + 5 * nc;
     A.probe_window = 0;
-    A.probeJF = s->pints.p; A.probeJB = s->pints.p + 2 * nc; A.probeEF = s->pints.p + 4 * nc; A.probeEB = s->pints.p + 7 * nc;
-    A.probeF = s->pvec.p; A.probeB = s->pvec.p + 3 * nc * K; A.solF = s->pvec.p + 6 * nc * K; A.solB = s->pvec.p + 7 * nc * K;
+    A.probeJF = s->pints.p; A.probeJB = s->pints.p + (kProbes - 1) * nc;
+    A.probeEF = s->pints.p + 2 * (kProbes - 1) * nc; A.probeEB = s->pints.p + (3 * kProbes - 2) * nc;
+    A.probeF = s->pvec.p; A.probeB = s->pvec.p + kProbes * nc * K;
+    A.solF = s->pvec.p + 2 * kProbes * nc * K; A.solB = s->pvec.p + (2 * kProbes + 1) * nc * K;
     A.chr_chunk0 = s->chr_chunk0.p;
     A.nChr = s->nChr;
     A.use_solved = 0;

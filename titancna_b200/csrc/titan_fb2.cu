@@ -641,21 +641,21 @@ __global__ void __launch_bounds__(32 * kWPC, 3) fb2_round_kernel(Fb2Args A, int 
 // through every run of dirty chunks (fb2_solve_kernel), and the round kernel re-runs the dirty chunks once from
 // the predicted vectors.  The next boundary test decides; nothing is accepted on the strength of a prediction.
 // ------------------------------------------------------------------------------------------
-constexpr int kProbes = 3;
 
 
-// the two states of largest posterior weight want_j * wgt_j (ties: lowest index), identical in every warp that asks
+// the kProbes - 1 states of largest posterior weight want_j * wgt_j (ties: lowest index), identical in every warp that asks
 template <int Z, int GS>
-__device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const double *wgt, const LaneInfo<Z, GS> &L, int U, int &j1,
-                                            int &j2) {
+__device__ __forceinline__ void top_states(const double (&want)[GS][Z], const double *wgt, const LaneInfo<Z, GS> &L, int U,
+                                           int (&found)[kProbes - 1]) {
   double g[GS][Z];
 #pragma unroll
   for (int s = 0; s < GS; ++s)
 #pragma unroll
     for (int z = 0; z < Z; ++z) g[s][z] = L.act[s] ? want[s][z] * wgt[L.g[s] + z * U] : -1.0;
-  int found[2] = {-1, -1};
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < kProbes - 1; ++pass) found[pass] = -1;
+#pragma unroll
+  for (int pass = 0; pass < kProbes - 1; ++pass) {
     double bv = -2.0;
     int bj = 0x7fffffff;
 #pragma unroll
@@ -663,7 +663,10 @@ __device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const d
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         const int j = L.g[s] + z * U;
-        const double v = (L.act[s] && j != found[0]) ? g[s][z] : -2.0;
+        bool taken = false;
+#pragma unroll
+        for (int q = 0; q < kProbes - 1; ++q) taken |= (q < pass) && (j == found[q]);
+        const double v = (L.act[s] && !taken) ? g[s][z] : -2.0;
         if (v > bv || (v == bv && j < bj)) { bv = v; bj = j; }
       }
 #pragma unroll
@@ -674,8 +677,6 @@ __device__ __forceinline__ void top2_states(const double (&want)[GS][Z], const d
     }
     found[pass] = bj;
   }
-  j1 = found[0];
-  j2 = found[1];
 }
 
 
@@ -718,12 +719,12 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
     if (!ok) atomicAdd(A.rerun + A.round, 1u);
   }
   if (!active) return;
-  int j1, j2;
-  top2_states<Z, GS>(v, wgt, L, U, j1, j2);
+  int jt[kProbes - 1];
+  top_states<Z, GS>(v, wgt, L, U, jt);
   if (p == 0 && lane == 0) {
-    int *J = (backward ? A.probeJB : A.probeJF) + 2 * c;
-    J[0] = j1;
-    J[1] = j2;
+    int *J = (backward ? A.probeJB : A.probeJF) + (kProbes - 1) * c;
+#pragma unroll
+    for (int q = 0; q < kProbes - 1; ++q) J[q] = jt[q];
   }
   // piece p of the vector this chunk last started from
   load_row<Z, GS>(v, used, L);
@@ -732,9 +733,15 @@ __device__ __forceinline__ void fb2_probe(const Fb2Args &A, int c, int p, bool b
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
       const int j = L.g[s] + z * U;
-      const bool top = (j == j1) || (j == j2);
+      bool top = false;
+      int mine = -1;
+#pragma unroll
+      for (int q = 0; q < kProbes - 1; ++q) {
+        top |= (j == jt[q]);
+        mine = (q == p) ? jt[q] : mine;
+      }
       double x;
-      if (p < 2) x = (j == (p == 0 ? j1 : j2)) ? 1.0 : 0.0;
+      if (p < kProbes - 1) x = (j == mine) ? 1.0 : 0.0;
       else x = top ? 0.0 : v[s][z];
       v[s][z] = L.act[s] ? x : 0.0;
     }
@@ -815,37 +822,52 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
     store_row<Z, GS>(sol + (size_t)c * K, cur, L);
     if (lane == 0) solved[c] = 1;
     // coefficients of cur[] in the three pieces of the vector the chunk started from
-    const int j1 = probeJ[2 * c], j2 = probeJ[2 * c + 1];
-    double x1 = 0.0, x2 = 0.0, rn = 0.0, ro = 0.0;
+    int jt[kProbes - 1];
+#pragma unroll
+    for (int q = 0; q < kProbes - 1; ++q) jt[q] = probeJ[(kProbes - 1) * c + q];
+    double x[kProbes];            // coefficients: the probed states' components, then the remainder's mass ratio
+    double rn = 0.0, ro = 0.0;
+#pragma unroll
+    for (int q = 0; q < kProbes; ++q) x[q] = 0.0;
 #pragma unroll
     for (int s = 0; s < GS; ++s)
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         const int j = L.g[s] + z * U;
         const double v = cur[s][z], o = L.act[s] ? startv[(size_t)c * K + j] : 0.0;
-        x1 += (j == j1) ? v : 0.0;
-        x2 += (j == j2) ? v : 0.0;
-        const bool rest = L.act[s] && j != j1 && j != j2;
+        bool top = false;
+#pragma unroll
+        for (int q = 0; q < kProbes - 1; ++q) {
+          x[q] += (j == jt[q]) ? v : 0.0;
+          top |= (j == jt[q]);
+        }
+        const bool rest = L.act[s] && !top;
         rn += rest ? v : 0.0;
         ro += rest ? o : 0.0;
       }
-    x1 = warp_sum(x1); x2 = warp_sum(x2); rn = warp_sum(rn); ro = warp_sum(ro);
-    const double x3 = ro > 0.0 ? rn / ro : 0.0;
-    const int E0 = probeE[c * kProbes], E1 = probeE[c * kProbes + 1], E2 = probeE[c * kProbes + 2];
+#pragma unroll
+    for (int q = 0; q < kProbes - 1; ++q) x[q] = warp_sum(x[q]);
+    rn = warp_sum(rn); ro = warp_sum(ro);
+    x[kProbes - 1] = ro > 0.0 ? rn / ro : 0.0;
     int Em = -2147483647;
-    if (x1 > 0.0) Em = max(Em, E0);
-    if (x2 > 0.0) Em = max(Em, E1);
-    if (x3 > 0.0) Em = max(Em, E2);
-    const double f0 = x1 > 0.0 ? scalbn(x1, max(E0 - Em, -2000)) : 0.0, f1 = x2 > 0.0 ? scalbn(x2, max(E1 - Em, -2000)) : 0.0,
-                 f2 = x3 > 0.0 ? scalbn(x3, max(E2 - Em, -2000)) : 0.0;
-    double e[GS][Z], p0[GS][Z], p1[GS][Z], p2[GS][Z];
-    load_row<Z, GS>(p0, probe + ((size_t)c * kProbes + 0) * K, L);
-    load_row<Z, GS>(p1, probe + ((size_t)c * kProbes + 1) * K, L);
-    load_row<Z, GS>(p2, probe + ((size_t)c * kProbes + 2) * K, L);
+#pragma unroll
+    for (int q = 0; q < kProbes; ++q)
+      if (x[q] > 0.0) Em = max(Em, probeE[c * kProbes + q]);
+    double e[GS][Z];
 #pragma unroll
     for (int s = 0; s < GS; ++s)
 #pragma unroll
-      for (int z = 0; z < Z; ++z) e[s][z] = f0 * p0[s][z] + f1 * p1[s][z] + f2 * p2[s][z];
+      for (int z = 0; z < Z; ++z) e[s][z] = 0.0;
+#pragma unroll
+    for (int q = 0; q < kProbes; ++q) {
+      const double f = x[q] > 0.0 ? scalbn(x[q], max(probeE[c * kProbes + q] - Em, -2000)) : 0.0;
+      double pq[GS][Z];
+      load_row<Z, GS>(pq, probe + ((size_t)c * kProbes + q) * K, L);
+#pragma unroll
+      for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int z = 0; z < Z; ++z) e[s][z] += f * pq[s][z];
+    }
     const double tot = vec_sum<Z, GS>(e);
     have = (tot > 0.0) && (tot < CUDART_INF);
     if (have) {

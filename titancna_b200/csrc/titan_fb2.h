@@ -17,6 +17,10 @@
 namespace titan {
 
 constexpr int kFbPadRows = 16;   // slack rows before and after every per-SNP array: tiles are copied whole
+#ifndef TITAN_PROBE_PIECES
+#define TITAN_PROBE_PIECES 3
+#endif
+constexpr int kProbes = TITAN_PROBE_PIECES;   // pieces a dirty chunk's start vector is split into: kProbes - 1 single states + the remainder
 
 struct Fb2Args {
   const double *Bm;            // [N][Kp] scaled emissions; column K holds the shift m_t
@@ -40,8 +44,8 @@ struct Fb2Args {
   int use_solved;              // round kernel: chunks flagged in solved* start from sol* without a test
   int probe_window;            // also probe this many chunks downstream of a dirty one (a re-run shifts its successors' inputs)
   unsigned char *dirtyF, *dirtyB, *solvedF, *solvedB, *probedF, *probedB;
-  int *probeJF, *probeJB;      // [nChunks][2] the two states probed individually
-  int *probeEF, *probeEB;      // [nChunks][3] accumulated power-of-two exponents of the probe results
+  int *probeJF, *probeJB;      // [nChunks][kProbes - 1] the states probed individually
+  int *probeEF, *probeEB;      // [nChunks][kProbes] accumulated power-of-two exponents of the probe results
   double *probeF, *probeB;     // [nChunks][3][K]
   double *solF, *solB;         // [nChunks][K] boundary vectors predicted by the chain solve
   const int *chr_chunk0;       // [nChr+1] first chunk of every chromosome
