@@ -30,6 +30,8 @@ if rank == 0:
     comm.close()
     print({"world": world, "nccl_version": ver, "iters": int(cp["n"].size - 1), "sharded_s": t_sh, "single_gpu_s": t_1, "max_abs_err": err, "loglik_rel_err": llerr,
            "shard_sizes": [int(x) for x in T.shard_chromosomes(data, world)[2]]})
-    assert max(err.values()) < 1e-8 and llerr < 1e-11
+    # the shards and the whole genome are chunked differently (chunk length follows the SNP count), so the two EMs agree
+    # to the boundary tolerance of the chunked scan, not bit for bit: contract 1e-6 on parameters, 1e-9 on log-likelihoods
+    assert max(err.values()) < 1e-7 and llerr < 1e-10, (err, llerr)
 dist.barrier()
 dist.destroy_process_group()

@@ -31,7 +31,7 @@ def test_sharded_em_equals_single_gpu_em():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     rec = [ast.literal_eval(l) for l in r.stdout.splitlines() if l.startswith("{'world'")][0]
     assert rec["world"] == world and rec["iters"] >= 2
-    assert max(rec["max_abs_err"].values()) < 1e-8 and rec["loglik_rel_err"] < 1e-11
+    assert max(rec["max_abs_err"].values()) < 1e-7 and rec["loglik_rel_err"] < 1e-10
     assert rec["nccl_version"] >= 20000
 
 
