@@ -453,7 +453,9 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   // chunk count, so shorter chunks shorten every pass (measured: 50 k-SNP exome 1.25 -> 0.58 ms per E-step at 128,
   // 200 k-SNP haplotype bins 1.40 -> 0.88 ms at 512; 1 M SNPs: 512 and 1024 equal).
   {
-    const int64_t target = in.N / 300;              // aim for >= 300 chunks
+    // aim for >= 300 chunks; with four or more clusters shorter chunks cost extra verification cycles (2 M SNPs, Z = 5:
+    // 512 needs 6-11 cycles where 1024 needs 4-6), so the length comes down only for half as many SNPs
+    const int64_t target = in.N / (in.Z >= 4 ? 150 : 300);
     int len = 1024;
     while (len > 128 && len > target) len >>= 1;
     s->chunk_len = len;
