@@ -255,14 +255,14 @@ def test_edge_cases_and_errors():
         T.Solver(data, g, 2, 0.0, 1.0)
 
 
-@pytest.mark.parametrize("env", [{"TITAN_WS_MODE": "0"}, {"TITAN_WS_MODE": "2"}, {"TITAN_OVERLAP": "0"},
-                                 {"TITAN_OVERLAP": "0", "TITAN_WS_MODE": "0"}, {"TITAN_VIT_MODE": "2"},
-                                 {"TITAN_VIT_MODE": "3"}])
+@pytest.mark.parametrize("env", [{}, {"TITAN_PROBES": "0"}, {"TITAN_SPEC_FINAL": "0"}, {"TITAN_PROBE_WINDOW": "0"},
+                                 {"TITAN_ROUND_BATCH": "1"}, {"TITAN_VIT_MODE": "2"}, {"TITAN_VIT_MODE": "3"},
+                                 {"TITAN_VIT_MODE": "4"}])
 def test_kernel_variants_agree(env, monkeypatch):
-    """Every execution strategy (warp-per-chunk only, warp-specialised only, forward/backward rounds
-    overlapped on two streams or run back to back) is the same function of the inputs: compare each
-    against the plain sequential recursion on a genome whose boundaries need several verification
-    rounds (two nearly identical clusters: slow forgetting)."""
+    """Every execution strategy (re-runs from the neighbour's vector only or with the probe-based prediction,
+    speculative final pass on or off, one or several cycles per host synchronisation, every Viterbi kernel) is the
+    same function of the inputs: compare each against the plain sequential recursion on a genome whose boundaries
+    need several verification cycles (two nearly identical clusters: slow forgetting)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     N, Z = 60000, 3
@@ -530,6 +530,31 @@ def test_estep_is_bitwise_reproducible_at_scale():
                 ref = key
             assert np.array_equal(ref, key), (chunk, r)
     sol.close()
+
+
+@pytest.mark.gpu
+def test_speculative_final_pass_is_bit_identical_to_a_single_final_pass(monkeypatch):
+    """The final pass of a chunk reads only that chunk's own verified inputs, so running it speculatively on a second
+    stream while the verification cycles still run (and redoing the chunks that ran again) must not change a bit."""
+    data, _ = synth.make_data(300000, Z=3, maxCN=8, n_chr=23, seed=bench_seed(), mean_seg=3000)
+    p = T.loadDefaultParameters(copyNumber=8, numberClonalClusters=3, data=data)
+    g, sP = p["genotypeParams"], p["cellPrevParams"]
+    args = (0.42, np.array([0.01, 0.30, 0.33]), 2.03, g["var_0"], g["piG_0"], sP["piZ_0"], g)
+    keys = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("TITAN_SPEC_FINAL", spec)
+        sol = T.Solver(data, g, 3, 1e15, 1.0)
+        out = sol.estep(*args, posteriors=True)
+        tm = sol.timing()
+        sol.close()
+        assert tm["last_fwd_rounds"] >= 3                   # at least one real cycle: the speculative pass had work to overlap
+        keys[spec] = np.concatenate([out["stats"][k].ravel() for k in "abcdeg"] + [out["loglik_chr"], out["rhoG"].ravel(), out["rhoZ"].ravel()])
+    assert np.array_equal(keys["1"], keys["0"])
+
+
+def bench_seed():
+    import bench
+    return bench.SEED
 
 
 @pytest.mark.gpu
