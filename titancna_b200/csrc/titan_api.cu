@@ -945,8 +945,10 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
         if (ctr_h[round] == 0) { done = true; break; }
         runs += ctr_h[round];
       }
-      if (!done && round >= hard_cap)
+      if (!done && round >= hard_cap) {
+        if (s->stream2) cudaStreamSynchronize(s->stream2);      // no speculative pass may outlive the failed call
         return fail(TITAN_ERR_NUMERIC, "chunk boundaries did not reach a fixed point in %d rounds", hard_cap);
+      }
     }
     rounds = round + 1;
     if (getenv("TITAN_TRACE") && atoi(getenv("TITAN_TRACE")) > 1) {
