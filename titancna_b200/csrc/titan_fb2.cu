@@ -191,29 +191,30 @@ struct Ring {
 // Alpha rows leave through shared memory: the owned steps of a forward chunk park their rows in one of two tile
 // buffers and lane 0 sends every full tile to HBM with one bulk store (cp.async.bulk.global.shared).
 struct AlphaOut {
-  unsigned sbuf[2], rowB, wr;   // wr: shared address of the next row to fill
+  unsigned sbuf0, sbuf1, rowB, wr;   // the two tile buffers (scalars, not an array: a dynamically indexed member would put
+                                     // the whole cursor into local memory); wr: shared address of the next row to fill
   char *gdst;
   int TS, filled, which, lane;
   __device__ __forceinline__ void start(unsigned smem_addr, int TS_, unsigned rowB_, double *dst, int lane_) {
     TS = TS_; rowB = rowB_; lane = lane_;
-    sbuf[0] = smem_addr;
-    sbuf[1] = smem_addr + (unsigned)TS * rowB;
+    sbuf0 = smem_addr;
+    sbuf1 = smem_addr + (unsigned)TS * rowB;
     gdst = reinterpret_cast<char *>(dst);
-    filled = 0; which = 0; wr = sbuf[0];
+    filled = 0; which = 0; wr = sbuf0;
   }
   __device__ __forceinline__ void flush() {
     if (filled == 0) return;
     fence_async_smem();                         // every lane: its rows were written through the generic proxy
     __syncwarp();
     if (lane == 0) {
-      bulk_s2g(gdst, sbuf[which], (unsigned)filled * rowB);
+      bulk_s2g(gdst, which ? sbuf1 : sbuf0, (unsigned)filled * rowB);
       bulk_commit();
       bulk_wait_read<1>();                      // the other buffer's store has finished reading it
     }
     __syncwarp();
     gdst += (size_t)filled * rowB;
     which ^= 1;
-    wr = sbuf[which];
+    wr = which ? sbuf1 : sbuf0;
     filled = 0;
   }
   __device__ __forceinline__ void row_done() {
