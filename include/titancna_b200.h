@@ -90,7 +90,12 @@ typedef struct titan_data_desc {
   int32_t U;                 /* genotype (unit) states                                               */
   int32_t Z;                 /* clonal clusters                                                      */
   const double *ZS;          /* [U] zygosity key, -1 = diploid HET; other entries must be distinct   */
+  int32_t alleleModel;       /* genotypeParams$alleleEmissionModel: TITAN_ALLELE_BINOMIAL (0, default) or
+                                TITAN_ALLELE_GAUSSIAN (1): bivariate normal on (ref / tumDepth, logR),
+                                R/hmmClonal.R:149-158,525-559                                         */
 } titan_data_desc;
+#define TITAN_ALLELE_BINOMIAL 0
+#define TITAN_ALLELE_GAUSSIAN 1
 
 /* Uploads the columns once, computes the parameter-independent per-SNP terms on the HOST with the
  * host libm (rhoG/rhoZ: fwd_backC_clonalCN.c:342-348,124-125; lgamma bracket: R/hmmClonal.R:618),
@@ -120,12 +125,17 @@ typedef struct titan_params {
   const double *rt;          /* [U] tumour reference allelic ratios                                  */
   const double *ct;          /* [U] tumour copy numbers                                              */
   double rn;                 /* normal reference allelic ratio                                       */
+  /* Gaussian allele model only (ignored by a binomial solver) */
+  const double *varR;        /* [U] allelic-ratio variances (convergeParams$varR column)             */
+  double corRho;             /* correlation of the bivariate normal: genotypeParams$corRho_0 in the EM; the
+                                Viterbi wrapper passes the data correlation (R/hmmClonal.R:447,536-538) */
 } titan_params;
 
 typedef struct titan_estep_out {
   /* all host pointers, caller-allocated; any of the optional ones may be NULL */
   double *loglik_chr;        /* [nChr] forward-backward log-likelihood per chromosome               */
-  double *stats;             /* [6][U*Z]: a,b,c,d,e,g of R/paramEstimation.R:34-40, joint index u+z*U*/
+  double *stats;             /* [6][U*Z]: a,b,c,d,e,g of R/paramEstimation.R:34-40, joint index u+z*U;
+                                Gaussian allele model: a,f,c,h,e,g of :30-32,37-39 in the same six slots */
   double *rhoG0;             /* [U x nChr] rhoG at the first SNP of each chromosome (chrPos_0)       */
   double *rhoZ0;             /* [Z x nChr] rhoZ at the first SNP of each chromosome                  */
   double *rhoG;              /* optional [U x N]  (R/hmmClonal.R:234)                                */
@@ -152,6 +162,9 @@ typedef struct titan_hyper {
   const double *s_0, *alphaSHyper, *betaSHyper, *kappaZHyper, *piZ_0; /* [Z]                         */
   double n_0, alphaNHyper, betaNHyper;
   double phi_0, alphaPHyper, betaPHyper;
+  /* Gaussian allele model only (R/utils.R:108-119); may be NULL / 0 for the binomial model */
+  const double *varR_0, *alphaRHyper, *betaRHyper;                /* [U]                             */
+  double corRho_0;
 } titan_hyper;
 
 typedef struct titan_em_opts {
@@ -178,9 +191,11 @@ typedef struct titan_em_out {
   double mstep_ms;            /* OUT: host time spent in the M-step                                  */
   double reduce_ms;           /* OUT: part of estep_ms spent in the final reduction and, for a sharded solution, in
                                  the all-reduce (which includes waiting for the slowest rank)         */
+  double *varR;               /* optional [U x (maxiter+1)]: allelic variances (constant columns for the binomial
+                                 model, R/paramEstimation.R:212)                                      */
 } titan_em_out;
 
-/* The whole runEMclonalCN loop (binomial allele model, no outlier state): E-steps on the device,
+/* The whole runEMclonalCN loop (the solver's allele model, no outlier state): E-steps on the device,
  * the O(U*Z) coordinate-descent M-step (R/paramEstimation.R:75-283) and priors
  * (R/hmmClonal.R:715-783) on the host. */
 int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_em_opts *o, titan_em_out *out);
@@ -194,6 +209,16 @@ int titan_mstep(const titan_hyper *h, int U, int Z, int nChr, int maxiterUpdate,
                 double prev_phi, const double *prev_piG, const double *prev_piZ, double *out_n,
                 double *out_s, double *out_var, double *out_phi, double *out_piG, double *out_piZ,
                 int *out_sweeps, double *out_prior);
+
+/* The same for the Gaussian allele model (R/paramEstimation.R:165-200,313-329,376-383,415-422,463-497,510-515):
+ * stats = a,f,c,h,e,g as titan_estep returns them from a Gaussian solver; h->varR_0 / alphaRHyper / betaRHyper /
+ * corRho_0 are required. */
+int titan_mstep_gaussian(const titan_hyper *h, int U, int Z, int nChr, int maxiterUpdate, int normal_map,
+                         int estimateS, int estimatePloidy, const double *stats, const double *rhoG0,
+                         const double *rhoZ0, double prev_n, const double *prev_s, const double *prev_var,
+                         const double *prev_varR, double prev_phi, const double *prev_piG, const double *prev_piZ,
+                         double *out_n, double *out_s, double *out_var, double *out_varR, double *out_phi,
+                         double *out_piG, double *out_piZ, int *out_sweeps, double *out_prior);
 
 /* Introspection for benchmarks and tests */
 typedef struct titan_timing {

@@ -231,6 +231,56 @@ def compute_py_c(ref, depth, logR, muR, muC, var, pseudo=1e-300):
     return py.T  # K x N view, Fortran-contiguous
 
 
+def bivariate_covariance(x1, x2):
+    """getBivariateCovariance, R/hmmClonal.R:561-567: sample covariance matrix (n-1 denominator) and the
+    correlation derived from it (covar[1,2] / sqrt(covar[1,1] * covar[2,2]))."""
+    x1, x2 = np.asarray(x1, float), np.asarray(x2, float)
+    ok = ~(np.isnan(x1) | np.isnan(x2))
+    a, b = x1[ok], x2[ok]
+    da, db = a - a.mean(), b - b.mean()
+    nm1 = a.size - 1
+    c11, c22, c12 = float(np.dot(da, da)) / nm1, float(np.dot(db, db)) / nm1, float(np.dot(da, db)) / nm1
+    return {"covar": np.array([[c11, c12], [c12, c22]]), "cor": c12 / math.sqrt(c11 * c22)}
+
+
+def compute_py_gauss(ref, depth, logR, muR, muC, varR, var, corRho, pseudo=0.0):
+    """K x N log emission matrix of the Gaussian allele model: computeBivariateNormalObslik +
+    bivariateNormalpdflog (R/hmmClonal.R:525-559), called as in :153-158 / :269-274 with x1 = ref / tumDepth,
+    x2 = logR, var1 = varR (allelic), var2 = var (logR).  Every operation in R's association order;
+    `pseudo` is the `py <- py + pseudoCounts` of :158,:274 (the Viterbi wrapper :444-447 adds nothing)."""
+    ref, depth, logR = (np.asarray(a, float) for a in (ref, depth, logR))
+    U, Z = muR.shape
+    with np.errstate(invalid="ignore", divide="ignore"):
+        x1, x2 = ref / depth, logR
+    varR, var = np.asarray(varR, float), np.asarray(var, float)
+    rho = float(corRho)
+    py = np.empty((U * Z, x1.size))
+    for k in range(U):
+        var1, var2 = float(varR[k]), float(var[k])
+        c = math.log((2 * math.pi) * math.sqrt((var1 * var2) * (1 - rho * rho)))
+        l0 = 1 / (2 * (1 - rho * rho))
+        sq = math.sqrt(var1 * var2)
+        for z in range(Z):
+            d1, d2 = x1 - muR[k, z], x2 - muC[k, z]
+            l1 = (d1 * d1) / var1
+            l2 = (d2 * d2) / var2
+            l3 = (((2 * rho) * d1) * d2) / sq
+            y = (-c) - (l0 * ((l1 + l2) - l3))
+            y[np.isnan(y)] = 1.0                         # :557
+            py[k + z * U] = y + pseudo
+    return py
+
+
+def sufficient_statistics_gauss(ref, depth, logR, rho):
+    """a,c,e,f,g,h of R/paramEstimation.R:27-42 (Gaussian allele model), each U x Z; b and d stay zero."""
+    ref, depth, logR = (np.asarray(a, float) for a in (ref, depth, logR))
+    r = ref / depth
+    ein = lambda w: np.einsum("kzt,t->kz", rho, w)
+    z = np.zeros(rho.shape[:2])
+    return {"a": ein(r), "b": z, "c": ein(logR), "d": z.copy(), "e": rho.sum(axis=2), "f": ein(r * r),
+            "g": ein(logR ** 2), "h": ein(r * logR)}
+
+
 # ----------------------------------------------------------------------------------------
 # native recursions through one of the two CPU engines
 # ----------------------------------------------------------------------------------------
@@ -354,8 +404,8 @@ def dirichletpdflog(x, k):
 
 
 def prior_probs(n, s, phi, var, piG, piZ, gParams, nParams, sParams, pParams,
-                normalEstimateMethod="map", estimateS=True, estimatePloidy=True):
-    """R/hmmClonal.R:715-783, binomial allele model (prior_gamma_varR = 0)."""
+                normalEstimateMethod="map", estimateS=True, estimatePloidy=True, varR=None):
+    """R/hmmClonal.R:715-783; prior_gamma_varR (:767-775) only for the Gaussian allele model."""
     out = {"piG": dirichletpdflog(piG, gParams["kappaGHyper"]),
            "piZ": dirichletpdflog(piZ, sParams["kappaZHyper"])}
     ps = 0.0
@@ -371,7 +421,11 @@ def prior_probs(n, s, phi, var, piG, piZ, gParams, nParams, sParams, pParams,
         pv += invgammapdflog(var[k], gParams["alphaKHyper"][k], gParams["betaKHyper"][k])
     out["var"] = pv
     out["phi"] = invgammapdflog(phi, pParams["alphaPHyper"], pParams["betaPHyper"]) if estimatePloidy else 0.0
-    out["varR"] = 0.0
+    pvr = 0.0
+    if gParams.get("alleleEmissionModel", "binomial") == "Gaussian":
+        for k in range(len(var)):
+            pvr += invgammapdflog(varR[k], gParams["alphaRHyper"][k], gParams["betaRHyper"][k])
+    out["varR"] = pvr
     out["prior"] = out["s"] + out["n"] + out["phi"] + out["var"] + out["varR"] + out["piG"] + out["piZ"]
     return out
 
@@ -457,6 +511,112 @@ def deriv_phi(phi, n, s, var, st, rt, rn, ct, alphaP, betaP):
             t1 = st["c"][k, z] / var[k]
             t2 = st["e"][k, z] * muC[k, z] / var[k]
             tot = tot + (t1 - t2) * dmuC
+    return tot + ((-alphaP - 1) / phi + betaP / phi ** 2)
+
+
+# ---- Gaussian allele model (alleleEmissionModel = "Gaussian"): the same functions' other branches -------------
+# The reference flags this model "not fully implemented" (vignettes/TitanCNA.Rnw:123); its objective carries an
+# operator-precedence slip (log(1 / 2 * pi * ...), R/paramEstimation.R:321) and the ploidy derivative indexes the
+# K x Z matrices with a single subscript (:512-513, i.e. column 1 for every cluster).  Both are restated as written.
+def likelihood_func_gauss(n, s, var, varR, phi, st, gParams, nParams, sParams, pParams, piG, piZ, likInitG, likInitZ,
+                          normalEstimateMethod, estimateS, estimatePloidy):
+    """R/paramEstimation.R:287-356, Gaussian branch :313-329."""
+    muR, muC = clonal_two_component_mixture(gParams["rt"], gParams["rn"], n, s, gParams["ct"], phi)
+    U, Z = muR.shape
+    rho = float(gParams["corRho_0"])
+    a, c, e, f, g, h = (st[k] for k in "acefgh")
+    lik = 0.0
+    for z in range(Z):
+        for k in range(U):
+            term1 = e[k, z] * math.log(((1 / 2) * math.pi) * math.sqrt((var[k] * varR[k]) * (1 - rho * rho)))
+            term2 = 1 / (2 * (1 - rho * rho))
+            term3 = ((f[k, z] - (2 * a[k, z]) * muR[k, z]) + e[k, z] * (muR[k, z] * muR[k, z])) / (2 * varR[k])
+            term4 = ((g[k, z] - (2 * c[k, z]) * muC[k, z]) + e[k, z] * (muC[k, z] * muC[k, z])) / (2 * var[k])
+            term5 = ((2 * rho) * (((h[k, z] - a[k, z] * muC[k, z]) - c[k, z] * muR[k, z])
+                                  + (e[k, z] * muC[k, z]) * muR[k, z])) / math.sqrt(var[k] * varR[k])
+            lik = (lik + term1) - term2 * ((term3 + term4) - term5)
+    pr = prior_probs(n, s, phi, var, piG, piZ, gParams, nParams, sParams, pParams,
+                     normalEstimateMethod, estimateS, estimatePloidy, varR=varR)
+    return lik + pr["prior"] + likInitG + likInitZ + 0.0
+
+
+def deriv_n_gauss(n, s, var, varR, phi, rho, st, rt, rn, ct, alphaN, betaN):
+    """R/paramEstimation.R:359-399, Gaussian branch :376-383."""
+    muR, muC = clonal_two_component_mixture(rt, rn, n, s, ct, phi)
+    cn = 2.0
+    a, c, e = st["a"], st["c"], st["e"]
+    tot = 0.0
+    for z in range(len(s)):
+        den = n * cn + (1 - n) * s[z] * cn + (1 - n) * (1 - s[z]) * ct
+        dmuC = (cn - s[z] * cn - (1 - s[z]) * ct) / den - (cn - phi) / (n * cn + (1 - n) * phi)
+        dmuR = ((1 - s[z]) * cn * ct * (rn - rt)) / (den ** 2)
+        for k in range(len(ct)):
+            term0 = 1 / (1 - rho * rho)
+            rR, rC = a[k, z] - e[k, z] * muR[k, z], c[k, z] - e[k, z] * muC[k, z]
+            term1 = rR * dmuR[k] / varR[k]
+            term2 = rC * dmuC[k] / var[k]
+            term3 = rho * ((rC * dmuR[k]) + (rR * dmuC[k])) / math.sqrt(varR[k] * var[k])
+            tot = tot + term0 * (term1 + term2 - term3)
+    return tot + ((alphaN - 1) / n - (betaN - 1) / (1 - n))
+
+
+def deriv_s_gauss(sz, z, n, var, varR, phi, rho, st, rt, rn, ct, alphaS, betaS):
+    """R/paramEstimation.R:401-437 for cluster z, Gaussian branch :415-422."""
+    muR, muC = clonal_two_component_mixture(rt, rn, n, [sz], ct, phi)
+    cn = 2.0
+    den = n * cn + (1 - n) * sz * cn + (1 - n) * (1 - sz) * ct
+    dmuC = ((1 - n) * cn - (1 - n) * ct) / den
+    dmuR = ((1 - n) * cn * ct * (rn - rt)) / (den ** 2)
+    a, c, e = st["a"], st["c"], st["e"]
+    tot = 0.0
+    for k in range(len(ct)):
+        term0 = 1 / (1 - rho * rho)
+        rR, rC = a[k, z] - e[k, z] * muR[k, 0], c[k, z] - e[k, z] * muC[k, 0]
+        term1 = rR * dmuR[k] / varR[k]
+        term2 = rC * dmuC[k] / var[k]
+        term3 = rho * ((rC * dmuR[k]) + (rR * dmuC[k])) / math.sqrt(varR[k] * var[k])
+        tot = tot + term0 * (term1 + term2 - term3)
+    return tot + ((alphaS - 1) / sz - (betaS - 1) / (1 - sz))
+
+
+def deriv_var_gauss(v, n, s, var2, phi, rho, a, c, e, g, h, rt, rn, ct, alphaK, betaK, kind):
+    """clonalCNDerivativeVarUpdateEqn, R/paramEstimation.R:463-497.  `a, c, e, g, h` are the row subsets the caller
+    hands over (|ind| x Z); for kind == "allelicRatio" the caller has already swapped a <-> c and passes f as g
+    (:189-190).  The prior term is summed over every state of the subset (:493-494); R's sum() accumulates in
+    long double."""
+    muR, muC = clonal_two_component_mixture(rt, rn, n, s, ct, phi)
+    mus1, mus2 = (muC, muR) if kind == "logRatio" else (muR, muC)
+    var2 = np.atleast_1d(np.asarray(var2, float))
+    K, Z = len(alphaK), len(s)
+    dlik = 0.0
+    for z in range(Z):
+        for k in range(K):
+            term1 = e[k, z] / (2 * v)
+            term2 = 1 / (2 * (1 - rho * rho))
+            term3 = ((g[k, z] - (2 * c[k, z]) * mus1[k, z]) + e[k, z] * (mus1[k, z] * mus1[k, z])) / (v * v)
+            term4 = (rho * (((h[k, z] - c[k, z] * mus2[k, z]) - a[k, z] * mus1[k, z])
+                            + (e[k, z] * mus1[k, z]) * mus2[k, z])) / (v * math.sqrt(v * var2[k]))
+            dlik = (dlik + (-term1)) + (term2 * (term3 - term4))
+    dinv = np.longdouble(0)
+    for k in range(K):
+        dinv = dinv + np.longdouble((-alphaK[k] - 1) / v + betaK[k] / (v * v))
+    return dlik + float(dinv)
+
+
+def deriv_phi_gauss(phi, n, s, var, varR, rho, st, rt, rn, ct, alphaP, betaP):
+    """R/paramEstimation.R:499-530, Gaussian branch :510-515: a[k], c[k], e[k], mus$R[k], mus$C[k] are single
+    subscripts into K x Z matrices, i.e. column 1, whatever z is."""
+    muR, muC = clonal_two_component_mixture(rt, rn, n, s, ct, phi)
+    cn = 2.0
+    dmuC = -(1 - n) / (n * cn + (1 - n) * phi)
+    a, c, e = st["a"], st["c"], st["e"]
+    tot = 0.0
+    for z in range(len(s)):
+        for k in range(len(ct)):
+            term0 = 1 / (1 - rho * rho)
+            term1 = (c[k, 0] - e[k, 0] * muC[k, 0]) * dmuC / var[k]
+            term2 = rho * ((a[k, 0] - e[k, 0] * muR[k, 0]) * dmuC) / math.sqrt(varR[k] * var[k])
+            tot = tot + term0 * (term1 - term2)
     return tot + ((-alphaP - 1) / phi + betaP / phi ** 2)
 
 
@@ -589,6 +749,79 @@ def update_parameters(n_0, s_0, var_0, phi_0, st, likInitG, likInitZ, piG, piZ, 
     return {"n": n, "s": s, "var": var, "phi": phi, "maxFind": i, "maxF": objfun[-1], "sweeps": i - 1}
 
 
+def update_parameters_gauss(n_0, s_0, var_0, varR_0, phi_0, st, likInitG, likInitZ, piG, piZ, gParams, nParams, sParams,
+                            pParams, normalEstimateMethod="map", estimateS=True, estimatePloidy=True,
+                            maxiter=500, miniter=10):
+    """Coordinate descent of R/paramEstimation.R:75-283, Gaussian allele model: per sweep n -> s_1..s_Z -> var per
+    copy-number level (uniroot on (eps, 5), :165-183) -> varR per genotype state (:185-200, with the NEW var[k]) ->
+    phi; failed roots keep the previous iterate; the last sweep is returned."""
+    rt, rn, ct = np.asarray(gParams["rt"], float), gParams["rn"], np.asarray(gParams["ct"], float)
+    rho = float(gParams["corRho_0"])
+    aK, bK = np.asarray(gParams["alphaKHyper"], float), np.asarray(gParams["betaKHyper"], float)
+    aR, bR = np.asarray(gParams["alphaRHyper"], float), np.asarray(gParams["betaRHyper"], float)
+    Z, U = len(s_0), len(rt)
+    n_prev, s_prev, phi_prev = float(n_0), np.array(s_0, float), float(phi_0)
+    var_prev, varR_prev = np.array(var_0, float), np.array(varR_0, float)
+    F = lambda n, s, var, varR, phi: likelihood_func_gauss(n, s, var, varR, phi, st, gParams, nParams, sParams, pParams,
+                                                           piG, piZ, likInitG, likInitZ, normalEstimateMethod,
+                                                           estimateS, estimatePloidy)
+    objfun = [F(n_prev, s_prev, var_prev, varR_prev, phi_prev)]
+    converged, i = False, 1
+    lo, hi = EPS, 1 - EPS
+    n, s, var, varR, phi = n_prev, s_prev.copy(), var_prev.copy(), varR_prev.copy(), phi_prev
+    bad = (RootError, ZeroDivisionError, ValueError)
+    while ((not converged) and i < maxiter) or i <= miniter:
+        i += 1
+        if normalEstimateMethod == "map":
+            try:
+                n = uniroot(lambda v: deriv_n_gauss(v, s_prev, var_prev, varR_prev, phi_prev, rho, st, rt, rn, ct,
+                                                    nParams["alphaNHyper"], nParams["betaNHyper"]), lo, hi)
+            except bad:
+                n = n_prev
+        else:
+            n = n_prev
+        s = s_prev.copy()
+        if estimateS:
+            for z in range(Z):
+                try:
+                    s[z] = uniroot(lambda v: deriv_s_gauss(v, z, n, var_prev, varR_prev, phi_prev, rho, st, rt, rn, ct,
+                                                           sParams["alphaSHyper"][z], sParams["betaSHyper"][z]), lo, hi)
+                except bad:
+                    s[z] = s_prev[z]
+        var = np.zeros_like(var_prev)
+        for lvl in _unique_in_order(ct):
+            ind = np.flatnonzero(ct == lvl)
+            try:
+                var[ind] = uniroot(lambda v: deriv_var_gauss(v, n, s, varR_prev[ind], phi_prev, rho, st["a"][ind], st["c"][ind],
+                                                             st["e"][ind], st["g"][ind], st["h"][ind], rt[ind], rn, ct[ind],
+                                                             aK[ind], bK[ind], "logRatio"), EPS, 5.0)
+            except bad:
+                var[ind] = var_prev[ind]
+        varR = np.zeros_like(varR_prev)
+        for k in range(U):
+            kk = slice(k, k + 1)
+            try:
+                varR[k] = uniroot(lambda v: deriv_var_gauss(v, n, s, var[k], phi_prev, rho, st["c"][kk], st["a"][kk],
+                                                            st["e"][kk], st["f"][kk], st["h"][kk], rt[kk], rn, ct[kk],
+                                                            aR[kk], bR[kk], "allelicRatio"), EPS, 5.0)
+            except bad:
+                varR[k] = varR_prev[k]
+        if estimatePloidy:
+            try:
+                phi = uniroot(lambda v: deriv_phi_gauss(v, n, s, var, varR, rho, st, rt, rn, ct, pParams["alphaPHyper"],
+                                                        pParams["betaPHyper"]), EPS, 10.0)
+            except bad:
+                phi = phi_prev
+        else:
+            phi = phi_prev
+        objfun.append(F(n, s, var, varR, phi))
+        n_prev, s_prev, var_prev, varR_prev, phi_prev = n, s.copy(), var.copy(), varR.copy(), phi
+        cur, prv = objfun[-1], objfun[-2]
+        if not math.isnan(cur) and (abs(cur - prv) / abs(cur)) <= 0.001:
+            converged = True
+    return {"n": n, "s": s, "var": var, "varR": varR, "phi": phi, "maxFind": i, "maxF": objfun[-1], "sweeps": i - 1}
+
+
 def estimate_mix_weights(rho_at_chr0, kappa):
     """R/paramEstimation.R:533-547: note sum() over the whole sub-matrix (Appendix B #3)."""
     kappa = np.asarray(kappa, float)
@@ -597,16 +830,23 @@ def estimate_mix_weights(rho_at_chr0, kappa):
 
 
 def m_step(data, es, n_0, s_0, phi_0, var_0, piG_0, piZ_0, chrPos_0, params, normalEstimateMethod="map",
-           estimateS=True, estimatePloidy=True, maxiterUpdate=1500, stats=None):
+           estimateS=True, estimatePloidy=True, maxiterUpdate=1500, stats=None, varR_0=None):
     """estimateClonalCNParamsMap, R/paramEstimation.R:10-70."""
     g, nP, sP, pP = (params[k] for k in ("genotypeParams", "normalParams", "cellPrevParams", "ploidyParams"))
-    st = stats if stats is not None else sufficient_statistics(data["ref"], data["tumDepth"], data["logR"], es["rho"])
+    gauss = g.get("alleleEmissionModel", "binomial") == "Gaussian"
+    suff = sufficient_statistics_gauss if gauss else sufficient_statistics
+    st = stats if stats is not None else suff(data["ref"], data["tumDepth"], data["logR"], es["rho"])
     rhoG0, rhoZ0 = es["rhoG"][:, chrPos_0], es["rhoZ"][:, chrPos_0]
     log = np.vectorize(math.log)
     likInitG = float(np.sum(log(np.asarray(piG_0, float)) @ rhoG0))        # :43
     likInitZ = float(np.sum(log(np.asarray(piZ_0, float)) @ rhoZ0))        # :44
-    out = update_parameters(n_0, s_0, var_0, phi_0, st, likInitG, likInitZ, piG_0, piZ_0, g, nP, sP, pP,
-                            normalEstimateMethod, estimateS, estimatePloidy, maxiter=maxiterUpdate, miniter=10)
+    if gauss:
+        out = update_parameters_gauss(n_0, s_0, var_0, varR_0, phi_0, st, likInitG, likInitZ, piG_0, piZ_0, g, nP, sP, pP,
+                                      normalEstimateMethod, estimateS, estimatePloidy, maxiter=maxiterUpdate, miniter=10)
+    else:
+        out = update_parameters(n_0, s_0, var_0, phi_0, st, likInitG, likInitZ, piG_0, piZ_0, g, nP, sP, pP,
+                                normalEstimateMethod, estimateS, estimatePloidy, maxiter=maxiterUpdate, miniter=10)
+        out["varR"] = None if varR_0 is None else np.array(varR_0, float)      # :212 varR <- varR_prev
     out["piZ"] = estimate_mix_weights(rhoZ0, sP["kappaZHyper"])
     out["piG"] = estimate_mix_weights(rhoG0, g["kappaGHyper"])
     out["stats"] = st
@@ -620,11 +860,10 @@ def m_step(data, es, n_0, s_0, phi_0, var_0, piG_0, piZ_0, chrPos_0, params, nor
 def run_em_clonal_cn(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, maxiterUpdate=1500,
                      pseudoCounts=1e-300, normalEstimateMethod="map", estimateS=True, estimatePloidy=True,
                      likChangeThreshold=0.001, engine="port", threads=1, verbose=False):
-    """runEMclonalCN (binomial allele model, useOutlierState=FALSE).  Returns the convergeParams
+    """runEMclonalCN (either allele model, useOutlierState=FALSE).  Returns the convergeParams
     list of R/hmmClonal.R:344-367 as a dict of arrays with an iteration axis last."""
     g, nP, sP, pP = (params[k] for k in ("genotypeParams", "normalParams", "cellPrevParams", "ploidyParams"))
-    if g.get("alleleEmissionModel", "binomial") != "binomial":
-        raise NotImplementedError("oracle covers the binomial allele model (production path)")
+    gauss = g.get("alleleEmissionModel", "binomial") == "Gaussian"
     ref, depth, logR = (np.asarray(data[k], float) for k in ("ref", "tumDepth", "logR"))
     Z, U, N = len(sP["s_0"]), len(g["rt"]), ref.size
     chrsI = chromosome_slices(data["chr"])
@@ -633,12 +872,21 @@ def run_em_clonal_cn(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15,
     n = np.zeros(maxit); phi = np.zeros(maxit); loglik = np.zeros(maxit)
     s = np.zeros((Z, maxit)); var = np.zeros((U, maxit)); piG = np.zeros((U, maxit)); piZ = np.zeros((Z, maxit))
     muR = np.zeros((U, Z, maxit)); muC = np.zeros((U, Z, maxit))
+    varR = np.zeros((U, maxit))
     i = 0                                   # 0-based column (R's i = 1)
     loglik[i] = -np.inf
     s[:, i], var[:, i], phi[i], n[i] = sP["s_0"], g["var_0"], pP["phi_0"], nP["n_0"]
+    varR[:, i] = g.get("varR_0", np.full(U, 1 / 20))
     piG[:, i], piZ[:, i] = g["piG_0"], sP["piZ_0"]
     muR[:, :, i], muC[:, :, i] = clonal_two_component_mixture(g["rt"], g["rn"], n[i], s[:, i], g["ct"], phi[i])
-    py = compute_py_c(ref, depth, logR, muR[:, :, i], muC[:, :, i], var[:, i], pseudoCounts)
+
+    def emissions(col):
+        if gauss:                                                   # :149-158, :265-274
+            return compute_py_gauss(ref, depth, logR, muR[:, :, col], muC[:, :, col], varR[:, col], var[:, col],
+                                    g["corRho_0"], pseudoCounts)
+        return compute_py_c(ref, depth, logR, muR[:, :, col], muC[:, :, col], var[:, col], pseudoCounts)
+
+    py = emissions(i)
     converged = False
     es = None
     sweeps = []
@@ -648,13 +896,15 @@ def run_em_clonal_cn(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15,
                     engine=engine, threads=threads)
         loglik[i] = es["loglik"]
         mo = m_step(data, es, n[i - 1], s[:, i - 1], phi[i - 1], var[:, i - 1], piG[:, i - 1], piZ[:, i - 1],
-                    chrPos_0, params, normalEstimateMethod, estimateS, estimatePloidy, maxiterUpdate)
+                    chrPos_0, params, normalEstimateMethod, estimateS, estimatePloidy, maxiterUpdate,
+                    varR_0=varR[:, i - 1])
         sweeps.append(mo["sweeps"])
         n[i], s[:, i], var[:, i], phi[i], piZ[:, i], piG[:, i] = mo["n"], mo["s"], mo["var"], mo["phi"], mo["piZ"], mo["piG"]
+        varR[:, i] = mo["varR"]
         muR[:, :, i], muC[:, :, i] = clonal_two_component_mixture(g["rt"], g["rn"], n[i], s[:, i], g["ct"], phi[i])
-        py = compute_py_c(ref, depth, logR, muR[:, :, i], muC[:, :, i], var[:, i], pseudoCounts)
+        py = emissions(i)
         pr = prior_probs(n[i], s[:, i], phi[i], var[:, i], piG[:, i], piZ[:, i], g, nP, sP, pP,
-                         normalEstimateMethod, estimateS, estimatePloidy)
+                         normalEstimateMethod, estimateS, estimatePloidy, varR=varR[:, i])
         loglik[i] = loglik[i] + pr["prior"]
         if verbose:
             print(f"EM iter {i}: loglik={loglik[i]:.4f} n={n[i]:.4f} phi={phi[i]:.4f} s={s[:, i]}")
@@ -664,7 +914,7 @@ def run_em_clonal_cn(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15,
             converged = True
             i -= 1
     m = i + 1
-    return {"n": n[:m], "s": s[:, :m], "var": var[:, :m], "phi": phi[:m], "piG": piG[:, :m], "piZ": piZ[:, :m],
+    return {"n": n[:m], "s": s[:, :m], "var": var[:, :m], "varR": varR[:, :m], "phi": phi[:m], "piG": piG[:, :m], "piZ": piZ[:, :m],
             "muR": muR[:, :, :m], "muC": muC[:, :, :m], "loglik": loglik[:m],
             "rhoG": es["rhoG"] if es else None, "rhoZ": es["rhoZ"] if es else None,
             "txnExpLen": txnExpLen, "txnZstrength": txnZstrength, "useOutlierState": False,
@@ -679,7 +929,14 @@ def viterbi_clonal_cn(data, cp, engine="port", threads=1):
     Z = cp["s"].shape[0]
     i = cp["s"].shape[1] - 1
     ref, depth, logR = (np.asarray(data[k], float) for k in ("ref", "tumDepth", "logR"))
-    py = compute_py_c(ref, depth, logR, cp["muR"][:, :, i], cp["muC"][:, :, i], cp["var"][:, i], 1e-300)
+    if g.get("alleleEmissionModel", "binomial") == "Gaussian":
+        # :439-447: convergeParams carries no corRho_0 element, so computeBivariateNormalObslik receives NULL and
+        # falls back to the correlation of getBivariateCovariance(x1, x2) (:536-538); no pseudoCounts are added
+        cor = bivariate_covariance(ref / depth, logR)["cor"]
+        py = compute_py_gauss(ref, depth, logR, cp["muR"][:, :, i], cp["muC"][:, :, i], cp["varR"][:, i], cp["var"][:, i],
+                              cor, 0.0)
+    else:
+        py = compute_py_c(ref, depth, logR, cp["muR"][:, :, i], cp["muC"][:, :, i], cp["var"][:, i], 1e-300)
     piGiZi = np.outer(cp["piG"][:, i - 1], cp["piZ"][:, i - 1]).reshape(-1, order="F")
     log_pi = np.vectorize(math.log)(piGiZi)
     chrsI = chromosome_slices(data["chr"])

@@ -583,7 +583,7 @@ def test_fused_r_glue_returns_the_runEMclonalCN_list_and_an_int_path():
     hyper.update({k: pP[k] for k in ("phi_0", "alphaPHyper", "betaPHyper")})
     out = glue.call("titan_em_run_R", solver, glue.named_list(hyper, keep), R(4), R(1500), R(1), R(1), R(1), R(0.001))
     fit = glue.list_to_dict(out)
-    assert list(fit) == ["n", "s", "var", "phi", "piG", "piZ", "muR", "muC", "loglik", "rhoG", "rhoZ"]
+    assert list(fit) == ["n", "s", "var", "varR", "phi", "piG", "piZ", "muR", "muC", "loglik", "rhoG", "rhoZ"]
     U, Z, N, I = len(g["rt"]), 2, data["posn"].size, want["n"].size
     assert fit["n"].shape == (I,) and fit["s"].shape == (Z, I) and fit["var"].shape == (U, I) and fit["muR"].shape == (U * Z, I)
     assert fit["rhoG"].shape == (U, N) and fit["rhoZ"].shape == (Z, N)

@@ -32,13 +32,14 @@ ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NUMERIC = 1, 2, 3, 4, 5
 class DataDesc(C.Structure):
     _fields_ = [("N", C.c_int64), ("nChr", C.c_int32), ("chr_start", c_i64_p), ("posn", c_double_p),
                 ("ref", c_double_p), ("tumDepth", c_double_p), ("logR", c_double_p), ("txnExpLen", C.c_double),
-                ("txnZstrength", C.c_double), ("U", C.c_int32), ("Z", C.c_int32), ("ZS", c_double_p)]
+                ("txnZstrength", C.c_double), ("U", C.c_int32), ("Z", C.c_int32), ("ZS", c_double_p),
+                ("alleleModel", C.c_int32)]
 
 
 class Params(C.Structure):
     _fields_ = [("n", C.c_double), ("phi", C.c_double), ("s", c_double_p), ("var", c_double_p),
                 ("piG", c_double_p), ("piZ", c_double_p), ("rt", c_double_p), ("ct", c_double_p),
-                ("rn", C.c_double)]
+                ("rn", C.c_double), ("varR", c_double_p), ("corRho", C.c_double)]
 
 
 class EstepOut(C.Structure):
@@ -53,7 +54,9 @@ class Hyper(C.Structure):
                 ("s_0", c_double_p), ("alphaSHyper", c_double_p), ("betaSHyper", c_double_p),
                 ("kappaZHyper", c_double_p), ("piZ_0", c_double_p),
                 ("n_0", C.c_double), ("alphaNHyper", C.c_double), ("betaNHyper", C.c_double),
-                ("phi_0", C.c_double), ("alphaPHyper", C.c_double), ("betaPHyper", C.c_double)]
+                ("phi_0", C.c_double), ("alphaPHyper", C.c_double), ("betaPHyper", C.c_double),
+                ("varR_0", c_double_p), ("alphaRHyper", c_double_p), ("betaRHyper", c_double_p),
+                ("corRho_0", C.c_double)]
 
 
 class EmOpts(C.Structure):
@@ -67,7 +70,7 @@ class EmOut(C.Structure):
                 ("s", c_double_p), ("piZ", c_double_p), ("var", c_double_p), ("piG", c_double_p),
                 ("muR", c_double_p), ("muC", c_double_p), ("rhoG", c_double_p), ("rhoZ", c_double_p),
                 ("cd_sweeps", C.POINTER(C.c_int32)), ("estep_ms", C.c_double), ("mstep_ms", C.c_double),
-                ("reduce_ms", C.c_double)]
+                ("reduce_ms", C.c_double), ("varR", c_double_p)]
 
 
 class Timing(C.Structure):
@@ -84,7 +87,7 @@ EXPORTS = [
     "titan_last_error", "titan_version", "titan_device_count", "titan_set_device",
     "titan_fwd_back_clonalCN", "titan_viterbi_clonalCN", "titan_get_position_overlap",
     "titan_solver_create", "titan_solver_destroy", "titan_solver_configure", "titan_solver_set_stream",
-    "titan_estep", "titan_viterbi", "titan_em_run", "titan_mstep", "titan_solver_timing",
+    "titan_estep", "titan_viterbi", "titan_em_run", "titan_mstep", "titan_mstep_gaussian", "titan_solver_timing",
     "titan_release_cached_memory", "titan_measure_fp64_peak",
     "titan_solver_shape", "titan_comm_unique_id", "titan_comm_create", "titan_comm_destroy", "titan_comm_info", "titan_solver_set_comm",
 ]
@@ -122,6 +125,10 @@ def lib():
                               c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, C.c_double,
                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                               c_double_p, c_int_p, c_double_p]
+    L.titan_mstep_gaussian.argtypes = [C.POINTER(Hyper), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p,
+                                       C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, c_double_p, c_double_p, c_int_p, c_double_p]
     L.titan_solver_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.titan_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
     L.titan_solver_shape.argtypes = [C.c_void_p, c_i64_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]

@@ -103,8 +103,10 @@ SEXP getPositionOverlapC(SEXP posn, SEXP start, SEXP stop) {
 SEXP titan_solver_create_R(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP titan_em_run_R(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP titan_viterbi_R(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP titan_solver_create_gaussian_R(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP titan_viterbi_gaussian_R(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
-/* the reference's table (src/register.c:8-13) first, unchanged; then the three additions */
+/* the reference's table (src/register.c:8-13) first, unchanged; then the solver routines */
 static const R_CallMethodDef callMethods[] = {
     {"getPositionOverlapC", (DL_FUNC)&getPositionOverlapC, 3},
     {"fwd_backC_clonalCN", (DL_FUNC)&fwd_backC_clonalCN, 9},
@@ -112,6 +114,8 @@ static const R_CallMethodDef callMethods[] = {
     {"titan_solver_create_R", (DL_FUNC)&titan_solver_create_R, 9},
     {"titan_em_run_R", (DL_FUNC)&titan_em_run_R, 8},
     {"titan_viterbi_R", (DL_FUNC)&titan_viterbi_R, 10},
+    {"titan_solver_create_gaussian_R", (DL_FUNC)&titan_solver_create_gaussian_R, 9},
+    {"titan_viterbi_gaussian_R", (DL_FUNC)&titan_viterbi_gaussian_R, 12},
     {NULL, NULL, 0}};
 
 void R_init_TitanCNA(DllInfo *info) { R_registerRoutines(info, NULL, callMethods, NULL, NULL); }

@@ -12,6 +12,11 @@
  *                                                    # loglik rhoG rhoZ, iteration axis trimmed to 1:i
  *   path   <- .Call("titan_viterbi_R", solver, n, s, phi, var, piG, piZ, rt, ct, rn)   # INTSXP[N], 1-based
  *
+ * alleleEmissionModel = "Gaussian" (R/hmmClonal.R:149-158,265-274,439-447): titan_solver_create_gaussian_R (same
+ * arguments) builds the solver for the bivariate-normal emission, titan_em_run_R then also reads hyper$varR_0,
+ * alphaRHyper, betaRHyper, corRho_0, and titan_viterbi_gaussian_R takes the varR column and the correlation as two
+ * more arguments.
+ *
  * The solver is an external pointer whose finalizer releases the device memory when R collects it.
  * In this repository (no R installation) the file is compiled against oracle/shim/R.h and driven through the
  * ctypes .Call emulation (tests/test_gpu_parity.py::test_fused_r_glue_*).
@@ -58,8 +63,8 @@ static titan_solver *solver_of(SEXP ptr, const char *who) {
 }
 
 /* chr_start: offsets [nChr+1] of the contiguous chromosome runs of data$chr (0-based, last = N) */
-SEXP titan_solver_create_R(SEXP chr_start, SEXP posn, SEXP ref, SEXP depth, SEXP logR, SEXP txnExpLen, SEXP txnZstrength,
-                           SEXP ZS, SEXP Z) {
+static SEXP solver_create(SEXP chr_start, SEXP posn, SEXP ref, SEXP depth, SEXP logR, SEXP txnExpLen, SEXP txnZstrength,
+                          SEXP ZS, SEXP Z, int alleleModel) {
   PROTECT(chr_start = AS_NUMERIC(chr_start));
   PROTECT(posn = AS_NUMERIC(posn));
   PROTECT(ref = AS_NUMERIC(ref));
@@ -77,12 +82,22 @@ SEXP titan_solver_create_R(SEXP chr_start, SEXP posn, SEXP ref, SEXP depth, SEXP
   d.posn = REAL(posn); d.ref = REAL(ref); d.tumDepth = REAL(depth); d.logR = REAL(logR);
   d.txnExpLen = asReal(txnExpLen); d.txnZstrength = asReal(txnZstrength);
   d.U = LENGTH(ZS); d.Z = asInteger(Z); d.ZS = REAL(ZS);
+  d.alleleModel = alleleModel;
   titan_solver *s = NULL;
   if (titan_solver_create(&d, &s) != TITAN_OK) error("titan_solver_create: %s", titan_last_error());
   SEXP ptr = PROTECT(R_MakeExternalPtr(s, R_NilValue, R_NilValue));
   R_RegisterCFinalizerEx(ptr, solver_finalizer, TRUE);
   UNPROTECT(7);
   return ptr;
+}
+
+SEXP titan_solver_create_R(SEXP chr_start, SEXP posn, SEXP ref, SEXP depth, SEXP logR, SEXP txnExpLen, SEXP txnZstrength,
+                           SEXP ZS, SEXP Z) {
+  return solver_create(chr_start, posn, ref, depth, logR, txnExpLen, txnZstrength, ZS, Z, TITAN_ALLELE_BINOMIAL);
+}
+SEXP titan_solver_create_gaussian_R(SEXP chr_start, SEXP posn, SEXP ref, SEXP depth, SEXP logR, SEXP txnExpLen,
+                                    SEXP txnZstrength, SEXP ZS, SEXP Z) {
+  return solver_create(chr_start, posn, ref, depth, logR, txnExpLen, txnZstrength, ZS, Z, TITAN_ALLELE_GAUSSIAN);
 }
 
 static SEXP named_real(SEXP list, SEXP names, int slot, const char *name, int nr, int nc) {
@@ -117,6 +132,11 @@ SEXP titan_em_run_R(SEXP solver, SEXP hyper, SEXP maxiter, SEXP maxiterUpdate, S
   h.kappaZHyper = need_vec(hyper, "kappaZHyper", Z); h.piZ_0 = need_vec(hyper, "piZ_0", Z);
   h.n_0 = need_num(hyper, "n_0"); h.alphaNHyper = need_num(hyper, "alphaNHyper"); h.betaNHyper = need_num(hyper, "betaNHyper");
   h.phi_0 = need_num(hyper, "phi_0"); h.alphaPHyper = need_num(hyper, "alphaPHyper"); h.betaPHyper = need_num(hyper, "betaPHyper");
+  /* optional: read by a Gaussian solver (which refuses to run without them), carried along by a binomial one */
+  if (!isNull(list_get(hyper, "varR_0"))) h.varR_0 = need_vec(hyper, "varR_0", U);
+  if (!isNull(list_get(hyper, "alphaRHyper"))) h.alphaRHyper = need_vec(hyper, "alphaRHyper", U);
+  if (!isNull(list_get(hyper, "betaRHyper"))) h.betaRHyper = need_vec(hyper, "betaRHyper", U);
+  if (!isNull(list_get(hyper, "corRho_0"))) h.corRho_0 = need_num(hyper, "corRho_0");
   titan_em_opts o;
   memset(&o, 0, sizeof o);
   o.maxiter = asInteger(maxiter); o.maxiterUpdate = asInteger(maxiterUpdate); o.normal_map = asInteger(normal_map);
@@ -131,8 +151,9 @@ SEXP titan_em_run_R(SEXP solver, SEXP hyper, SEXP maxiter, SEXP maxiterUpdate, S
   out.s = (double *)R_alloc((size_t)Z * M, sizeof(double)); out.piZ = (double *)R_alloc((size_t)Z * M, sizeof(double));
   out.var = (double *)R_alloc((size_t)U * M, sizeof(double)); out.piG = (double *)R_alloc((size_t)U * M, sizeof(double));
   out.muR = (double *)R_alloc((size_t)K * M, sizeof(double)); out.muC = (double *)R_alloc((size_t)K * M, sizeof(double));
+  out.varR = (double *)R_alloc((size_t)U * M, sizeof(double));
 
-  enum { F_n, F_s, F_var, F_phi, F_piG, F_piZ, F_muR, F_muC, F_loglik, F_rhoG, F_rhoZ, F_count };
+  enum { F_n, F_s, F_var, F_varR, F_phi, F_piG, F_piZ, F_muR, F_muC, F_loglik, F_rhoG, F_rhoZ, F_count };
   SEXP list = PROTECT(allocVector(VECSXP, F_count)), names = PROTECT(allocVector(STRSXP, F_count));
   SEXP rhoG = named_real(list, names, F_rhoG, "rhoG", U, N), rhoZ = named_real(list, names, F_rhoZ, "rhoZ", Z, N);
   out.rhoG = REAL(rhoG);
@@ -145,6 +166,7 @@ SEXP titan_em_run_R(SEXP solver, SEXP hyper, SEXP maxiter, SEXP maxiterUpdate, S
   memcpy(REAL(named_real(list, names, F_s, "s", Z, I)), out.s, sizeof(double) * (size_t)Z * I);
   memcpy(REAL(named_real(list, names, F_piZ, "piZ", Z, I)), out.piZ, sizeof(double) * (size_t)Z * I);
   memcpy(REAL(named_real(list, names, F_var, "var", U, I)), out.var, sizeof(double) * (size_t)U * I);
+  memcpy(REAL(named_real(list, names, F_varR, "varR", U, I)), out.varR, sizeof(double) * (size_t)U * I);
   memcpy(REAL(named_real(list, names, F_piG, "piG", U, I)), out.piG, sizeof(double) * (size_t)U * I);
   /* muR / muC: [U, Z, i] arrays; handed over as (U*Z) x i matrices, R sets dim <- c(U, Z, i) */
   memcpy(REAL(named_real(list, names, F_muR, "muR", K, I)), out.muR, sizeof(double) * (size_t)K * I);
@@ -156,7 +178,8 @@ SEXP titan_em_run_R(SEXP solver, SEXP hyper, SEXP maxiter, SEXP maxiterUpdate, S
 
 /* Emission parameters from column i, initial distribution from column i-1 (R/hmmClonal.R:402,466-467): the caller
  * passes exactly those vectors. */
-SEXP titan_viterbi_R(SEXP solver, SEXP n, SEXP s_, SEXP phi, SEXP var, SEXP piG, SEXP piZ, SEXP rt, SEXP ct, SEXP rn) {
+static SEXP viterbi_call(SEXP solver, SEXP n, SEXP s_, SEXP phi, SEXP var, SEXP piG, SEXP piZ, SEXP rt, SEXP ct, SEXP rn,
+                         SEXP varR, SEXP corRho) {
   titan_solver *s = solver_of(solver, "titan_viterbi_R");
   PROTECT(s_ = AS_NUMERIC(s_));
   PROTECT(var = AS_NUMERIC(var));
@@ -171,10 +194,25 @@ SEXP titan_viterbi_R(SEXP solver, SEXP n, SEXP s_, SEXP phi, SEXP var, SEXP piG,
   memset(&p, 0, sizeof p);
   p.n = asReal(n); p.phi = asReal(phi); p.s = REAL(s_); p.var = REAL(var); p.piG = REAL(piG); p.piZ = REAL(piZ);
   p.rt = REAL(rt); p.ct = REAL(ct); p.rn = asReal(rn);
+  if (varR != R_NilValue) {
+    PROTECT(varR = AS_NUMERIC(varR));
+    if (LENGTH(varR) != U) error("titan_viterbi_gaussian_R: varR must have length(rt) entries");
+    p.varR = REAL(varR);
+    p.corRho = asReal(corRho);
+  }
   int64_t N = 0;
   if (titan_solver_shape(s, &N, NULL, NULL, NULL) != TITAN_OK) error("titan_viterbi_R: %s", titan_last_error());
   SEXP path = PROTECT(allocVector(INTSXP, (R_len_t)N));
   if (titan_viterbi(s, &p, (int32_t *)INTEGER(path)) != TITAN_OK) error("titan_viterbi: %s", titan_last_error());
-  UNPROTECT(7);
+  UNPROTECT(varR != R_NilValue ? 8 : 7);
   return path;
+}
+
+SEXP titan_viterbi_R(SEXP solver, SEXP n, SEXP s_, SEXP phi, SEXP var, SEXP piG, SEXP piZ, SEXP rt, SEXP ct, SEXP rn) {
+  return viterbi_call(solver, n, s_, phi, var, piG, piZ, rt, ct, rn, R_NilValue, R_NilValue);
+}
+/* corRho: the reference's viterbiClonalCN re-derives it from the data (R/hmmClonal.R:447,536-538) */
+SEXP titan_viterbi_gaussian_R(SEXP solver, SEXP n, SEXP s_, SEXP phi, SEXP var, SEXP piG, SEXP piZ, SEXP rt, SEXP ct, SEXP rn,
+                              SEXP varR, SEXP corRho) {
+  return viterbi_call(solver, n, s_, phi, var, piG, piZ, rt, ct, rn, varR, corRho);
 }

@@ -265,6 +265,7 @@ struct titan_solver {
   int64_t N = 0;
   int nChr = 0, U = 0, Z = 0, K = 0, h = 0;
   bool legacy_py = false;          // emissions come from a materialised py matrix
+  bool gauss = false;              // alleleEmissionModel == "Gaussian": bivariate normal on (ref / tumDepth, logR)
   std::vector<int64_t> chr_start;
   std::vector<unsigned char> het;
   std::shared_ptr<const GapTables> gaps;   // host-exact transition terms of this data set (shared between solvers)
@@ -300,6 +301,7 @@ struct titan_solver {
   int round_batch = 4;             // verification rounds queued per host synchronisation
   DevBuf<unsigned int> rerun;      // [2][kRoundSlots]
   DevBuf<double> model;            // packed ModelConsts arrays
+  double model_l0 = 0, model_rho2 = 0;   // Gaussian allele model: scalars of the last upload_model
   DevBuf<unsigned char> het_d;
   PinBuf<double> model_h, out_h;
   PinBuf<unsigned int> rerun_h;
@@ -405,6 +407,7 @@ struct SolverInit {
   int U, Z;
   const double *ZS;
   int nZS;
+  int alleleModel = 0;
 };
 
 
@@ -420,6 +423,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (in.U < 1 || in.U > 64)
     return fail(TITAN_ERR_UNSUPPORTED, "%d genotype states: the warp-per-chunk kernels cover up to 64 (two per lane)", in.U);
   if (!in.ZS || in.nZS < in.U) return fail(TITAN_ERR_ARG, "zygosityKey must have %d entries", in.U);
+  if (in.alleleModel != TITAN_ALLELE_BINOMIAL && in.alleleModel != TITAN_ALLELE_GAUSSIAN)
+    return fail(TITAN_ERR_ARG, "loadDefaultParameters: alleleEmissionModel must be either \"binomial\" or \"Gaussian\".");
   if (!(in.txnExpLen > 0) || !(in.zStrength > 0))
     return fail(TITAN_ERR_ARG, "txnExpLen / zStrength must be positive scalars (length-0 arguments are rejected, "
                                "cf. R/utils.R:1514-1516)");
@@ -479,6 +484,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     s->h = 0;
     for (int u = 0; u < in.U; ++u) { s->het[u] = (in.ZS[u] == -1); s->h += s->het[u]; }
     s->legacy_py = in.py != nullptr;
+    s->gauss = !s->legacy_py && in.alleleModel == TITAN_ALLELE_GAUSSIAN;
+    const bool gauss = s->gauss;
     const int64_t N = in.N;
     const int K = s->K;
 
@@ -492,11 +499,11 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     } rec_builder;
     if (!s->legacy_py && in.ref && in.depth && in.logR) {
       rec.resize((size_t)N);
-      rec_builder.t = std::thread([&rec, &bad_snp, &in, N]() {
+      rec_builder.t = std::thread([&rec, &bad_snp, &in, N, gauss]() {
         double dmax = 0;
         for (int64_t t = 0; t < N; ++t) dmax = std::max(dmax, in.depth[t]);
         th::LgammaTable tab;
-        if (dmax >= 0 && dmax < 1e7) tab.ensure((int64_t)dmax);       // shared read-only table; larger depths use lgamma directly
+        if (!gauss && dmax >= 0 && dmax < 1e7) tab.ensure((int64_t)dmax);       // shared read-only table; larger depths use lgamma directly
         const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
         std::vector<std::thread> pool;
         for (unsigned w = 0; w < nt; ++w)
@@ -509,6 +516,19 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
                 int64_t expect = -1;
                 bad_snp.compare_exchange_strong(expect, t);
                 return;
+              }
+              if (gauss) {      // x1 = ref / tumDepth (R/hmmClonal.R:153); a NaN ratio makes the reference's sums NA
+                const double r = x / d;
+                if (!(r == r)) {
+                  int64_t expect = -1;
+                  bad_snp.compare_exchange_strong(expect, t);
+                  return;
+                }
+                rec[t].x = r;
+                rec[t].nx = r * r;
+                rec[t].lr = in.logR[t];
+                rec[t].lb = r * in.logR[t];
+                continue;
               }
               rec[t].x = x;
               rec[t].nx = d - x;
@@ -634,8 +654,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     trace.mark("alpha alloc");
     s->het_d.alloc(s->U);
     CK(cudaMemcpy(s->het_d.p, s->het.data(), s->U, cudaMemcpyHostToDevice));
-    s->model.alloc(5 * (size_t)K + 3 * (size_t)s->U);
-    s->model_h.alloc(5 * (size_t)K + 3 * (size_t)s->U);
+    s->model.alloc(5 * (size_t)K + 7 * (size_t)s->U);
+    s->model_h.alloc(5 * (size_t)K + 7 * (size_t)s->U);
     s->out.alloc(6 * (size_t)K + s->nChr);
     s->rhoG0.alloc((size_t)s->nChr * s->U);
     s->rhoZ0.alloc((size_t)s->nChr * s->Z);
@@ -658,6 +678,7 @@ extern "C" int titan_solver_create(const titan_data_desc *d, titan_solver **out)
   if (!d) return fail(TITAN_ERR_ARG, "titan_solver_create: desc is NULL");
   SolverInit in{d->N, d->nChr, d->chr_start, d->posn, d->ref, d->tumDepth, d->logR, nullptr,
                 d->txnExpLen, d->txnZstrength * d->txnExpLen, d->U, d->Z, d->ZS, d->U};
+  in.alleleModel = d->alleleModel;
   return solver_create_impl(in, out);
 }
 
@@ -790,6 +811,12 @@ static ModelConsts model_layout(const titan_solver *s, double *base) {
   M.cN = base + 5 * K;
   M.i2v = base + 5 * K + U;
   M.tv = base + 5 * K + 2 * U;
+  M.gR = base + 5 * K + 3 * U;
+  M.gX = base + 5 * K + 4 * U;
+  M.vR = base + 5 * K + 5 * U;
+  M.sq = base + 5 * K + 6 * U;
+  M.l0 = s->model_l0; M.rho2 = s->model_rho2;
+  M.gauss = s->gauss ? 1 : 0;
   return M;
 }
 
@@ -812,6 +839,35 @@ static int upload_model(titan_solver *s, const titan_params *p, double *muR_out,
     if (!p->s || !p->var || !p->rt || !p->ct) return fail(TITAN_ERR_ARG, "titan_params: s, var, rt and ct are required");
     std::vector<double> muR((size_t)K);
     th::mixture_means(U, Z, p->rt, p->rn, p->n, p->s, p->ct, p->phi, muR.data(), muC);
+    if (s->gauss) {
+      // bivariateNormalpdflog (R/hmmClonal.R:550-559) with var1 = varR (allelic), var2 = var (logR): the constants in
+      // R's association order for the exact (Viterbi) evaluation, and folded coefficients for the E-step
+      if (!p->varR) return fail(TITAN_ERR_ARG, "titan_params: varR is required by the Gaussian allele model");
+      const double rho = p->corRho;
+      if (!(rho > -1 && rho < 1)) return fail(TITAN_ERR_NUMERIC, "corRho=%g outside (-1, 1)", rho);
+      double *gR = (double *)H.gR, *gX = (double *)H.gX, *vR = (double *)H.vR, *sq = (double *)H.sq;
+      const double l0 = 1 / (2 * (1 - rho * rho));
+      s->model_l0 = l0;
+      s->model_rho2 = 2 * rho;
+      for (int j = 0; j < K; ++j) {
+        if (!std::isfinite(muR[j]) || !std::isfinite(muC[j]))
+          return fail(TITAN_ERR_NUMERIC, "mixture mean out of range at state %d (muR=%g muC=%g)", j, muR[j], muC[j]);
+        lmu[j] = muR[j];
+        l1mu[j] = 0.0;
+      }
+      for (int u = 0; u < U; ++u) {
+        const double var1 = p->varR[u], var2 = p->var[u];
+        if (!(var1 > 0) || !(var2 > 0))
+          return fail(TITAN_ERR_NUMERIC, "non-positive variance at state %d (varR=%g var=%g)", u, var1, var2);
+        cN[u] = -std::log((2 * th::kPi) * std::sqrt((var1 * var2) * (1 - rho * rho)));
+        tv[u] = var2;
+        vR[u] = var1;
+        sq[u] = std::sqrt(var1 * var2);
+        i2v[u] = l0 / var2;
+        gR[u] = l0 / var1;
+        gX[u] = l0 * (2 * rho) / sq[u];
+      }
+    } else {
     for (int j = 0; j < K; ++j) {
       if (!(muR[j] > 0) || !(muR[j] <= 1) || !std::isfinite(muC[j]))
         return fail(TITAN_ERR_NUMERIC, "mixture mean out of range at state %d (muR=%g muC=%g)", j, muR[j], muC[j]);
@@ -824,10 +880,12 @@ static int upload_model(titan_solver *s, const titan_params *p, double *muR_out,
       tv[u] = 2 * p->var[u];
       i2v[u] = 1.0 / tv[u];
     }
+    }
     if (muR_out) std::copy(muR.begin(), muR.end(), muR_out);
     if (muC_out) std::copy(muC, muC + K, muC_out);
   }
-  CK(cudaMemcpyAsync(s->model.p, hb, sizeof(double) * (5 * (size_t)K + 3 * (size_t)U), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->model.p, hb, sizeof(double) * (5 * (size_t)K + (s->gauss ? 7 : 3) * (size_t)U), cudaMemcpyHostToDevice,
+                     s->stream));
   return TITAN_OK;
 }
 
@@ -1290,7 +1348,8 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   if (mode == 4 && !redux_ok) mode = cluster_ok ? 3 : 2;
   if (mode == 3 && !cluster_ok) mode = 2;
   if (mode == 2 && !fast_ok) mode = 0;
-  if (mode >= 2) {
+  bool dense_from_py = s->legacy_py;
+  if (mode >= 2 || s->gauss) {   // (the dense scan evaluates only the binomial emission in place)
     if (!s->legacy_py) {   // exact log emissions, materialised in the (idle) alpha buffer
       const long long total = (long long)s->N * K;
       const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
@@ -1299,12 +1358,15 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
       s->tm.kernel_launches += 1;
       s->state_valid = false;
       A.py = s->alpha.p;
+      dense_from_py = true;
     }
+  }
+  if (mode >= 2) {
     if (mode == 4) launch_vit_redux(A, s->nChr, s->stream);
     else if (mode == 3) launch_vit_cluster(A, s->nChr, s->stream);
     else launch_vit_fast(A, s->nChr, K, fP, fPER, s->stream);
   } else {
-    launch_vit_dense(A, s->nChr, K, s->legacy_py, s->stream);
+    launch_vit_dense(A, s->nChr, K, dense_from_py, s->stream);
   }
   CK(cudaGetLastError());
   launch_backtrace(A, s->nTiles, s->stream);
@@ -1553,7 +1615,7 @@ extern "C" int titan_get_position_overlap(const double *posn, int T, const doubl
 // ---------------------------------------------------------------------------------------------
 // M-step and the EM driver
 // ---------------------------------------------------------------------------------------------
-static int hyper_from_c(const titan_hyper *h, int U, int Z, th::Hyper *H) {
+static int hyper_from_c(const titan_hyper *h, int U, int Z, th::Hyper *H, bool gauss = false) {
   if (!h || !h->rt || !h->ct || !h->var_0 || !h->alphaKHyper || !h->betaKHyper || !h->kappaGHyper || !h->piG_0 ||
       !h->s_0 || !h->alphaSHyper || !h->betaSHyper || !h->kappaZHyper || !h->piZ_0)
     return fail(TITAN_ERR_ARG, "params must include genotypeParams, ploidyParams, normalParams, cellPrevParams.");
@@ -1566,6 +1628,16 @@ static int hyper_from_c(const titan_hyper *h, int U, int Z, th::Hyper *H) {
   H->piZ_0.assign(h->piZ_0, h->piZ_0 + Z);
   H->rn = h->rn; H->n_0 = h->n_0; H->alphaN = h->alphaNHyper; H->betaN = h->betaNHyper;
   H->phi_0 = h->phi_0; H->alphaP = h->alphaPHyper; H->betaP = h->betaPHyper;
+  H->gauss = gauss;
+  if (gauss) {
+    if (!h->varR_0 || !h->alphaRHyper || !h->betaRHyper)
+      return fail(TITAN_ERR_ARG, "genotypeParams must contain varR_0, alphaRHyper, betaRHyper and corRho_0 for the Gaussian "
+                                 "allele model. See loadDefaultParameters(data=).");
+    if (!(h->corRho_0 > -1 && h->corRho_0 < 1)) return fail(TITAN_ERR_ARG, "genotypeParams$corRho_0=%g outside (-1, 1)", h->corRho_0);
+    H->varR_0.assign(h->varR_0, h->varR_0 + U); H->alphaR.assign(h->alphaRHyper, h->alphaRHyper + U);
+    H->betaR.assign(h->betaRHyper, h->betaRHyper + U);
+    H->corRho = h->corRho_0;
+  }
   return TITAN_OK;
 }
 
@@ -1574,9 +1646,11 @@ static int mstep_core(const th::Hyper &H, int nChr, int maxiterUpdate, bool norm
                       const double *stats, const double *rhoG0, const double *rhoZ0, double prev_n, const double *prev_s,
                       const double *prev_var, double prev_phi, const double *prev_piG, const double *prev_piZ,
                       double *out_n, double *out_s, double *out_var, double *out_phi, double *out_piG, double *out_piZ,
-                      int *out_sweeps) {
+                      int *out_sweeps, const double *prev_varR = nullptr, double *out_varR = nullptr) {
   const int U = H.U, Z = H.Z, K = U * Z;
   th::Stats st{stats, stats + K, stats + 2 * K, stats + 3 * K, stats + 4 * K, stats + 5 * K};
+  // Gaussian allele model: the six slots hold a, f, c, h, e, g (titan_common.cuh)
+  th::GStats gst{stats, stats + 2 * K, stats + 4 * K, stats + K, stats + 5 * K, stats + 3 * K};
   // likInitG/Z: sum(t(log(pi_0)) %*% rho[, chrPos_0])  (:43-44)
   double likG = 0, likZ = 0, totG = 0, totZ = 0;
   for (int c = 0; c < nChr; ++c) {
@@ -1587,11 +1661,14 @@ static int mstep_core(const th::Hyper &H, int nChr, int maxiterUpdate, bool norm
     for (int z = 0; z < Z; ++z) { acc += std::log(prev_piZ[z]) * rhoZ0[(size_t)c * Z + z]; totZ += rhoZ0[(size_t)c * Z + z]; }
     likZ += acc;
   }
-  th::MStepOut mo = th::update_parameters(H, st, prev_n, prev_s, prev_var, prev_phi, prev_piG, prev_piZ, likG, likZ,
-                                          normal_map, estS, estP, maxiterUpdate, 10);
+  th::MStepOut mo = H.gauss ? th::update_parameters_gauss(H, gst, prev_n, prev_s, prev_var, prev_varR, prev_phi, prev_piG,
+                                                          prev_piZ, likG, likZ, normal_map, estS, estP, maxiterUpdate, 10)
+                            : th::update_parameters(H, st, prev_n, prev_s, prev_var, prev_phi, prev_piG, prev_piZ, likG, likZ,
+                                                    normal_map, estS, estP, maxiterUpdate, 10);
   *out_n = mo.n; *out_phi = mo.phi;
   std::copy(mo.s.begin(), mo.s.end(), out_s);
   std::copy(mo.var.begin(), mo.var.end(), out_var);
+  if (H.gauss && out_varR) std::copy(mo.varR.begin(), mo.varR.end(), out_varR);
   // pi updates: sum() over the whole sub-matrix (R/paramEstimation.R:533-547)
   double skZ = 0, skG = 0;
   for (int z = 0; z < Z; ++z) skZ += H.kappaZ[z];
@@ -1624,16 +1701,43 @@ extern "C" int titan_mstep(const titan_hyper *h, int U, int Z, int nChr, int max
   return rc;
 }
 
-// runEMclonalCN, R/hmmClonal.R:8-368 (binomial allele model, useOutlierState = FALSE)
+extern "C" int titan_mstep_gaussian(const titan_hyper *h, int U, int Z, int nChr, int maxiterUpdate, int normal_map,
+                                    int estimateS, int estimatePloidy, const double *stats, const double *rhoG0,
+                                    const double *rhoZ0, double prev_n, const double *prev_s, const double *prev_var,
+                                    const double *prev_varR, double prev_phi, const double *prev_piG, const double *prev_piZ,
+                                    double *out_n, double *out_s, double *out_var, double *out_varR, double *out_phi,
+                                    double *out_piG, double *out_piZ, int *out_sweeps, double *out_prior) {
+  th::Hyper H;
+  int rc = hyper_from_c(h, U, Z, &H, true);
+  if (rc != TITAN_OK) return rc;
+  if (!stats || !rhoG0 || !rhoZ0 || !prev_s || !prev_var || !prev_varR || !prev_piG || !prev_piZ || !out_n || !out_s ||
+      !out_var || !out_varR || !out_phi || !out_piG || !out_piZ)
+    return fail(TITAN_ERR_ARG, "titan_mstep_gaussian: NULL argument");
+  rc = mstep_core(H, nChr, maxiterUpdate, normal_map != 0, estimateS != 0, estimatePloidy != 0, stats, rhoG0, rhoZ0, prev_n,
+                  prev_s, prev_var, prev_phi, prev_piG, prev_piZ, out_n, out_s, out_var, out_phi, out_piG, out_piZ,
+                  out_sweeps, prev_varR, out_varR);
+  if (rc == TITAN_OK && out_prior) {
+    th::Priors pr = th::prior_probs(H, *out_n, out_s, *out_phi, out_var, out_piG, out_piZ, normal_map != 0, estimateS != 0,
+                                    estimatePloidy != 0, out_varR);
+    *out_prior = pr.prior;
+  }
+  return rc;
+}
+
+// runEMclonalCN, R/hmmClonal.R:8-368 (either allele model, useOutlierState = FALSE)
 extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_em_opts *o, titan_em_out *out) {
   if (!s || !h || !o || !out) return fail(TITAN_ERR_ARG, "titan_em_run: NULL argument");
   if (s->legacy_py) return fail(TITAN_ERR_ARG, "titan_em_run: solver was created for materialised emissions");
   const int U = s->U, Z = s->Z, K = s->K, nChr = s->nChrOut();      // whole genome when the solution is sharded
   th::Hyper H;
-  int rc = hyper_from_c(h, U, Z, &H);
+  int rc = hyper_from_c(h, U, Z, &H, s->gauss);
   if (rc != TITAN_OK) return rc;
   if (!out->n || !out->phi || !out->loglik || !out->s || !out->piZ || !out->var || !out->piG || !out->muR || !out->muC)
     return fail(TITAN_ERR_ARG, "titan_em_run: output arrays are required");
+  // allelic variances per iteration (:100,:132,:252); the caller's array when given
+  std::vector<double> varR_own;
+  double *varR = out->varR;
+  if (s->gauss && !varR) { varR_own.assign((size_t)U * (o->maxiter + 1), 0.0); varR = varR_own.data(); }
   const int maxit = o->maxiter + 1;   // :92
   const bool nmap = o->normal_map != 0, estS = o->estimateS != 0, estP = o->estimatePloidy != 0;
   double *n = out->n, *phi = out->phi, *loglik = out->loglik;
@@ -1661,6 +1765,11 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
   n[0] = H.n_0;
   std::copy(H.piG_0.begin(), H.piG_0.end(), col(out->piG, U, 0));
   std::copy(H.piZ_0.begin(), H.piZ_0.end(), col(out->piZ, Z, 0));
+  if (varR) {
+    if (s->gauss) std::copy(H.varR_0.begin(), H.varR_0.end(), col(varR, U, 0));
+    else if (h->varR_0) std::copy(h->varR_0, h->varR_0 + U, col(varR, U, 0));
+    else std::fill(col(varR, U, 0), col(varR, U, 0) + U, 1.0 / 20);
+  }
   th::mixture_means(U, Z, H.rt.data(), H.rn, n[0], col(out->s, Z, 0), H.ct.data(), phi[0], col(out->muR, K, 0),
                     col(out->muC, K, 0));
   std::vector<double> stats(6 * (size_t)K), llc(nChr), rG0((size_t)nChr * U), rZ0((size_t)nChr * Z);
@@ -1677,6 +1786,7 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
       p.n = n[i - 1]; p.phi = phi[i - 1]; p.s = col(out->s, Z, i - 1); p.var = col(out->var, U, i - 1);
       p.piG = col(out->piG, U, i - 1); p.piZ = col(out->piZ, Z, i - 1);
       p.rt = H.rt.data(); p.ct = H.ct.data(); p.rn = H.rn;
+      if (s->gauss) { p.varR = col(varR, U, i - 1); p.corRho = H.corRho; }
       titan_estep_out eo{};
       eo.loglik_chr = llc.data(); eo.stats = stats.data(); eo.rhoG0 = rG0.data(); eo.rhoZ0 = rZ0.data();
       rc = estep_impl(s, &p, &eo, false, nullptr);
@@ -1693,13 +1803,15 @@ extern "C" int titan_em_run(titan_solver *s, const titan_hyper *h, const titan_e
       rc = mstep_core(H, nChr, o->maxiterUpdate, nmap, estS, estP, stats.data(), rG0.data(), rZ0.data(), n[i - 1],
                       col(out->s, Z, i - 1), col(out->var, U, i - 1), phi[i - 1], col(out->piG, U, i - 1),
                       col(out->piZ, Z, i - 1), &n[i], col(out->s, Z, i), col(out->var, U, i), &phi[i], col(out->piG, U, i),
-                      col(out->piZ, Z, i), &sweeps);
+                      col(out->piZ, Z, i), &sweeps, s->gauss ? col(varR, U, i - 1) : nullptr,
+                      s->gauss ? col(varR, U, i) : nullptr);
       if (rc != TITAN_OK) return rc;
+      if (varR && !s->gauss) std::copy(col(varR, U, i - 1), col(varR, U, i - 1) + U, col(varR, U, i));   // :212
       if (out->cd_sweeps) out->cd_sweeps[i] = sweeps;
       th::mixture_means(U, Z, H.rt.data(), H.rn, n[i], col(out->s, Z, i), H.ct.data(), phi[i], col(out->muR, K, i),
                         col(out->muC, K, i));
       th::Priors pr = th::prior_probs(H, n[i], col(out->s, Z, i), phi[i], col(out->var, U, i), col(out->piG, U, i),
-                                      col(out->piZ, Z, i), nmap, estS, estP);
+                                      col(out->piZ, Z, i), nmap, estS, estP, s->gauss ? col(varR, U, i) : nullptr);
       loglik[i] = ll + pr.prior;                          // :311
       out->mstep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (o->verbose)

@@ -12,6 +12,9 @@ struct __align__(16) SnpRec {   // parameter-independent per-SNP columns (HBM, r
   double lr;   // logR (natural log)
   double lb;   // lgamma(N+1)-lgamma(x+1)-lgamma(N-x+1), host libm (R/hmmClonal.R:618)
 };
+// Gaussian allele model (alleleEmissionModel = "Gaussian"): the same four slots carry r = ref / tumDepth, r*r, logR and
+// r*logR, so that the six posterior-weighted sums of the final pass (slots x, nx, lr, lb, 1, lr*lr) come out as
+// a, f, c, h, e, g of R/paramEstimation.R:30-32,37-39 without another kernel variant.
 
 // Structured transition between SNP t-1 and t (unused at a chromosome start), stored once per lane class so that a
 // lane reads its own coefficients without selects: half 0 serves non-HET genotypes, half 1 the diploid-HET genotype.
@@ -44,6 +47,14 @@ struct ModelConsts {            // device pointers, refreshed every E-step (K- a
   const double *tv;     // [U] 2*var_u           (Viterbi, exact division as in the reference)
   const double *pi;     // [K] piG_u*piZ_z
   const double *logpi;  // [K] host-libm log of the above
+  // Gaussian allele model (bivariateNormalpdflog, R/hmmClonal.R:550-559); then lmu holds muR itself, cN = -c_u,
+  // i2v = l0/var_u and tv = var_u, and:
+  const double *gR;     // [U] l0/varR_u
+  const double *gX;     // [U] l0*2*corRho/sqrt(varR_u*var_u)
+  const double *vR;     // [U] varR_u                  (Viterbi, exact divisions as in the reference)
+  const double *sq;     // [U] sqrt(varR_u*var_u)
+  double l0, rho2;      // 1/(2*(1-corRho^2)), 2*corRho
+  int gauss;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

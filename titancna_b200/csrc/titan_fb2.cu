@@ -1036,8 +1036,11 @@ __global__ void __launch_bounds__(32 * kWPC, 3) fb2_final_kernel(Fb2Args A, int 
 // ------------------------------------------------------------------------------------------
 constexpr int kEmRun = 32;
 
-template <int Z, int GS, bool FROM_PY>
+// SRC: 0 binomial allele model, 1 materialised log emissions (legacy .Call path), 2 Gaussian allele model
+// (bivariate normal on (ref / tumDepth, logR), R/hmmClonal.R:525-559)
+template <int Z, int GS, int SRC>
 __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
+  constexpr bool FROM_PY = SRC == 1, GAUSS = SRC == 2;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long ta = gw * kEmRun;
@@ -1046,7 +1049,7 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
   const int U = E.U, K = E.K, Kp = E.Kp;
   bool act[GS];
   int g[GS];
-  double lmu[GS][Z], l1mu[GS][Z], muC[GS][Z], cN[GS], i2v[GS];
+  double lmu[GS][Z], l1mu[GS][Z], muC[GS][Z], cN[GS], i2v[GS], gR[GS], gX[GS];
 #pragma unroll
   for (int s = 0; s < GS; ++s) {
     g[s] = lane + 32 * s;
@@ -1056,11 +1059,12 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         lmu[s][z] = E.M.lmu[gg + z * U];
-        l1mu[s][z] = E.M.l1mu[gg + z * U];
+        if (!GAUSS) l1mu[s][z] = E.M.l1mu[gg + z * U];
         muC[s][z] = E.M.muC[gg + z * U];
       }
       cN[s] = E.M.cN[gg];
       i2v[s] = E.M.i2v[gg];
+      if (GAUSS) { gR[s] = E.M.gR[gg]; gX[s] = E.M.gX[gg]; }
     }
   }
   // the run's per-SNP records: one coalesced load per warp, then broadcast reads from shared memory (the dependent
@@ -1090,7 +1094,13 @@ __global__ void __launch_bounds__(128) fb2_emission_kernel(EmArgs E) {
 #pragma unroll
         for (int z = 0; z < Z; ++z) {
           const double d = r.lr - muC[s][z];
-          const double e = (r.lb + (r.x * lmu[s][z] + r.nx * l1mu[s][z])) + (cN[s] - d * d * i2v[s]);
+          double e;
+          if (GAUSS) {
+            const double dr = r.x - lmu[s][z];        // r.x = ref / tumDepth, lmu = muR
+            e = cN[s] - ((dr * dr * gR[s] + d * d * i2v[s]) - dr * d * gX[s]);
+          } else {
+            e = (r.lb + (r.x * lmu[s][z] + r.nx * l1mu[s][z])) + (cN[s] - d * d * i2v[s]);
+          }
           v[s][z] = act[s] ? e : -CUDART_INF;
           mx = fmax(mx, v[s][z]);
         }
@@ -1159,8 +1169,9 @@ cudaError_t fb2_launch_emission(const EmArgs &E, int Z, cudaStream_t st) {
   const int GS = E.U > 32 ? 2 : 1;
   const long long warps = (E.N + kEmRun - 1) / kEmRun;
   const unsigned blocks = (unsigned)((warps + 3) / 4);
-  if (E.py != nullptr) { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, true><<<blocks, 128, 0, st>>>(E))); }
-  else { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, false><<<blocks, 128, 0, st>>>(E))); }
+  if (E.py != nullptr) { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, 1><<<blocks, 128, 0, st>>>(E))); }
+  else if (E.M.gauss) { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, 2><<<blocks, 128, 0, st>>>(E))); }
+  else { FB2_DISPATCH(Z, GS, (fb2_emission_kernel<ZZ, GG, 0><<<blocks, 128, 0, st>>>(E))); }
   return cudaGetLastError();
 }
 

@@ -134,6 +134,10 @@ struct Hyper {
   int U = 0, Z = 0;
   std::vector<double> rt, ct, var_0, alphaK, betaK, kappaG, piG_0, s_0, alphaS, betaS, kappaZ, piZ_0;
   double rn = 0.5, n_0 = 0.5, alphaN = 2, betaN = 2, phi_0 = 2, alphaP = 20, betaP = 42;
+  // alleleEmissionModel == "Gaussian" (R/utils.R:108-119): allelic variance, its prior, the fixed correlation
+  bool gauss = false;
+  std::vector<double> varR_0, alphaR, betaR;
+  double corRho = 0;
 };
 
 struct Stats {   // each [K], joint index u + z*U  (R/paramEstimation.R:34-40)
@@ -156,11 +160,11 @@ inline double dirichletpdflog(const double *x, const double *k, int n) {
   return (std::lgamma(sk) - sl) + l;
 }
 
-struct Priors { double prior, s, n, phi, var, piG, piZ; };
+struct Priors { double prior, s, n, phi, var, piG, piZ, varR; };
 
-// R/hmmClonal.R:715-783 (binomial allele model: no varR term)
+// R/hmmClonal.R:715-783; the varR term (:767-775) only for the Gaussian allele model
 inline Priors prior_probs(const Hyper &h, double n, const double *s, double phi, const double *var, const double *piG,
-                          const double *piZ, bool normal_map, bool estS, bool estP) {
+                          const double *piZ, bool normal_map, bool estS, bool estP, const double *varR = nullptr) {
   Priors p{};
   p.piG = dirichletpdflog(piG, h.kappaG.data(), h.U);
   p.piZ = dirichletpdflog(piZ, h.kappaZ.data(), h.Z);
@@ -174,7 +178,9 @@ inline Priors prior_probs(const Hyper &h, double n, const double *s, double phi,
     if (first) p.var += invgammapdflog(var[k], h.alphaK[k], h.betaK[k]);
   }
   p.phi = estP ? invgammapdflog(phi, h.alphaP, h.betaP) : 0.0;
-  p.prior = p.s + p.n + p.phi + p.var + 0.0 + p.piG + p.piZ;
+  if (h.gauss && varR)
+    for (int k = 0; k < h.U; ++k) p.varR += invgammapdflog(varR[k], h.alphaR[k], h.betaR[k]);
+  p.prior = p.s + p.n + p.phi + p.var + p.varR + p.piG + p.piZ;
   return p;
 }
 
@@ -275,6 +281,139 @@ inline double deriv_phi(const Hyper &h, const Stats &st, double phi, double n, c
   return tot + ((-h.alphaP - 1) / phi + h.betaP / (phi * phi));
 }
 
+// ---- Gaussian allele model: the other branch of the same R functions ---------------------------
+// Statistics (R/paramEstimation.R:29-33,37-39): a = sum (x/N) rho, f = sum (x/N)^2 rho, h = sum (x/N) l rho, c, e, g.
+// The reference's own slips are kept as written: log(1 / 2 * pi * ...) in the objective (:321) and the single
+// subscript a[k], c[k], e[k], mus$R[k], mus$C[k] (= column 1 for every cluster) in the ploidy derivative (:512-513).
+struct GStats {
+  const double *a, *c, *e, *f, *g, *h;   // each [K], joint index u + z*U
+};
+
+// R/paramEstimation.R:287-356, Gaussian branch :313-329
+inline double likelihood_func_gauss(const Hyper &h, const GStats &st, double n, const double *s, const double *var,
+                                    const double *varR, double phi, const double *piG, const double *piZ, double likInitG,
+                                    double likInitZ, bool normal_map, bool estS, bool estP) {
+  const int U = h.U, Z = h.Z;
+  const double rho = h.corRho;
+  std::vector<double> muR((size_t)U * Z), muC((size_t)U * Z);
+  mixture_means(U, Z, h.rt.data(), h.rn, n, s, h.ct.data(), phi, muR.data(), muC.data());
+  double lik = 0;
+  for (int z = 0; z < Z; ++z)
+    for (int k = 0; k < U; ++k) {
+      const int j = k + z * U;
+      const double term1 = st.e[j] * std::log(((1.0 / 2) * kPi) * std::sqrt((var[k] * varR[k]) * (1 - rho * rho)));
+      const double term2 = 1 / (2 * (1 - rho * rho));
+      const double term3 = ((st.f[j] - (2 * st.a[j]) * muR[j]) + st.e[j] * (muR[j] * muR[j])) / (2 * varR[k]);
+      const double term4 = ((st.g[j] - (2 * st.c[j]) * muC[j]) + st.e[j] * (muC[j] * muC[j])) / (2 * var[k]);
+      const double term5 = ((2 * rho) * (((st.h[j] - st.a[j] * muC[j]) - st.c[j] * muR[j]) + (st.e[j] * muC[j]) * muR[j])) /
+                           std::sqrt(var[k] * varR[k]);
+      lik = (lik + term1) - term2 * ((term3 + term4) - term5);
+    }
+  Priors p = prior_probs(h, n, s, phi, var, piG, piZ, normal_map, estS, estP, varR);
+  return lik + p.prior + likInitG + likInitZ + 0.0;
+}
+
+// R/paramEstimation.R:359-399, Gaussian branch :376-383
+inline double deriv_n_gauss(const Hyper &h, const GStats &st, double n, const double *s, const double *var,
+                            const double *varR, double phi) {
+  const int U = h.U, Z = h.Z;
+  const double cn = 2.0, rho = h.corRho;
+  std::vector<double> muR((size_t)U * Z), muC((size_t)U * Z);
+  mixture_means(U, Z, h.rt.data(), h.rn, n, s, h.ct.data(), phi, muR.data(), muC.data());
+  double tot = 0;
+  for (int z = 0; z < Z; ++z)
+    for (int k = 0; k < U; ++k) {
+      const int j = k + z * U;
+      double den = n * cn + (1 - n) * s[z] * cn + (1 - n) * (1 - s[z]) * h.ct[k];
+      double dmuC = (cn - s[z] * cn - (1 - s[z]) * h.ct[k]) / den - (cn - phi) / (n * cn + (1 - n) * phi);
+      double dmuR = ((1 - s[z]) * cn * h.ct[k] * (h.rn - h.rt[k])) / (den * den);
+      const double term0 = 1 / (1 - rho * rho);
+      const double rR = st.a[j] - st.e[j] * muR[j], rC = st.c[j] - st.e[j] * muC[j];
+      const double term1 = rR * dmuR / varR[k];
+      const double term2 = rC * dmuC / var[k];
+      const double term3 = rho * ((rC * dmuR) + (rR * dmuC)) / std::sqrt(varR[k] * var[k]);
+      tot = tot + term0 * (term1 + term2 - term3);
+    }
+  return tot + ((h.alphaN - 1) / n - (h.betaN - 1) / (1 - n));
+}
+
+// R/paramEstimation.R:401-437 for cluster z, Gaussian branch :415-422
+inline double deriv_s_gauss(const Hyper &h, const GStats &st, double sz, int z, double n, const double *var,
+                            const double *varR, double phi) {
+  const int U = h.U;
+  const double cn = 2.0, rho = h.corRho;
+  double tot = 0;
+  for (int k = 0; k < U; ++k) {
+    const int j = k + z * U;
+    double numRef = n * h.rn * cn + (1 - n) * sz * h.rn * cn + (1 - n) * (1 - sz) * h.rt[k] * h.ct[k];
+    double den = n * cn + (1 - n) * sz * cn + (1 - n) * (1 - sz) * h.ct[k];
+    double muR = numRef / den;
+    double muC = std::log(den / (n * cn + (1 - n) * phi));
+    double dmuC = ((1 - n) * cn - (1 - n) * h.ct[k]) / den;
+    double dmuR = ((1 - n) * cn * h.ct[k] * (h.rn - h.rt[k])) / (den * den);
+    const double term0 = 1 / (1 - rho * rho);
+    const double rR = st.a[j] - st.e[j] * muR, rC = st.c[j] - st.e[j] * muC;
+    const double term1 = rR * dmuR / varR[k];
+    const double term2 = rC * dmuC / var[k];
+    const double term3 = rho * ((rC * dmuR) + (rR * dmuC)) / std::sqrt(varR[k] * var[k]);
+    tot = tot + term0 * (term1 + term2 - term3);
+  }
+  return tot + ((h.alphaS[z] - 1) / sz - (h.betaS[z] - 1) / (1 - sz));
+}
+
+// clonalCNDerivativeVarUpdateEqn, R/paramEstimation.R:463-497, over the genotype states ind[0..nInd).
+// logRatio (:168-176): unknown = var of a copy-number level, var2 = varR_prev of the same states.
+// allelicRatio (:187-192): unknown = varR[k] (nInd = 1), var2 = the NEW var[k]; the caller's swap of a <-> c and
+// g := f is done here.  The inverse-gamma prior derivative is summed over all nInd states (:493-494) with R's
+// long-double sum().
+inline double deriv_var_gauss(const Hyper &h, const GStats &st, double v, double n, const double *s, const double *var2,
+                              double phi, const int *ind, int nInd, bool logratio) {
+  const int U = h.U, Z = h.Z;
+  const double cn = 2.0, rho = h.corRho;
+  double dlik = 0;
+  for (int z = 0; z < Z; ++z)
+    for (int q = 0; q < nInd; ++q) {
+      const int k = ind[q], j = k + z * U;
+      double numRef = n * h.rn * cn + (1 - n) * s[z] * h.rn * cn + (1 - n) * (1 - s[z]) * h.rt[k] * h.ct[k];
+      double den = n * cn + (1 - n) * s[z] * cn + (1 - n) * (1 - s[z]) * h.ct[k];
+      const double muR = numRef / den, muC = std::log(den / (n * cn + (1 - n) * phi));
+      const double mus1 = logratio ? muC : muR, mus2 = logratio ? muR : muC;
+      const double A = logratio ? st.a[j] : st.c[j], Cc = logratio ? st.c[j] : st.a[j];
+      const double G = logratio ? st.g[j] : st.f[j];
+      const double term1 = st.e[j] / (2 * v);
+      const double term2 = 1 / (2 * (1 - rho * rho));
+      const double term3 = ((G - (2 * Cc) * mus1) + st.e[j] * (mus1 * mus1)) / (v * v);
+      const double term4 = (rho * (((st.h[j] - Cc * mus2) - A * mus1) + (st.e[j] * mus1) * mus2)) / (v * std::sqrt(v * var2[q]));
+      dlik = (dlik + (-term1)) + (term2 * (term3 - term4));
+    }
+  long double dinv = 0;
+  for (int q = 0; q < nInd; ++q) {
+    const int k = ind[q];
+    const double aK = logratio ? h.alphaK[k] : h.alphaR[k], bK = logratio ? h.betaK[k] : h.betaR[k];
+    dinv += (long double)((-aK - 1) / v + bK / (v * v));
+  }
+  return dlik + (double)dinv;
+}
+
+// R/paramEstimation.R:499-530, Gaussian branch :510-515 (single-subscript indexing = cluster 1, repeated Z times)
+inline double deriv_phi_gauss(const Hyper &h, const GStats &st, double phi, double n, const double *s, const double *var,
+                              const double *varR) {
+  const int U = h.U, Z = h.Z;
+  const double cn = 2.0, rho = h.corRho;
+  std::vector<double> muR((size_t)U * Z), muC((size_t)U * Z);
+  mixture_means(U, Z, h.rt.data(), h.rn, n, s, h.ct.data(), phi, muR.data(), muC.data());
+  const double dmuC = -(1 - n) / (n * cn + (1 - n) * phi);
+  double tot = 0;
+  for (int z = 0; z < Z; ++z)
+    for (int k = 0; k < U; ++k) {
+      const double term0 = 1 / (1 - rho * rho);
+      const double term1 = (st.c[k] - st.e[k] * muC[k]) * dmuC / var[k];
+      const double term2 = rho * ((st.a[k] - st.e[k] * muR[k]) * dmuC) / std::sqrt(varR[k] * var[k]);
+      tot = tot + term0 * (term1 - term2);
+    }
+  return tot + ((-h.alphaP - 1) / phi + h.betaP / (phi * phi));
+}
+
 // Brent's zeroin as used by stats::uniroot (R core zeroin.c, R_zeroin2); R core is not vendored in
 // the reference checkout, so this follows the published Forsythe-Malcolm-Moler / netlib form.
 template <class F>
@@ -339,7 +478,7 @@ inline bool uniroot(F &&f, double lower, double upper, double *root) {
 
 struct MStepOut {
   double n, phi;
-  std::vector<double> s, var;
+  std::vector<double> s, var, varR;
   int sweeps;
   double maxF;
 };
@@ -400,6 +539,77 @@ inline MStepOut update_parameters(const Hyper &h, const Stats &st, double n_0, c
   }
   MStepOut o;
   o.n = n; o.phi = phi; o.s = s; o.var = var; o.sweeps = i - 1; o.maxF = obj;
+  return o;
+}
+
+// Coordinate descent of R/paramEstimation.R:75-283, Gaussian allele model: per sweep n -> s_1..s_Z -> var per
+// copy-number level (uniroot on (eps, 5), :165-183) -> varR per genotype state (:185-200, with the NEW var[k]) -> phi.
+inline MStepOut update_parameters_gauss(const Hyper &h, const GStats &st, double n_0, const double *s_0, const double *var_0,
+                                        const double *varR_0, double phi_0, const double *piG, const double *piZ,
+                                        double likInitG, double likInitZ, bool normal_map, bool estS, bool estP, int maxiter,
+                                        int miniter = 10) {
+  const int U = h.U, Z = h.Z;
+  const double EPS = std::numeric_limits<double>::epsilon();
+  double n_prev = n_0, phi_prev = phi_0;
+  std::vector<double> s_prev(s_0, s_0 + Z), var_prev(var_0, var_0 + U), varR_prev(varR_0, varR_0 + U);
+  auto F = [&](double n, const double *s, const double *var, const double *varR, double phi) {
+    return likelihood_func_gauss(h, st, n, s, var, varR, phi, piG, piZ, likInitG, likInitZ, normal_map, estS, estP);
+  };
+  double obj_prev = F(n_prev, s_prev.data(), var_prev.data(), varR_prev.data(), phi_prev), obj = obj_prev;
+  bool converged = false;
+  int i = 1;
+  double n = n_prev, phi = phi_prev;
+  std::vector<double> s = s_prev, var = var_prev, varR = varR_prev;
+  while ((!converged && i < maxiter) || i <= miniter) {
+    ++i;
+    if (normal_map) {
+      double r;
+      auto fn = [&](double v) { return deriv_n_gauss(h, st, v, s_prev.data(), var_prev.data(), varR_prev.data(), phi_prev); };
+      n = uniroot(fn, EPS, 1 - EPS, &r) ? r : n_prev;
+    } else {
+      n = n_prev;
+    }
+    s = s_prev;
+    if (estS)
+      for (int z = 0; z < Z; ++z) {
+        double r;
+        auto fs = [&](double v) { return deriv_s_gauss(h, st, v, z, n, var_prev.data(), varR_prev.data(), phi_prev); };
+        s[z] = uniroot(fs, EPS, 1 - EPS, &r) ? r : s_prev[z];
+      }
+    std::vector<double> varn(U, 0.0);
+    std::vector<char> done(U, 0);
+    for (int k = 0; k < U; ++k) {
+      if (done[k]) continue;
+      std::vector<int> ind;
+      std::vector<double> v2;
+      for (int q = k; q < U; ++q)
+        if (h.ct[q] == h.ct[k]) { ind.push_back(q); v2.push_back(varR_prev[q]); done[q] = 1; }
+      double r;
+      auto fv = [&](double v) { return deriv_var_gauss(h, st, v, n, s.data(), v2.data(), phi_prev, ind.data(), (int)ind.size(), true); };
+      const bool ok = uniroot(fv, EPS, 5.0, &r);
+      for (int q : ind) varn[q] = ok ? r : var_prev[q];
+    }
+    var = varn;
+    for (int k = 0; k < U; ++k) {
+      double r;
+      const double v2 = var[k];
+      auto fv = [&](double v) { return deriv_var_gauss(h, st, v, n, s.data(), &v2, phi_prev, &k, 1, false); };
+      varR[k] = uniroot(fv, EPS, 5.0, &r) ? r : varR_prev[k];
+    }
+    if (estP) {
+      double r;
+      auto fp = [&](double v) { return deriv_phi_gauss(h, st, v, n, s.data(), var.data(), varR.data()); };
+      phi = uniroot(fp, EPS, 10.0, &r) ? r : phi_prev;
+    } else {
+      phi = phi_prev;
+    }
+    obj = F(n, s.data(), var.data(), varR.data(), phi);
+    n_prev = n; s_prev = s; var_prev = var; varR_prev = varR; phi_prev = phi;
+    if (!std::isnan(obj) && (std::fabs(obj - obj_prev) / std::fabs(obj)) <= 0.001) converged = true;
+    obj_prev = obj;
+  }
+  MStepOut o;
+  o.n = n; o.phi = phi; o.s = s; o.var = var; o.varR = varR; o.sweeps = i - 1; o.maxF = obj;
   return o;
 }
 

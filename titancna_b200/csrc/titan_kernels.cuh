@@ -202,6 +202,17 @@ __device__ __forceinline__ double emission_exact(const SnpRec &r, double lmu, do
   return __dadd_rn(__dadd_rn(pyR, pyC), 1e-300);
 }
 
+// Gaussian allele model: bivariateNormalpdflog (R/hmmClonal.R:550-559) in R's association order, single roundings;
+// the Viterbi wrapper adds no pseudoCounts to it (:444-447).  r.x = ref / tumDepth (host division).
+__device__ __forceinline__ double emission_exact_gauss(const SnpRec &r, double muR, double muC, double negc, double varR,
+                                                       double varC, double sq, double l0, double rho2) {
+  const double d1 = __dsub_rn(r.x, muR), d2 = __dsub_rn(r.lr, muC);
+  const double l1 = __ddiv_rn(__dmul_rn(d1, d1), varR);
+  const double l2 = __ddiv_rn(__dmul_rn(d2, d2), varC);
+  const double l3 = __ddiv_rn(__dmul_rn(__dmul_rn(rho2, d1), d2), sq);
+  return __dsub_rn(negc, __dmul_rn(l0, __dsub_rn(__dadd_rn(l1, l2), l3)));
+}
+
 // Thread layout: P = blockDim/K' threads per destination state (P a power of two <= 32, consecutive
 // lanes), each scanning a contiguous ascending slice of the sources.  Per step:
 //   phase A  thread i < K forms the four class values v[c][i] = delta[i] (+) logA_class_c(i)  -- 4K
@@ -332,7 +343,8 @@ __global__ void __launch_bounds__(256) viterbi_emission_kernel(const SnpRec *__r
     const long long t = q / K;
     const int j = (int)(q - t * K), g = j % U;
     const SnpRec r = snp[t];
-    py[q] = emission_exact(r, M.lmu[j], M.l1mu[j], M.muC[j], M.cN[g], M.tv[g]);
+    py[q] = M.gauss ? emission_exact_gauss(r, M.lmu[j], M.muC[j], M.cN[g], M.vR[g], M.tv[g], M.sq[g], M.l0, M.rho2)
+                    : emission_exact(r, M.lmu[j], M.l1mu[j], M.muC[j], M.cN[g], M.tv[g]);
   }
 }
 

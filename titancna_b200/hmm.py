@@ -63,6 +63,11 @@ class Solver:
         d.txnExpLen, d.txnZstrength = float(txnExpLen), float(txnZstrength)
         d.U, d.Z = self.U, self.Z
         zs, d.ZS = f64(genotypeParams["ZS"])
+        model = genotypeParams.get("alleleEmissionModel") or "binomial"        # R/hmmClonal.R:392-394
+        if model not in ("binomial", "Gaussian"):
+            raise ValueError('loadDefaultParameters: alleleEmissionModel must be either "binomial" or "Gaussian".')
+        self.gauss = model == "Gaussian"
+        d.alleleModel = 1 if self.gauss else 0
         h = C.c_void_p()
         check(L.titan_solver_create(C.byref(d), C.byref(h)))
         self._h = h
@@ -101,19 +106,31 @@ class Solver:
         check(lib().titan_solver_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
 
-    def _params(self, n, s, phi, var, piG, piZ, g, keep):
+    def _params(self, n, s, phi, var, piG, piZ, g, keep, varR=None, corRho=None):
         p = Params()
         p.n, p.phi, p.rn = float(n), float(phi), float(g["rn"])
-        for name, val in (("s", s), ("var", var), ("piG", piG), ("piZ", piZ), ("rt", g["rt"]), ("ct", g["ct"])):
+        cols = [("s", s), ("var", var), ("piG", piG), ("piZ", piZ), ("rt", g["rt"]), ("ct", g["ct"])]
+        if self.gauss:
+            cols.append(("varR", g["varR_0"] if varR is None else varR))
+            rho = g.get("corRho_0") if corRho is None else corRho
+            if rho is None:
+                raise ValueError("genotypeParams$corRho_0 is NULL: the Gaussian allele model needs "
+                                 "loadDefaultParameters(data=) (R/utils.R:79-83)")
+            p.corRho = float(rho)
+        for name, val in cols:
             arr, ptr = f64(np.atleast_1d(val))
+            if name in ("var", "varR", "rt", "ct", "piG") and arr.size < self.U:
+                raise ValueError(f"{name} has {arr.size} entries, the solver has {self.U} genotype states")
             keep.append(arr)
             setattr(p, name, ptr)
         return p
 
-    def estep(self, n, s, phi, var, piG, piZ, genotypeParams, posteriors=False):
-        """One E-step -> dict(loglik_chr, stats{a,b,c,d,e,g}[U,Z], rhoG0, rhoZ0, [rhoG, rhoZ], muR, muC)."""
+    def estep(self, n, s, phi, var, piG, piZ, genotypeParams, posteriors=False, varR=None, corRho=None):
+        """One E-step -> dict(loglik_chr, stats{a,b,c,d,e,g}[U,Z], rhoG0, rhoZ0, [rhoG, rhoZ], muR, muC).
+        Gaussian allele model: stats{a,f,c,h,e,g} (R/paramEstimation.R:30-32), `varR` / `corRho` default to
+        genotypeParams$varR_0 / corRho_0."""
         keep = []
-        p = self._params(n, s, phi, var, piG, piZ, genotypeParams, keep)
+        p = self._params(n, s, phi, var, piG, piZ, genotypeParams, keep, varR, corRho)
         U, Z, K, nChr, N = self.U, self.Z, self.K, self.nChrOut, self.N
         ll = np.zeros(nChr); st = np.zeros(6 * K); g0 = np.zeros(nChr * U); z0 = np.zeros(nChr * Z)
         muR = np.zeros(K); muC = np.zeros(K)
@@ -126,7 +143,8 @@ class Solver:
             o.rhoG, o.rhoZ = rG.ctypes.data_as(c_double_p), rZ.ctypes.data_as(c_double_p)
         check(lib().titan_estep(self._h, C.byref(p), C.byref(o)))
         out = {"loglik_chr": ll, "loglik": float(np.sum(ll)),
-               "stats": {nm: st[i * K:(i + 1) * K].reshape((U, Z), order="F") for i, nm in enumerate("abcdeg")},
+               "stats": {nm: st[i * K:(i + 1) * K].reshape((U, Z), order="F")
+                         for i, nm in enumerate("afcheg" if self.gauss else "abcdeg")},
                "stats_flat": st,
                "rhoG0": g0.reshape((U, nChr), order="F"), "rhoZ0": z0.reshape((Z, nChr), order="F"),
                "muR": muR.reshape((U, Z), order="F"), "muC": muC.reshape((U, Z), order="F")}
@@ -134,9 +152,9 @@ class Solver:
             out["rhoG"], out["rhoZ"] = rG.T, rZ.T          # U x N, Z x N like R
         return out
 
-    def viterbi(self, n, s, phi, var, piG, piZ, genotypeParams):
+    def viterbi(self, n, s, phi, var, piG, piZ, genotypeParams, varR=None, corRho=None):
         keep = []
-        p = self._params(n, s, phi, var, piG, piZ, genotypeParams, keep)
+        p = self._params(n, s, phi, var, piG, piZ, genotypeParams, keep, varR, corRho)
         path = np.zeros(self.N, dtype=np.int32)
         check(lib().titan_viterbi(self._h, C.byref(p), path.ctypes.data_as(C.POINTER(C.c_int32))))
         return path
@@ -156,6 +174,17 @@ def _hyper(params, keep):
     h.rn = float(g["rn"])
     h.n_0, h.alphaNHyper, h.betaNHyper = float(nP["n_0"]), float(nP["alphaNHyper"]), float(nP["betaNHyper"])
     h.phi_0, h.alphaPHyper, h.betaPHyper = float(pP["phi_0"]), float(pP["alphaPHyper"]), float(pP["betaPHyper"])
+    gauss = g.get("alleleEmissionModel", "binomial") == "Gaussian"
+    if gauss and any(g.get(k) is None for k in ("varR_0", "alphaRHyper", "betaRHyper", "corRho_0")):
+        raise ValueError("genotypeParams must contain varR_0, alphaRHyper, betaRHyper and corRho_0 for the Gaussian "
+                         "allele model. See loadDefaultParameters(data=).")
+    for name in ("varR_0", "alphaRHyper", "betaRHyper"):       # binomial model: varR_0 is only carried along (:212)
+        if g.get(name) is not None:
+            arr, ptr = f64(np.atleast_1d(g[name]))
+            keep.append(arr)
+            setattr(h, name, ptr)
+    if gauss:
+        h.corRho_0 = float(g["corRho_0"])
     return h
 
 
@@ -188,9 +217,6 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
     Extra keyword arguments (solver reuse, chunking knobs) have no R counterpart."""
     _check_params(params)
     g, pP, nP, sP = (params[k] for k in ("genotypeParams", "ploidyParams", "normalParams", "cellPrevParams"))
-    if g.get("alleleEmissionModel", "binomial") != "binomial":
-        raise TitanError(_lib.ERR_UNSUPPORTED, 'alleleEmissionModel="Gaussian" is not covered by the B200 path '
-                                               "(flagged 'not fully implemented' in the reference vignette)")
     if useOutlierState:
         raise TitanError(_lib.ERR_UNSUPPORTED, "useOutlierState=TRUE is not covered (no shipped driver enables it)")
     Z, U = len(sP["s_0"]), len(g["rt"])
@@ -208,7 +234,8 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
                    int(bool(estimatePloidy)), float(likChangeThreshold), 1, int(bool(verbose)))
         bufs = {"n": np.zeros(M), "phi": np.zeros(M), "loglik": np.zeros(M), "s": np.zeros((M, Z)),
                 "piZ": np.zeros((M, Z)), "var": np.zeros((M, U)), "piG": np.zeros((M, U)),
-                "muR": np.zeros((M, K)), "muC": np.zeros((M, K)), "rhoG": np.zeros((N, U)), "rhoZ": np.zeros((N, Z))}
+                "muR": np.zeros((M, K)), "muC": np.zeros((M, K)), "rhoG": np.zeros((N, U)), "rhoZ": np.zeros((N, Z)),
+                "varR": np.zeros((M, U))}
         sweeps = np.zeros(M, dtype=np.int32)
         out = EmOut()
         for k, a in bufs.items():
@@ -217,7 +244,7 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
         check(lib().titan_em_run(solver._h, C.byref(h), C.byref(o), C.byref(out)))
         i = out.iters
         res = {"n": bufs["n"][:i].copy(), "s": bufs["s"][:i].T.copy(), "var": bufs["var"][:i].T.copy(),
-               "varR": np.tile(np.asarray(g.get("varR_0", np.full(U, 1 / 20)), float)[:, None], (1, i)),
+               "varR": bufs["varR"][:i].T.copy(),
                "phi": bufs["phi"][:i].copy(), "piG": bufs["piG"][:i].T.copy(), "piZ": bufs["piZ"][:i].T.copy(),
                "muR": bufs["muR"][:i].reshape((i, Z, U)).transpose(2, 1, 0).copy(),
                "muC": bufs["muC"][:i].reshape((i, Z, U)).transpose(2, 1, 0).copy(),
@@ -258,9 +285,21 @@ def viterbiClonalCN(data, convergeParams, genotypeParams=None, solver=None):
         solver = Solver(data, genotypeParams, Z, float(np.ravel(cp["txnExpLen"])[0]),
                         float(np.ravel(cp["txnZstrength"])[0]))
     try:
+        varR = corRho = None
+        if solver.gauss:
+            # R/hmmClonal.R:439-447 hands computeBivariateNormalObslik `convergeParams$corRho_0`, an element the
+            # convergeParams list does not have (:344-367): NULL, so the correlation is re-derived from the data by
+            # getBivariateCovariance (:536-538,561-567) as covar[1,2] / sqrt(covar[1,1] * covar[2,2])
+            varR = np.asarray(cp["varR"], float)[:, i]
+            x1, x2 = np.asarray(data["ref"], float) / np.asarray(data["tumDepth"], float), np.asarray(data["logR"], float)
+            ok = ~(np.isnan(x1) | np.isnan(x2))
+            d1, d2 = x1[ok] - x1[ok].mean(), x2[ok] - x2[ok].mean()
+            nm1 = d1.size - 1
+            c11, c22, c12 = float(np.dot(d1, d1)) / nm1, float(np.dot(d2, d2)) / nm1, float(np.dot(d1, d2)) / nm1
+            corRho = c12 / np.sqrt(c11 * c22)
         return solver.viterbi(np.ravel(cp["n"])[i], s[:, i], np.ravel(cp["phi"])[i], var[:, i],
                               np.asarray(cp["piG"], float)[:, i - 1], np.asarray(cp["piZ"], float)[:, i - 1],
-                              genotypeParams)
+                              genotypeParams, varR=varR, corRho=corRho)
     finally:
         if own:
             solver.close()
