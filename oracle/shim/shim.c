@@ -164,6 +164,7 @@ typedef SEXP (*fn1)(SEXP);
 typedef SEXP (*fn2)(SEXP, SEXP);
 typedef SEXP (*fn8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*fn10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*fn12)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP shim_calln(void *f, int n, SEXP *a) {
   SEXP out = NULL;
   shim_msg[0] = 0;
@@ -176,6 +177,7 @@ SEXP shim_calln(void *f, int n, SEXP *a) {
       case 8: out = ((fn8)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
       case 9: out = ((fn9)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
       case 10: out = ((fn10)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
+      case 12: out = ((fn12)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]); break;
       default: snprintf(shim_msg, sizeof shim_msg, "shim_calln: arity %d not supported", n); break;
     }
   }
