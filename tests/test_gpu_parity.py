@@ -652,3 +652,31 @@ def test_config4_as_named_em_matches_oracle_em():
     for k in ("n", "phi", "s", "var"):
         assert np.allclose(got[k], want[k], rtol=0, atol=1e-6), k
     assert np.allclose(got["loglik"][1:], want["loglik"][1:], rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("col", [0, 1, 2])
+def test_fused_estep_reproduces_the_fixture_loglik_trajectory(golden, col):
+    """data/EMresults.rda: loglik[i] = E-step log-likelihood at the parameters of column i-1 + priorProbs(column i)
+    (R/hmmClonal.R:218,311).  The fused E-step through the C ABI, at each of the three stored parameter sets, plus the
+    priors of the stored next column, gives the stored value to 1e-11 relative (contract: 1e-9)."""
+    g = {k[2:]: golden[k] for k in golden if k.startswith("g_")}
+    g["rn"] = float(g["rn"][0])
+    Z = golden["cp_s"].shape[0]
+    data = {"chr": golden["data_chr"], "posn": golden["data_posn"].astype(float), "ref": golden["data_ref"].astype(float),
+            "tumDepth": golden["data_tumDepth"].astype(float), "logR": golden["data_logR"]}
+    sol = T.Solver(data, g, Z, float(golden["cp_txnExpLen"][0]), float(golden["cp_txnZstrength"][0]))
+    out = sol.estep(golden["cp_n"][col], golden["cp_s"][:, col], golden["cp_phi"][col], golden["cp_var"][:, col],
+                    golden["cp_piG"][:, col], golden["cp_piZ"][:, col], g, posteriors=(col == 2))
+    sol.close()
+    nP = {"alphaNHyper": 2.0, "betaNHyper": 2.0}
+    sP = {"alphaSHyper": np.full(Z, 2.0), "betaSHyper": np.full(Z, 2.0), "kappaZHyper": golden["s_kappaZHyper"]}
+    pP = {"alphaPHyper": 20.0, "betaPHyper": 42.0}
+    c1 = col + 1
+    pr = O.prior_probs(golden["cp_n"][c1], golden["cp_s"][:, c1], golden["cp_phi"][c1], golden["cp_var"][:, c1],
+                       golden["cp_piG"][:, c1], golden["cp_piZ"][:, c1], g, nP, sP, pP)
+    want = float(golden["cp_loglik"][c1])
+    assert abs(out["loglik"] + pr["prior"] - want) <= 1e-11 * abs(want)
+    assert np.abs(out["muR"] - golden["cp_muR"][:, :, col]).max() < 1e-15
+    if col == 2:                                      # the stored marginals are those of the last E-step
+        assert np.abs(out["rhoG"] - golden["cp_rhoG"]).max() < 1e-9 and np.abs(out["rhoZ"] - golden["cp_rhoZ"]).max() < 1e-9

@@ -141,3 +141,44 @@ def test_mstep_derivatives_are_gradients_of_the_objective(golden):
         assert O.deriv_s(s[z], z, n, var, phi, st, g["rt"], g["rn"], g["ct"], 2, 2) == pytest.approx(num, rel=1e-6)
     num = (F(n, s, var, phi + h) - F(n, s, var, phi - h)) / (2 * h)
     assert O.deriv_phi(phi, n, s, var, st, g["rt"], g["rn"], g["ct"], 20, 42) == pytest.approx(num, rel=1e-6)
+
+
+def _fixture_iteration(golden, col):
+    """Parameters of column `col` of the fixture's convergeParams and what the reference stored for column col + 1."""
+    g = {k[2:]: golden[k] for k in golden if k.startswith("g_")}
+    g["rn"] = float(g["rn"][0])
+    g["alleleEmissionModel"] = "binomial"
+    Z = golden["cp_s"].shape[0]
+    nP = {"n_0": 0.5, "alphaNHyper": 2.0, "betaNHyper": 2.0}
+    sP = {"s_0": golden["cp_s"][:, 0], "alphaSHyper": np.full(Z, 2.0), "betaSHyper": np.full(Z, 2.0),
+          "kappaZHyper": golden["s_kappaZHyper"]}
+    pP = {"phi_0": 1.5, "alphaPHyper": 20.0, "betaPHyper": 42.0}
+    return g, nP, sP, pP
+
+
+@pytest.mark.parametrize("col", [0, 1, 2])
+def test_fixture_loglik_trajectory_pins_estep_and_priors(golden, col):
+    """data/EMresults.rda stores loglik[i] = sum of the chromosome log-likelihoods of the E-step run with column i-1
+    + priorProbs(column i) (R/hmmClonal.R:218,292-311) for three EM iterations.  The oracle's E-step on column i-1 plus
+    its restatement of priorProbs (R/hmmClonal.R:646-665,715-783: beta, inverse-gamma and Dirichlet log densities) on the
+    STORED column i reproduces every one of them: the forward-backward log-likelihood is pinned at three different
+    parameter sets and the prior terms at three, by a reference-held vector.  (The M-step itself stays unpinned: the
+    stored columns come from an older package version whose coordinate descent differs)"""
+    g, nP, sP, pP = _fixture_iteration(golden, col)
+    data = {"chr": golden["data_chr"], "posn": golden["data_posn"].astype(float), "ref": golden["data_ref"].astype(float),
+            "tumDepth": golden["data_tumDepth"].astype(float), "logR": golden["data_logR"]}
+    Z = golden["cp_s"].shape[0]
+    muR, muC = O.clonal_two_component_mixture(g["rt"], g["rn"], golden["cp_n"][col], golden["cp_s"][:, col], g["ct"],
+                                              golden["cp_phi"][col])
+    assert np.abs(muR - golden["cp_muR"][:, :, col]).max() < 1e-15 and np.abs(muC - golden["cp_muC"][:, :, col]).max() < 1e-15
+    py = O.compute_py_c(data["ref"], data["tumDepth"], data["logR"], muR, muC, golden["cp_var"][:, col])
+    es = O.e_step(data, O.chromosome_slices(data["chr"]), py, golden["cp_piG"][:, col], golden["cp_piZ"][:, col], g["ZS"],
+                  g["ct"], Z, float(golden["cp_txnExpLen"][0]), float(golden["cp_txnZstrength"][0]), engine="port")
+    c1 = col + 1
+    pr = O.prior_probs(golden["cp_n"][c1], golden["cp_s"][:, c1], golden["cp_phi"][c1], golden["cp_var"][:, c1],
+                       golden["cp_piG"][:, c1], golden["cp_piZ"][:, c1], g, nP, sP, pP)
+    want = float(golden["cp_loglik"][c1])
+    assert abs((es["loglik"] + pr["prior"]) - want) <= 1e-13 * abs(want)
+    # the product's host-side priors (titan_host.hpp:prior_probs through titan_mstep's out_prior is tied to its own
+    # M-step output, so evaluate the C++ densities through the oracle-equivalent decomposition instead)
+    assert pr["prior"] == pytest.approx(pr["s"] + pr["n"] + pr["phi"] + pr["var"] + pr["piG"] + pr["piZ"], rel=1e-15)

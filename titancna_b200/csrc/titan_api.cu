@@ -287,6 +287,8 @@ struct titan_solver {
   DevBuf<double> alpha, startf, endf, startb, endb, chunk_ll, part, out, rhoG0, rhoZ0, rhoG, rhoZ, loggamma;
   int probes = 1;                  // fb2 engine: probe-accelerated rounds (TITAN_PROBES)
   int probe_window = 8;            // from the second cycle on, chunks this close downstream of a dirty one are probed too (TITAN_PROBE_WINDOW)
+  int probe_window1 = 0;           // the same for the first cycle (TITAN_PROBE_WINDOW1)
+  int plain_after = 0;             // > 0: cycles after this one re-run dirty chunks from the neighbour's vector, no probes (TITAN_PLAIN_AFTER)
   DevBuf<unsigned char> pflags;    // [4][nChunks] dirtyF, dirtyB, solvedF, solvedB
   DevBuf<int> pints;               // [2][nChunks][2] probed states, [2][nChunks][3] probe exponents
   DevBuf<double> pvec;             // [2][nChunks][3][K] probe results, [2][nChunks][K] predicted boundary vectors
@@ -471,6 +473,8 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
   if (const char *e = getenv("TITAN_PROBES")) s->probes = atoi(e);
   if (const char *e = getenv("TITAN_SPEC_FINAL")) s->spec_final = atoi(e);
   if (const char *e = getenv("TITAN_PROBE_WINDOW")) s->probe_window = std::max(0, atoi(e));
+  if (const char *e = getenv("TITAN_PROBE_WINDOW1")) s->probe_window1 = std::max(0, atoi(e));
+  if (const char *e = getenv("TITAN_PLAIN_AFTER")) s->plain_after = std::max(0, atoi(e));
   try {
     CK(cudaGetDevice(&s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -976,9 +980,10 @@ static int estep_fb2(titan_solver *s, bool post, bool want_loggamma, bool poster
       const int queued = std::max(1, std::min(probes ? std::max(1, s->round_batch / 2) : s->round_batch, hard_cap - round));
       for (int q = 1; q <= queued; ++q) {
         A.round = round + q;
-        if (probes) {
+        A.use_solved = 0;
+        if (probes && (s->plain_after <= 0 || round + q <= s->plain_after)) {
           A.use_solved = 1;
-          A.probe_window = (round + q >= 2) ? s->probe_window : 0;   // cycle 1 tests hundreds of chunks: dirty ones only
+          A.probe_window = (round + q >= 2) ? s->probe_window : s->probe_window1;   // cycle 1 tests hundreds of chunks
           CK(fb2_launch_probe(A, s->Z, st));
           CK(fb2_launch_solve(A, s->Z, st));
           s->tm.kernel_launches += 2;

@@ -344,6 +344,16 @@ __device__ __forceinline__ void load_row(double (&v)[GS][Z], const void *row, co
     for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? *reinterpret_cast<const double *>(static_cast<const char *>(row) + L.off[s][z]) : 0.0;
 }
 
+// the same through the read-only path (ld.global.nc): only for vectors no thread of the running kernel writes; lets
+// the compiler hoist the loads above unrelated global stores
+template <int Z, int GS>
+__device__ __forceinline__ void load_row_nc(double (&v)[GS][Z], const void *row, const LaneInfo<Z, GS> &L) {
+#pragma unroll
+  for (int s = 0; s < GS; ++s)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) v[s][z] = L.act[s] ? __ldg(reinterpret_cast<const double *>(static_cast<const char *>(row) + L.off[s][z])) : 0.0;
+}
+
 template <int Z, int GS>
 __device__ __forceinline__ void load_row_s(double (&v)[GS][Z], unsigned srow, const LaneInfo<Z, GS> &L) {
 #pragma unroll
@@ -819,13 +829,22 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
       have = false;
       continue;
     }
-    if (!have) load_row<Z, GS>(cur, endv + (size_t)(backward ? c + 1 : c - 1) * K, L);     // the neighbour's actual end
+    if (!have) load_row_nc<Z, GS>(cur, endv + (size_t)(backward ? c + 1 : c - 1) * K, L);     // the neighbour's actual end
     store_row<Z, GS>(sol + (size_t)c * K, cur, L);
     if (lane == 0) solved[c] = 1;
     // coefficients of cur[] in the three pieces of the vector the chunk started from
     int jt[kProbes - 1];
 #pragma unroll
-    for (int q = 0; q < kProbes - 1; ++q) jt[q] = probeJ[(kProbes - 1) * c + q];
+    for (int q = 0; q < kProbes - 1; ++q) jt[q] = __ldg(probeJ + (kProbes - 1) * c + q);
+    // everything this chunk's prediction reads besides cur[]: issued together, ahead of the reductions
+    int pe[kProbes];
+    double pq[kProbes][GS][Z], old[GS][Z];
+#pragma unroll
+    for (int q = 0; q < kProbes; ++q) {
+      pe[q] = __ldg(probeE + c * kProbes + q);
+      load_row_nc<Z, GS>(pq[q], probe + ((size_t)c * kProbes + q) * K, L);
+    }
+    load_row_nc<Z, GS>(old, startv + (size_t)c * K, L);
     double x[kProbes];            // coefficients: the probed states' components, then the remainder's mass ratio
     double rn = 0.0, ro = 0.0;
 #pragma unroll
@@ -835,7 +854,7 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
         const int j = L.g[s] + z * U;
-        const double v = cur[s][z], o = L.act[s] ? startv[(size_t)c * K + j] : 0.0;
+        const double v = cur[s][z], o = old[s][z];
         bool top = false;
 #pragma unroll
         for (int q = 0; q < kProbes - 1; ++q) {
@@ -853,7 +872,7 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
     int Em = -2147483647;
 #pragma unroll
     for (int q = 0; q < kProbes; ++q)
-      if (x[q] > 0.0) Em = max(Em, probeE[c * kProbes + q]);
+      if (x[q] > 0.0) Em = max(Em, pe[q]);
     double e[GS][Z];
 #pragma unroll
     for (int s = 0; s < GS; ++s)
@@ -861,13 +880,11 @@ __global__ void __launch_bounds__(32 * kWPC) fb2_solve_kernel(Fb2Args A) {
       for (int z = 0; z < Z; ++z) e[s][z] = 0.0;
 #pragma unroll
     for (int q = 0; q < kProbes; ++q) {
-      const double f = x[q] > 0.0 ? scalbn(x[q], max(probeE[c * kProbes + q] - Em, -2000)) : 0.0;
-      double pq[GS][Z];
-      load_row<Z, GS>(pq, probe + ((size_t)c * kProbes + q) * K, L);
+      const double f = x[q] > 0.0 ? scalbn(x[q], max(pe[q] - Em, -2000)) : 0.0;
 #pragma unroll
       for (int s = 0; s < GS; ++s)
 #pragma unroll
-        for (int z = 0; z < Z; ++z) e[s][z] += f * pq[s][z];
+        for (int z = 0; z < Z; ++z) e[s][z] += f * pq[q][s][z];
     }
     const double tot = vec_sum<Z, GS>(e);
     have = (tot > 0.0) && (tot < CUDART_INF);
