@@ -427,7 +427,9 @@ def main():
             t1 = time.perf_counter()
             so = T.Solver(d, pp["genotypeParams"], len(pp["cellPrevParams"]["s_0"]), kw["txnExpLen"], kw["txnZstrength"], device=local)
             try:
-                c = T.runEMclonalCN(d, pp, verbose=False, solver=so, **kw)
+                # the sweep keeps the parameter sets, the paths and the selection indices; the N-sized posterior
+                # marginals stay on the device (T.run_sweep's own run_one does the same)
+                c = T.runEMclonalCN(d, pp, verbose=False, solver=so, posteriors=False, **kw)
                 pth = T.viterbiClonalCN(d, c, solver=so)
             finally:
                 so.close()

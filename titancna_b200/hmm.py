@@ -212,9 +212,11 @@ def _check_params(params):
 def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, maxiterUpdate=1500,
                   pseudoCounts=1e-300, normalEstimateMethod="map", estimateS=True, estimatePloidy=True,
                   useOutlierState=False, likChangeThreshold=0.001, verbose=True, solver=None,
-                  chunk_len=None, warmup_len=None, rel_tol=None, return_timing=False):
+                  chunk_len=None, warmup_len=None, rel_tol=None, return_timing=False, posteriors=True):
     """R/hmmClonal.R:8-368.  Returns the convergeParams list as a dict (iteration axis last).
-    Extra keyword arguments (solver reuse, chunking knobs) have no R counterpart."""
+    Extra keyword arguments (solver reuse, chunking knobs) have no R counterpart.  `posteriors=False` leaves
+    rhoG / rhoZ (8 (U + Z) N bytes, the only N-sized output) on the device and returns None for them: nothing in
+    the sweep -> outputTitanResults(posteriorProbs=FALSE) -> selectSolution chain reads them."""
     _check_params(params)
     g, pP, nP, sP = (params[k] for k in ("genotypeParams", "ploidyParams", "normalParams", "cellPrevParams"))
     if useOutlierState:
@@ -231,11 +233,12 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
         keep = []
         h = _hyper(params, keep)
         o = EmOpts(int(maxiter), int(maxiterUpdate), int(normalEstimateMethod == "map"), int(bool(estimateS)),
-                   int(bool(estimatePloidy)), float(likChangeThreshold), 1, int(bool(verbose)))
+                   int(bool(estimatePloidy)), float(likChangeThreshold), int(bool(posteriors)), int(bool(verbose)))
         bufs = {"n": np.zeros(M), "phi": np.zeros(M), "loglik": np.zeros(M), "s": np.zeros((M, Z)),
                 "piZ": np.zeros((M, Z)), "var": np.zeros((M, U)), "piG": np.zeros((M, U)),
-                "muR": np.zeros((M, K)), "muC": np.zeros((M, K)), "rhoG": np.zeros((N, U)), "rhoZ": np.zeros((N, Z)),
-                "varR": np.zeros((M, U))}
+                "muR": np.zeros((M, K)), "muC": np.zeros((M, K)), "varR": np.zeros((M, U))}
+        if posteriors:
+            bufs["rhoG"], bufs["rhoZ"] = np.zeros((N, U)), np.zeros((N, Z))
         sweeps = np.zeros(M, dtype=np.int32)
         out = EmOut()
         for k, a in bufs.items():
@@ -248,7 +251,8 @@ def runEMclonalCN(data, params, txnExpLen=1e15, txnZstrength=5e5, maxiter=15, ma
                "phi": bufs["phi"][:i].copy(), "piG": bufs["piG"][:i].T.copy(), "piZ": bufs["piZ"][:i].T.copy(),
                "muR": bufs["muR"][:i].reshape((i, Z, U)).transpose(2, 1, 0).copy(),
                "muC": bufs["muC"][:i].reshape((i, Z, U)).transpose(2, 1, 0).copy(),
-               "loglik": bufs["loglik"][:i].copy(), "rhoG": bufs["rhoG"].T, "rhoZ": bufs["rhoZ"].T,
+               "loglik": bufs["loglik"][:i].copy(), "rhoG": bufs["rhoG"].T if posteriors else None,
+               "rhoZ": bufs["rhoZ"].T if posteriors else None,
                "txnExpLen": txnExpLen, "txnZstrength": txnZstrength, "useOutlierState": useOutlierState,
                "genotypeParams": g, "ploidyParams": pP, "normalParams": nP, "cellPrevParams": sP,
                "symmetric": g.get("symmetric", True), "cd_sweeps": sweeps[:i].copy()}

@@ -219,6 +219,7 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
             sol = Solver(d, p["genotypeParams"], len(p["cellPrevParams"]["s_0"]), kw.get("txnExpLen", 1e15),
                          kw.get("txnZstrength", 5e5), device=device)
             try:
+                kw.setdefault("posteriors", False)      # nothing below reads the N-sized marginals (posteriorProbs = FALSE)
                 cp = runEMclonalCN(d, p, verbose=False, solver=sol, **kw)
                 path = viterbiClonalCN(d, cp, solver=sol)
             finally:
