@@ -237,8 +237,11 @@ typedef struct titan_timing {
 int titan_solver_timing(const titan_solver *s, titan_timing *t);
 
 /* Device buffers of destroyed solvers stay cached in the CUDA memory pool of the current device (a sweep
- * creates one solver per solution; cudaMalloc/cudaFree of such blocks cost more than an E-step).  This
- * returns the cached memory to the driver.  No counterpart in the reference (R frees through its GC). */
+ * creates one solver per solution; cudaMalloc/cudaFree of such blocks cost more than an E-step), and the
+ * parameter-independent tables of the last few (positions, transition settings, state layout) combinations --
+ * transition coefficients (128 B per SNP) and the decode's log-transition tables (32 K bytes per distinct gap) --
+ * stay resident so that the solutions of a sweep share them.  This drops those tables (live solvers keep theirs)
+ * and returns the cached memory to the driver.  No counterpart in the reference (R frees through its GC). */
 int titan_release_cached_memory(void);
 
 /* ------------------------------------------------------------------------------------------

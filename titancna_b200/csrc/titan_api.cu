@@ -305,6 +305,53 @@ static VitCache &vit_cache() {
   return *c;
 }
 
+// The structured transition coefficients of every SNP (128 bytes each, derived on the device from the host-exact
+// rhoG / rhoZ): parameter-independent like the decode tables and shared the same way.
+struct TxnTable {
+  int device = 0;
+  DevBuf<TxnRec> rec;              // [N + 2 kFbPadRows]
+  ~TxnTable() {
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+      cudaSetDevice(device);
+      rec.release();
+      cudaSetDevice(cur);
+    }
+  }
+};
+struct TxnKey {
+  GapKey gk;
+  int K = 0, U = 0, Z = 0, h = 0, device = 0;
+  bool operator==(const TxnKey &o) const {
+    return gk == o.gk && K == o.K && U == o.U && Z == o.Z && h == o.h && device == o.device;
+  }
+};
+struct TxnCache {
+  std::mutex mu;
+  std::vector<std::pair<TxnKey, std::shared_ptr<const TxnTable>>> recent;      // newest last, at most 6
+  std::shared_ptr<const TxnTable> find(const TxnKey &k) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : recent)
+      if (e.first == k) return e.second;
+    return nullptr;
+  }
+  void put(const TxnKey &k, std::shared_ptr<const TxnTable> v) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : recent)
+      if (e.first == k) { e.second = std::move(v); return; }
+    if (recent.size() >= 6) recent.erase(recent.begin());
+    recent.emplace_back(k, std::move(v));
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lock(mu);
+    recent.clear();
+  }
+};
+static TxnCache &txn_cache() {
+  static TxnCache *c = new TxnCache();
+  return *c;
+}
+
 struct titan_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -330,7 +377,7 @@ struct titan_solver {
 
   // device data
   DevBuf<SnpRec> snp;
-  DevBuf<TxnRec> txn;
+  std::shared_ptr<const TxnTable> txn;     // shared between solvers of the same positions and state layout (TxnCache)
   DevBuf<double> py;               // legacy mode only
   DevBuf<Chunk> chunks;
   std::vector<Chunk> chunks_h;
@@ -347,7 +394,7 @@ struct titan_solver {
   DevBuf<double> Bm, extf, extb;   // fb2 engine: scaled emissions [N][Kp]; one-step-extended boundary vectors [2][nChunks][K]
   // per-SNP arrays carry kFbPadRows rows of slack on both sides (TMA copies whole tiles)
   SnpRec *snp_p() const { return snp.p + kFbPadRows; }
-  TxnRec *txn_p() const { return txn.p + kFbPadRows; }
+  const TxnRec *txn_p() const { return txn->rec.p + kFbPadRows; }
   double *alpha_p() const { return alpha.p + (size_t)kFbPadRows * Kp; }
   double *Bm_p() const { return Bm.p + (size_t)kFbPadRows * Kp; }
   DevBuf<int> chr_chunk0;          // [nChr+1]
@@ -670,22 +717,30 @@ static int solver_create_impl(const SolverInit &in, titan_solver **out) {
       gap_cache().put(gkey, s->gaps);
     }
     trace.mark("distinct gaps (host exp)");
-    {
+    TxnKey tkey;
+    tkey.gk = gkey; tkey.K = K; tkey.U = s->U; tkey.Z = s->Z; tkey.h = s->h; tkey.device = s->device;
+    s->txn = txn_cache().find(tkey);
+    if (!s->txn) {
       DevBuf<double> dG, dZ;
       dG.alloc(N); dZ.alloc(N);
       trace.mark("  rho alloc");
       CK(cudaMemcpy(dG.p, s->gaps->rhoG_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(dZ.p, s->gaps->rhoZ_h.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
       trace.mark("  rho memcpy");
-      s->txn.alloc(N + 2 * kFbPadRows);
-      CK(cudaMemsetAsync(s->txn.p, 0, sizeof(TxnRec) * (N + 2 * kFbPadRows), s->stream));
+      std::shared_ptr<TxnTable> tt = std::make_shared<TxnTable>();
+      tt->device = s->device;
+      tt->rec.alloc(N + 2 * kFbPadRows);
+      CK(cudaMemsetAsync(tt->rec.p, 0, sizeof(TxnRec) * (N + 2 * kFbPadRows), s->stream));
       trace.mark("  txn alloc");
-      txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h, s->txn_p());
+      txn_coeff_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(dG.p, dZ.p, (int)N, K, s->U, s->Z, s->h,
+                                                                           tt->rec.p + kFbPadRows);
       CK(cudaGetLastError());
       trace.mark("  txn launch");
       CK(cudaStreamSynchronize(s->stream));
       trace.mark("  txn sync");
       s->tm.kernel_launches++;
+      s->txn = tt;
+      txn_cache().put(tkey, s->txn);
     }
     trace.mark("  rho free");
     if (s->legacy_py) {
@@ -813,7 +868,8 @@ extern "C" int titan_release_cached_memory(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
-  vit_cache().clear();                                // shared decode tables no live solver holds go back to the pool first
+  vit_cache().clear();                                // shared tables no live solver holds go back to the pool first
+  txn_cache().clear();
   cudaMemPool_t pool = titan_pool(dev);
   if (pool) {
     cudaDeviceSynchronize();
