@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--no-em", action="store_true", help="skip the whole-solution record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 15-solution sweep record")
     ap.add_argument("--no-sharded", action="store_true", help="skip the chromosome-sharded configs[3] record")
-    ap.add_argument("--sweep-concurrent", type=int, default=1, help="solutions in flight per GPU in the sweep record")
+    ap.add_argument("--sweep-concurrent", type=int, default=4, help="solutions in flight per GPU in the sweep record")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: CPU seconds for all its steps")
     return ap.parse_args()
 
