@@ -39,6 +39,9 @@ const char *titan_version(void);
 int titan_device_count(int *count);
 /* select the CUDA device used by the calling thread's subsequent calls (one process per GPU) */
 int titan_set_device(int device);
+/* the calling thread's current CUDA device (worker threads of a host program start on device 0, not on their
+ * creator's device: a driver that fans solutions out to threads reads it here and passes it on) */
+int titan_get_device(int *device);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Legacy-compatible entry points: one chromosome per call, materialised log-emissions in,

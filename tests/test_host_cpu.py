@@ -243,3 +243,14 @@ def test_interleaved_viterbi_table_builder_is_bit_identical(tmp_path):
                     "-o", str(exe), os.path.join(ROOT, "tests", "host_tables_check.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "mismatching tables: 0" in out.stdout, out.stdout + out.stderr
+
+
+def test_current_device_query_fails_loudly_without_a_device():
+    """titan_get_device is what run_sweep reads before it fans solutions out to worker threads (which start on CUDA
+    device 0, not on their creator's device)."""
+    if T.device_count() > 0:
+        assert 0 <= _lib.current_device() < T.device_count()
+        return
+    with pytest.raises(T.TitanError) as ei:
+        _lib.current_device()
+    assert ei.value.code == _lib.ERR_NO_DEVICE

@@ -84,7 +84,7 @@ class Timing(C.Structure):
 
 
 EXPORTS = [
-    "titan_last_error", "titan_version", "titan_device_count", "titan_set_device",
+    "titan_last_error", "titan_version", "titan_device_count", "titan_set_device", "titan_get_device",
     "titan_fwd_back_clonalCN", "titan_viterbi_clonalCN", "titan_get_position_overlap",
     "titan_solver_create", "titan_solver_destroy", "titan_solver_configure", "titan_solver_set_stream",
     "titan_estep", "titan_viterbi", "titan_em_run", "titan_mstep", "titan_mstep_gaussian", "titan_solver_timing",
@@ -108,6 +108,7 @@ def lib():
     L.titan_version.restype = C.c_char_p
     L.titan_device_count.argtypes = [c_int_p]
     L.titan_set_device.argtypes = [C.c_int]
+    L.titan_get_device.argtypes = [c_int_p]
     legacy = [c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, C.c_int,
               c_double_p, C.c_double, C.c_double, C.c_int]
     L.titan_fwd_back_clonalCN.argtypes = legacy + [c_double_p, c_double_p]
@@ -160,6 +161,13 @@ def device_count() -> int:
     n = C.c_int(0)
     rc = lib().titan_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def current_device() -> int:
+    """CUDA device of the calling thread (titan_get_device)."""
+    d = C.c_int(0)
+    check(lib().titan_get_device(C.byref(d)))
+    return d.value
 
 
 def measure_fp64_peak():

@@ -75,6 +75,16 @@ extern "C" int titan_device_count(int *count) {
   return n > 0 ? TITAN_OK : fail(TITAN_ERR_NO_DEVICE, "no CUDA device present (this library has no CPU fallback)");
 }
 
+extern "C" int titan_get_device(int *device) {
+  if (!device) return fail(TITAN_ERR_ARG, "titan_get_device: device is NULL");
+  cudaError_t e = cudaGetDevice(device);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TITAN_ERR_NO_DEVICE, "no usable CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  }
+  return TITAN_OK;
+}
+
 extern "C" int titan_set_device(int device) {
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(TITAN_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));

@@ -205,6 +205,9 @@ def run_sweep(data, rank, world, ploidies=(2, 3, 4), clusters=(1, 2, 3, 4, 5), m
     grid, costs = solution_grid(ploidies, clusters)
     where, load = lpt_assign(costs, world)
     mine = [grid[i] for i in range(len(grid)) if where[i] == rank]
+    if device is None and run_one is None and concurrent > 1 and len(mine) > 1:
+        # worker threads start on CUDA device 0, not on the caller's: pin the solvers to the device this rank is on
+        device = _lib.current_device()
     if make_params is None:
         moments = dataMoments(data)          # the data-dependent defaults once, not once per solution
 
