@@ -61,6 +61,24 @@ def test_model_parameter_file_fields():
     assert S._rnum(1e-5, 4) == "1e-05" and S._rnum(float("nan"), 4) == "NA" and S._rnum(123456.789, 4) == "123500"
 
 
+def test_model_parameter_file_of_the_gaussian_allele_model():
+    """R/utils.R:1006,1018-1023: the means line names the allele model and the allelic variances get their own line
+    between the means and the logR variances."""
+    cp, tab, _ = _table(2, 7)
+    U = np.asarray(cp["var"]).shape[0]
+    cp = dict(cp)
+    cp["genotypeParams"] = dict(cp.get("genotypeParams") or {}, alleleEmissionModel="Gaussian")
+    cp["varR"] = np.tile(np.linspace(0.011, 0.019, U)[:, None], (1, np.asarray(cp["var"]).shape[1]))
+    lines = S.outputModelParameters(cp, tab)["lines"]
+    heads = [ln.split("\t")[0] for ln in lines]
+    assert heads[3] == "AllelicRatio Gaussian means for clonal cluster Z=1:"
+    k = heads.index("AllelicRatio Gaussian variance:")
+    assert heads[k + 1] == "logRatio Gaussian variance:" and heads[k - 1].startswith("logRatio Gaussian means for clonal cluster Z=2")
+    assert lines[k].split("\t")[1].split(" ")[0] == "0.011" and len(lines[k].split("\t")[1].split(" ")) == U
+    binom = S.outputModelParameters(dict(cp, genotypeParams={"alleleEmissionModel": "binomial"}), tab)["lines"]
+    assert "AllelicRatio Gaussian variance:" not in [ln.split("\t")[0] for ln in binom] and len(binom) == len(lines) - 1
+
+
 def _records(ll2, ll3, ll4, sdbw):
     out = []
     for p, lls in ((2, ll2), (3, ll3), (4, ll4)):
